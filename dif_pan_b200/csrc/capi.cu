@@ -1,0 +1,243 @@
+// extern "C" surface of libddif_b200.so: immediate launches, the recorded op list ("plan") that replays one
+// UNet forward per call, CUDA-graph capture of a plan, and per-op event profiling.  See include/ddif_b200.h.
+#include <vector>
+
+#include "common.cuh"
+#include "ddif_internal.h"
+
+namespace ddif {
+
+union OpParams {
+  ddif_gemm_t gemm;
+  ddif_in_convert_t in_convert;
+  ddif_time_embed_t time_embed;
+  ddif_gn_apply_t gn_apply;
+  ddif_softmax_h_t softmax_h;
+  ddif_attn_t attn;
+  ddif_upsample2x_t upsample2x;
+  ddif_conv_direct_t conv_direct;
+  ddif_stats_t stats;
+  ddif_memset_t memset_;
+  ddif_resize_t resize;
+  ddif_fwm_context_t fwm_context;
+  ddif_fwm_weff_t fwm_weff;
+  ddif_ddpm_step_t ddpm;
+  ddif_ddim_step_t ddim;
+  ddif_dpmpp_step_t dpmpp;
+  ddif_q_sample_t q_sample;
+  ddif_haar_t haar;
+  ddif_cond_assemble_t cond_assemble;
+  ddif_randn_t randn;
+  ddif_axpby_clip_t axpby_clip;
+};
+
+static size_t params_size(int kind) {
+  switch (kind) {
+    case DDIF_OP_GEMM: return sizeof(ddif_gemm_t);
+    case DDIF_OP_IN_CONVERT: return sizeof(ddif_in_convert_t);
+    case DDIF_OP_TIME_EMBED: return sizeof(ddif_time_embed_t);
+    case DDIF_OP_GN_APPLY: return sizeof(ddif_gn_apply_t);
+    case DDIF_OP_SOFTMAX_H: return sizeof(ddif_softmax_h_t);
+    case DDIF_OP_ATTN: return sizeof(ddif_attn_t);
+    case DDIF_OP_UPSAMPLE2X: return sizeof(ddif_upsample2x_t);
+    case DDIF_OP_CONV_DIRECT: return sizeof(ddif_conv_direct_t);
+    case DDIF_OP_STATS: return sizeof(ddif_stats_t);
+    case DDIF_OP_MEMSET: return sizeof(ddif_memset_t);
+    case DDIF_OP_RESIZE: return sizeof(ddif_resize_t);
+    case DDIF_OP_FWM_CONTEXT: return sizeof(ddif_fwm_context_t);
+    case DDIF_OP_FWM_WEFF: return sizeof(ddif_fwm_weff_t);
+    case DDIF_OP_DDPM_STEP: return sizeof(ddif_ddpm_step_t);
+    case DDIF_OP_DDIM_STEP: return sizeof(ddif_ddim_step_t);
+    case DDIF_OP_DPMPP_STEP: return sizeof(ddif_dpmpp_step_t);
+    case DDIF_OP_Q_SAMPLE: return sizeof(ddif_q_sample_t);
+    case DDIF_OP_HAAR_DWT2:
+    case DDIF_OP_HAAR_IDWT2: return sizeof(ddif_haar_t);
+    case DDIF_OP_COND_ASSEMBLE: return sizeof(ddif_cond_assemble_t);
+    case DDIF_OP_RANDN: return sizeof(ddif_randn_t);
+    case DDIF_OP_AXPBY_CLIP: return sizeof(ddif_axpby_clip_t);
+    default: return 0;
+  }
+}
+
+struct Op {
+  int kind;
+  OpParams p;
+  GemmLaunch* gemm;  // owned, only for DDIF_OP_GEMM
+};
+
+static int dispatch(const Op& op, cudaStream_t s) {
+  switch (op.kind) {
+    case DDIF_OP_GEMM: return gemm_launch(*op.gemm, s);
+    case DDIF_OP_IN_CONVERT: return launch_in_convert(op.p.in_convert, s);
+    case DDIF_OP_TIME_EMBED: return launch_time_embed(op.p.time_embed, s);
+    case DDIF_OP_GN_APPLY: return launch_gn_apply(op.p.gn_apply, s);
+    case DDIF_OP_SOFTMAX_H: return launch_softmax_h(op.p.softmax_h, s);
+    case DDIF_OP_ATTN: return launch_attn(op.p.attn, s);
+    case DDIF_OP_UPSAMPLE2X: return launch_upsample2x(op.p.upsample2x, s);
+    case DDIF_OP_CONV_DIRECT: return launch_conv_direct(op.p.conv_direct, s);
+    case DDIF_OP_STATS: return launch_stats(op.p.stats, s);
+    case DDIF_OP_MEMSET: {
+      cudaError_t e = cudaMemsetAsync(op.p.memset_.ptr, 0, (size_t)op.p.memset_.bytes, s);
+      return e == cudaSuccess ? DDIF_OK : (int)e;
+    }
+    case DDIF_OP_RESIZE: return launch_resize(op.p.resize, s);
+    case DDIF_OP_FWM_CONTEXT: return launch_fwm_context(op.p.fwm_context, s);
+    case DDIF_OP_FWM_WEFF: return launch_fwm_weff(op.p.fwm_weff, s);
+    case DDIF_OP_DDPM_STEP: return launch_ddpm_step(op.p.ddpm, s);
+    case DDIF_OP_DDIM_STEP: return launch_ddim_step(op.p.ddim, s);
+    case DDIF_OP_DPMPP_STEP: return launch_dpmpp_step(op.p.dpmpp, s);
+    case DDIF_OP_Q_SAMPLE: return launch_q_sample(op.p.q_sample, s);
+    case DDIF_OP_HAAR_DWT2: return launch_haar_dwt2(op.p.haar, s);
+    case DDIF_OP_HAAR_IDWT2: return launch_haar_idwt2(op.p.haar, s);
+    case DDIF_OP_COND_ASSEMBLE: return launch_cond_assemble(op.p.cond_assemble, s);
+    case DDIF_OP_RANDN: return launch_randn(op.p.randn, s);
+    case DDIF_OP_AXPBY_CLIP: return launch_axpby_clip(op.p.axpby_clip, s);
+    default: return DDIF_ERR_ARG;
+  }
+}
+
+static int make_op(int kind, const void* params, Op& op) {
+  const size_t sz = params_size(kind);
+  if (!sz || !params) return DDIF_ERR_ARG;
+  op.kind = kind;
+  op.gemm = nullptr;
+  memset(&op.p, 0, sizeof(op.p));
+  memcpy(&op.p, params, sz);
+  if (kind == DDIF_OP_GEMM) {
+    op.gemm = new GemmLaunch();
+    int rc = gemm_prepare(op.p.gemm, *op.gemm);
+    if (rc != DDIF_OK) {
+      delete op.gemm;
+      op.gemm = nullptr;
+      return rc;
+    }
+  }
+  return DDIF_OK;
+}
+
+}  // namespace ddif
+
+struct ddif_plan {
+  std::vector<ddif::Op> ops;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};
+
+extern "C" {
+
+int ddif_version(void) { return 100; }
+
+const char* ddif_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  switch (code) {
+    case DDIF_ERR_ARG: return "ddif: bad argument";
+    case DDIF_ERR_SHAPE: return "ddif: unsupported shape / alignment";
+    case DDIF_ERR_DRIVER: return "ddif: CUDA driver call failed (cuTensorMapEncodeTiled unavailable or rejected the map)";
+    case DDIF_ERR_STATE: return "ddif: bad plan state";
+    default: return "ddif: unknown error";
+  }
+}
+
+int ddif_launch(int kind, const void* params, ddif_stream_t stream) {
+  ddif::Op op;
+  int rc = ddif::make_op(kind, params, op);
+  if (rc != DDIF_OK) return rc;
+  rc = ddif::dispatch(op, (cudaStream_t)stream);
+  delete op.gemm;
+  return rc;
+}
+
+ddif_plan_t* ddif_plan_create(void) { return new ddif_plan(); }
+
+void ddif_plan_destroy(ddif_plan_t* plan) {
+  if (!plan) return;
+  if (plan->exec) cudaGraphExecDestroy(plan->exec);
+  if (plan->graph) cudaGraphDestroy(plan->graph);
+  for (auto& op : plan->ops) delete op.gemm;
+  delete plan;
+}
+
+int ddif_plan_add(ddif_plan_t* plan, int kind, const void* params) {
+  if (!plan) return DDIF_ERR_ARG;
+  if (plan->exec) return DDIF_ERR_STATE;
+  ddif::Op op;
+  int rc = ddif::make_op(kind, params, op);
+  if (rc != DDIF_OK) return rc;
+  plan->ops.push_back(op);
+  return (int)plan->ops.size() - 1;
+}
+
+int ddif_plan_size(const ddif_plan_t* plan) { return plan ? (int)plan->ops.size() : DDIF_ERR_ARG; }
+int ddif_plan_launches(const ddif_plan_t* plan) { return plan ? (int)plan->ops.size() : DDIF_ERR_ARG; }
+
+int ddif_plan_run(ddif_plan_t* plan, int first, int last, ddif_stream_t stream) {
+  if (!plan) return DDIF_ERR_ARG;
+  const int n = (int)plan->ops.size();
+  if (last < 0 || last > n) last = n;
+  if (first < 0) first = 0;
+  for (int i = first; i < last; ++i) {
+    int rc = ddif::dispatch(plan->ops[i], (cudaStream_t)stream);
+    if (rc != DDIF_OK) return rc;
+  }
+  return DDIF_OK;
+}
+
+int ddif_plan_graph_build(ddif_plan_t* plan, ddif_stream_t stream) {
+  if (!plan) return DDIF_ERR_ARG;
+  if (plan->exec) return DDIF_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  DDIF_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = ddif_plan_run(plan, 0, -1, stream);
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(s, &g);
+  if (rc != DDIF_OK) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  if (e != cudaSuccess) return (int)e;
+  plan->graph = g;
+  DDIF_CUDA_CHECK(cudaGraphInstantiate(&plan->exec, g, 0));
+  return DDIF_OK;
+}
+
+int ddif_plan_graph_launch(ddif_plan_t* plan, ddif_stream_t stream) {
+  if (!plan || !plan->exec) return DDIF_ERR_STATE;
+  DDIF_CUDA_CHECK(cudaGraphLaunch(plan->exec, (cudaStream_t)stream));
+  return DDIF_OK;
+}
+
+int ddif_plan_profile(ddif_plan_t* plan, ddif_stream_t stream, float* ms, int* kinds, int capacity) {
+  if (!plan || !ms || !kinds) return DDIF_ERR_ARG;
+  const int n = (int)plan->ops.size();
+  if (capacity < n) return DDIF_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) DDIF_CUDA_CHECK(cudaEventCreate(&e));
+  DDIF_CUDA_CHECK(cudaEventRecord(ev[0], s));
+  int rc = DDIF_OK;
+  for (int i = 0; i < n && rc == DDIF_OK; ++i) {
+    rc = ddif::dispatch(plan->ops[i], s);
+    cudaEventRecord(ev[i + 1], s);
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (rc == DDIF_OK && e != cudaSuccess) rc = (int)e;
+  if (rc == DDIF_OK)
+    for (int i = 0; i < n; ++i) {
+      cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+      kinds[i] = plan->ops[i].kind;
+    }
+  for (auto& x : ev) cudaEventDestroy(x);
+  return rc;
+}
+
+int ddif_haar_dwt2_f32(const ddif_haar_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_HAAR_DWT2, p, s); }
+int ddif_haar_idwt2_f32(const ddif_haar_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_HAAR_IDWT2, p, s); }
+int ddif_cond_assemble_f32(const ddif_cond_assemble_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_COND_ASSEMBLE, p, s); }
+int ddif_ddpm_step_f32(const ddif_ddpm_step_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_DDPM_STEP, p, s); }
+int ddif_ddim_step_f32(const ddif_ddim_step_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_DDIM_STEP, p, s); }
+int ddif_dpmpp_step_f32(const ddif_dpmpp_step_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_DPMPP_STEP, p, s); }
+int ddif_q_sample_f32(const ddif_q_sample_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_Q_SAMPLE, p, s); }
+int ddif_conv_igemm_bf16(const ddif_gemm_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_GEMM, p, s); }
+
+}  // extern "C"

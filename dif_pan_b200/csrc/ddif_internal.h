@@ -1,0 +1,44 @@
+// Internal declarations shared by the translation units of libddif_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/ddif_b200.h"
+
+namespace ddif {
+
+// A GEMM op resolved to kernel parameters (tensor maps encoded) + launch geometry.
+struct alignas(64) GemmLaunch {
+  unsigned char kparams[1024];
+  int grid_x, grid_y, smem_bytes;
+};
+
+int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L);
+int gemm_launch(const GemmLaunch& L, cudaStream_t stream);
+
+// elementwise.cu
+int launch_in_convert(const ddif_in_convert_t& p, cudaStream_t s);
+int launch_time_embed(const ddif_time_embed_t& p, cudaStream_t s);
+int launch_gn_apply(const ddif_gn_apply_t& p, cudaStream_t s);
+int launch_softmax_h(const ddif_softmax_h_t& p, cudaStream_t s);
+int launch_attn(const ddif_attn_t& p, cudaStream_t s);
+int launch_upsample2x(const ddif_upsample2x_t& p, cudaStream_t s);
+int launch_conv_direct(const ddif_conv_direct_t& p, cudaStream_t s);
+int launch_stats(const ddif_stats_t& p, cudaStream_t s);
+int launch_resize(const ddif_resize_t& p, cudaStream_t s);
+int launch_fwm_context(const ddif_fwm_context_t& p, cudaStream_t s);
+int launch_fwm_weff(const ddif_fwm_weff_t& p, cudaStream_t s);
+
+// sampler.cu
+int launch_ddpm_step(const ddif_ddpm_step_t& p, cudaStream_t s);
+int launch_ddim_step(const ddif_ddim_step_t& p, cudaStream_t s);
+int launch_dpmpp_step(const ddif_dpmpp_step_t& p, cudaStream_t s);
+int launch_q_sample(const ddif_q_sample_t& p, cudaStream_t s);
+int launch_haar_dwt2(const ddif_haar_t& p, cudaStream_t s);
+int launch_haar_idwt2(const ddif_haar_t& p, cudaStream_t s);
+int launch_cond_assemble(const ddif_cond_assemble_t& p, cudaStream_t s);
+int launch_randn(const ddif_randn_t& p, cudaStream_t s);
+int launch_axpby_clip(const ddif_axpby_clip_t& p, cudaStream_t s);
+
+}  // namespace ddif

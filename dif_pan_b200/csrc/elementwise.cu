@@ -1,0 +1,532 @@
+// Memory-bound kernels of the SR3-DWT UNet forward: layout conversion, GroupNorm(1 group) apply (+Swish, +depthwise
+// 3x3), FWM softmaxes / context, self-attention core, time embedding, bilinear cond resize, nearest upsample,
+// per-sample statistics, and a CUDA-core direct convolution used as on-GPU checker for the tcgen05 path.
+// All activations are NHWC bf16; every thread moves 16-byte vectors (8 channels) with channel-contiguous,
+// warp-coalesced accesses.  Reference: /root/reference/models/sr3_dwt.py (line numbers per kernel).
+#include "common.cuh"
+#include "ddif_internal.h"
+
+namespace ddif {
+
+static inline int grid_for(int64_t items, int threads, int cap = 148 * 16) {
+  int64_t b = ceil_div(items, threads);
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ---- NCHW fp32 (x, self_cond) -> NHWC bf16 [self_cond | x | 0-pad]   (sr3_dwt.py:172-174) -----------------
+__global__ void in_convert_kernel(const float* __restrict__ x, const float* __restrict__ sc, bf16* __restrict__ out,
+                                  int B, int C, int HW, int c_pad) {
+  const int64_t total = (int64_t)B * HW;
+  const int nsrc = sc ? 2 : 1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int pix = (int)(i - (int64_t)b * HW);
+    bf16* o = out + i * c_pad;
+    for (int c0 = 0; c0 < c_pad; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        float t = 0.f;
+        if (c < nsrc * C) {
+          const float* src = (nsrc == 2 && c < C) ? sc : x;
+          const int cc = (nsrc == 2 && c >= C) ? c - C : c;
+          t = __ldg(src + ((size_t)b * C + cc) * HW + pix);
+        }
+        v[j] = t;
+      }
+      *reinterpret_cast<bf16x8*>(o + c0) = pack8(v);
+    }
+  }
+}
+int launch_in_convert(const ddif_in_convert_t& p, cudaStream_t s) {
+  if (p.c_pad % 8 != 0 || p.c_pad < (p.self_cond ? 2 : 1) * p.c) return DDIF_ERR_SHAPE;
+  const int64_t hw = p.h * p.w;
+  in_convert_kernel<<<grid_for(p.batch * hw, 256), 256, 0, s>>>(p.x, p.self_cond, (bf16*)p.out, (int)p.batch, (int)p.c, (int)hw, (int)p.c_pad);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- time embedding + all FiLM vectors (sr3_dwt.py:57-64, 223-238, 245-257) ------------------------------
+__global__ void time_embed_kernel(ddif_time_embed_t p) {
+  extern __shared__ float sm[];
+  const int inner = (int)p.inner, hid = 4 * inner, count = inner / 2;
+  float* enc = sm;
+  float* h = sm + inner;
+  float* te = h + hid;
+  const int b = blockIdx.x;
+  const float t = p.time[b];
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+    const int k = i < count ? i : i - count;
+    const float step = (float)k / (float)count;
+    const float e = t * expf(-9.210340371976184f * step);
+    enc[i] = i < count ? sinf(e) : cosf(e);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < hid; j += blockDim.x) {
+    float a = p.b1[j];
+    for (int k = 0; k < inner; ++k) a += p.w1[j * inner + k] * enc[k];
+    h[j] = a / (1.0f + expf(-a));
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < inner; j += blockDim.x) {
+    float a = p.b2[j];
+    for (int k = 0; k < hid; ++k) a += p.w2[j * hid + k] * h[k];
+    te[j] = a;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < (int)p.nfilm; j += blockDim.x) {
+    float a = p.bf[j];
+    for (int k = 0; k < inner; ++k) a += p.wf[(size_t)j * inner + k] * te[k];
+    p.film[(size_t)b * p.nfilm + j] = a;
+  }
+}
+int launch_time_embed(const ddif_time_embed_t& p, cudaStream_t s) {
+  if (p.inner % 2 != 0 || p.inner > 256) return DDIF_ERR_SHAPE;
+  time_embed_kernel<<<(int)p.batch, 256, (size_t)(6 * p.inner) * sizeof(float), s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- GroupNorm(1 group) apply (+Swish) (+depthwise 3x3)   (sr3_dwt.py:292-294, 336, 381-382, 507-512) ------
+struct GnK {
+  const bf16* src1; const bf16* src2; int c1, c2;
+  const double* st1; const double* st2;
+  const float* gamma; const float* beta;
+  bf16* out; const float* dw_w; bf16* out_dw;
+  int H, W, act; float eps;
+};
+
+__device__ __forceinline__ void gn_norm8(const bf16* src, const float* a, const float* d, int act, float* y) {
+  float v[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(src), v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float t = v[j] * a[j] + d[j];
+    y[j] = act ? t / (1.0f + __expf(-t)) : t;
+  }
+}
+
+__global__ void gn_apply_kernel(GnK p) {
+  const int b = blockIdx.y;
+  const int C = p.c1 + p.c2;
+  const int nchunk = C >> 3;
+  const int HW = p.H * p.W;
+  // per-sample statistics of the (virtually) concatenated tensor
+  double s = p.st1[2 * b], ss = p.st1[2 * b + 1];
+  double n = (double)p.c1 * HW;
+  if (p.c2) {
+    s += p.st2[2 * b];
+    ss += p.st2[2 * b + 1];
+    n += (double)p.c2 * HW;
+  }
+  const double mean_d = s / n;
+  double var_d = ss / n - mean_d * mean_d;
+  if (var_d < 0) var_d = 0;
+  const float mean = (float)mean_d;
+  const float rstd = rsqrtf((float)var_d + p.eps);
+  const int64_t items = (int64_t)HW * nchunk;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i / nchunk);
+    const int ch = (int)(i - (int64_t)pix * nchunk) << 3;
+    float a[8], d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = rstd * __ldg(p.gamma + ch + j);
+      d[j] = __ldg(p.beta + ch + j) - mean * a[j];
+    }
+    const bool first = ch < p.c1;
+    const bf16* base = first ? p.src1 : p.src2;
+    const int ld = first ? p.c1 : p.c2;
+    const int cc = first ? ch : ch - p.c1;
+    const size_t img = (size_t)b * HW;
+    float y[8];
+    gn_norm8(base + (img + pix) * ld + cc, a, d, p.act, y);
+    *reinterpret_cast<bf16x8*>(p.out + (img + pix) * C + ch) = pack8(y);
+    if (p.dw_w) {
+      const int py = pix / p.W, px = pix - py * p.W;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+        if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+        float z[8];
+        if (tap == 4) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] = y[j];
+        } else {
+          gn_norm8(base + (img + (size_t)yy * p.W + xx) * ld + cc, a, d, p.act, z);
+        }
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.dw_w + (size_t)tap * C + ch));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.dw_w + (size_t)tap * C + ch + 4));
+        acc[0] += w0.x * z[0]; acc[1] += w0.y * z[1]; acc[2] += w0.z * z[2]; acc[3] += w0.w * z[3];
+        acc[4] += w1.x * z[4]; acc[5] += w1.y * z[5]; acc[6] += w1.z * z[6]; acc[7] += w1.w * z[7];
+      }
+      *reinterpret_cast<bf16x8*>(p.out_dw + (img + pix) * C + ch) = pack8(acc);
+    }
+  }
+}
+int launch_gn_apply(const ddif_gn_apply_t& p, cudaStream_t s) {
+  if (p.c1 % 8 != 0 || p.c2 % 8 != 0 || p.c1 <= 0) return DDIF_ERR_SHAPE;
+  if (p.c2 && (!p.src2 || !p.stats2)) return DDIF_ERR_ARG;
+  if (p.dw_w && !p.out_dw) return DDIF_ERR_ARG;
+  GnK k{(const bf16*)p.src1, (const bf16*)p.src2, (int)p.c1, (int)p.c2, p.stats1, p.stats2, p.gamma, p.beta,
+        (bf16*)p.out, p.dw_w, (bf16*)p.out_dw, (int)p.h, (int)p.w, (int)p.act, (float)p.eps};
+  const int64_t items = p.h * p.w * ((p.c1 + p.c2) / 8);
+  int gx = grid_for(items, 256, 148 * 8);
+  int cap = (int)ceil_div(148 * 16, p.batch);
+  if (gx > cap && cap >= 1) gx = cap;
+  gn_apply_kernel<<<dim3(gx, (unsigned)p.batch), 256, 0, s>>>(k);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- q.softmax(dim=-2) * scale   (sr3_dwt.py:545, 561): softmax over H for every (b, x, channel) ---------
+__global__ void softmax_h_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C, float scale) {
+  const int nchunk = C >> 3;
+  const int64_t items = (int64_t)B * W * nchunk;
+  const size_t row = (size_t)W * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / ((int64_t)W * nchunk));
+    const int r = (int)(i - (int64_t)b * W * nchunk);  // (x, chunk) linear == offset/8 inside a row
+    const bf16* src = in + (size_t)b * H * row + (size_t)r * 8;
+    bf16* dst = out + (size_t)b * H * row + (size_t)r * 8;
+    float m[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; l[j] = 0.f; }
+    for (int y = 0; y < H; ++y) {
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(src + (size_t)y * row), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float mn = fmaxf(m[j], v[j]);
+        l[j] = l[j] * __expf(m[j] - mn) + __expf(v[j] - mn);
+        m[j] = mn;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l[j] = scale / l[j];
+    for (int y = 0; y < H; ++y) {
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(src + (size_t)y * row), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __expf(v[j] - m[j]) * l[j];
+      *reinterpret_cast<bf16x8*>(dst + (size_t)y * row) = pack8(v);
+    }
+  }
+}
+int launch_softmax_h(const ddif_softmax_h_t& p, cudaStream_t s) {
+  if (p.c % 8 != 0) return DDIF_ERR_SHAPE;
+  softmax_h_kernel<<<grid_for(p.batch * p.w * (p.c / 8), 128), 128, 0, s>>>((const bf16*)p.in, (bf16*)p.out, (int)p.batch, (int)p.h,
+                                                                              (int)p.w, (int)p.c, (float)p.scale);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- self-attention core (sr3_dwt.py:347-357): flash-style, one block per (b, head, 64-query tile) ---------
+template <int HD>
+__global__ void attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int ntok, int C, int heads, float scale) {
+  __shared__ float sk[64][HD];
+  __shared__ float sv[64][HD];
+  const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * 64;
+  const int tid = threadIdx.x;  // 64 threads
+  const int C3 = 3 * C;
+  const bf16* base = qkv + (size_t)b * ntok * C3 + head * 3 * HD;
+  const int qi = q0 + tid;
+  float q[HD], acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) {
+    q[d] = (qi < ntok) ? __bfloat162float(base[(size_t)qi * C3 + d]) * scale : 0.f;
+    acc[d] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < ntok; k0 += 64) {
+    __syncthreads();
+    for (int i = tid; i < 64 * HD; i += 64) {
+      const int j = i / HD, d = i - j * HD;
+      const int kj = k0 + j;
+      sk[j][d] = (kj < ntok) ? __bfloat162float(base[(size_t)kj * C3 + HD + d]) : 0.f;
+      sv[j][d] = (kj < ntok) ? __bfloat162float(base[(size_t)kj * C3 + 2 * HD + d]) : 0.f;
+    }
+    __syncthreads();
+    const int kn = min(64, ntok - k0);
+    for (int j = 0; j < kn; ++j) {
+      float sdot = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) sdot += q[d] * sk[j][d];
+      const float mn = fmaxf(m, sdot);
+      const float corr = __expf(m - mn);
+      const float pj = __expf(sdot - mn);
+      l = l * corr + pj;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] = acc[d] * corr + pj * sv[j][d];
+      m = mn;
+    }
+  }
+  if (qi < ntok) {
+    const float inv = 1.0f / l;
+    bf16* o = out + ((size_t)b * ntok + qi) * C + head * HD;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = __float2bfloat16(acc[d] * inv);
+  }
+}
+int launch_attn(const ddif_attn_t& p, cudaStream_t s) {
+  if (p.c % p.heads != 0) return DDIF_ERR_SHAPE;
+  const int hd = (int)(p.c / p.heads);
+  dim3 grid((unsigned)ceil_div(p.ntok, 64), (unsigned)p.heads, (unsigned)p.batch);
+  const bf16* in = (const bf16*)p.qkv;
+  bf16* out = (bf16*)p.out;
+  switch (hd) {
+    case 8: attn_kernel<8><<<grid, 64, 0, s>>>(in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale); break;
+    case 16: attn_kernel<16><<<grid, 64, 0, s>>>(in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale); break;
+    case 32: attn_kernel<32><<<grid, 64, 0, s>>>(in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale); break;
+    case 64: attn_kernel<64><<<grid, 64, 0, s>>>(in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale); break;
+    default: return DDIF_ERR_SHAPE;
+  }
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- nearest x2 (sr3_dwt.py:269) ---------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
+  const int nchunk = C >> 3;
+  const int OW = 2 * W, OH = 2 * H;
+  const int64_t items = (int64_t)B * OH * OW * nchunk;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % nchunk);
+    int64_t r = i / nchunk;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const int b = (int)(r / OH);
+    const bf16x8 v = *reinterpret_cast<const bf16x8*>(in + (((size_t)b * H + (oy >> 1)) * W + (ox >> 1)) * C + ch * 8);
+    *reinterpret_cast<bf16x8*>(out + (size_t)i * 8) = v;
+  }
+}
+int launch_upsample2x(const ddif_upsample2x_t& p, cudaStream_t s) {
+  if (p.c % 8 != 0) return DDIF_ERR_SHAPE;
+  upsample2x_kernel<<<grid_for(p.batch * p.h * p.w * 4 * (p.c / 8), 256), 256, 0, s>>>((const bf16*)p.in, (bf16*)p.out, (int)p.batch,
+                                                                                         (int)p.h, (int)p.w, (int)p.c);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- CUDA-core direct convolution: checker for the tcgen05 path -------------------------------------------
+__global__ void conv_direct_kernel(ddif_conv_direct_t p) {
+  const bf16* in = (const bf16*)p.in;
+  const bf16* w = (const bf16*)p.w;
+  bf16* out = (bf16*)p.out;
+  const int N = (int)p.n_valid;
+  const int64_t items = p.batch * p.out_h * p.out_w * N;
+  const int pad = p.taps == 9 ? 1 : 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    int64_t r = i / N;
+    const int ox = (int)(r % p.out_w); r /= p.out_w;
+    const int oy = (int)(r % p.out_h);
+    const int b = (int)(r / p.out_h);
+    float acc = p.bias ? p.bias[n] : 0.f;
+    for (int tap = 0; tap < (int)p.taps; ++tap) {
+      const int dy = p.taps == 9 ? tap / 3 : 0, dx = p.taps == 9 ? tap % 3 : 0;
+      const int iy = oy * (int)p.stride + dy - pad, ix = ox * (int)p.stride + dx - pad;
+      if (iy < 0 || iy >= p.in_h || ix < 0 || ix >= p.in_w) continue;
+      const bf16* a = in + (((size_t)b * p.in_h + iy) * p.in_w + ix) * p.in_ld;
+      const bf16* ww = w + ((size_t)tap * p.n_pad + n) * p.w_k;
+      for (int c = 0; c < (int)p.cin; ++c) acc += __bfloat162float(a[c]) * __bfloat162float(ww[c]);
+    }
+    if (p.act == 1) acc = acc / (1.0f + __expf(-acc));
+    out[(((size_t)b * p.out_h + oy) * p.out_w + ox) * p.out_ld + n] = __float2bfloat16(acc);
+  }
+}
+int launch_conv_direct(const ddif_conv_direct_t& p, cudaStream_t s) {
+  if (p.taps != 1 && p.taps != 9) return DDIF_ERR_ARG;
+  conv_direct_kernel<<<grid_for(p.batch * p.out_h * p.out_w * p.n_valid, 256, 148 * 32), 256, 0, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- per-sample sum / sum of squares (GroupNorm statistics for tensors not produced by a GEMM epilogue) ----
+__global__ void stats_kernel(const bf16* __restrict__ in, double* __restrict__ stats, int64_t per_sample) {
+  const int b = blockIdx.y;
+  const bf16* src = in + (size_t)b * per_sample;
+  float s1 = 0.f, s2 = 0.f;
+  const int64_t nvec = per_sample >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(src + i * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 += v[j]; s2 += v[j] * v[j]; }
+  }
+  __shared__ float r1[8], r2[8];
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += r1[i]; c += r2[i]; }
+    atomicAdd(stats + 2 * b, a);
+    atomicAdd(stats + 2 * b + 1, c);
+  }
+}
+int launch_stats(const ddif_stats_t& p, cudaStream_t s) {
+  const int64_t per = p.hw * p.c;
+  if (per % 8 != 0) return DDIF_ERR_SHAPE;
+  int gx = grid_for(per / 8, 256, 64);
+  stats_kernel<<<dim3(gx, (unsigned)p.batch), 256, 0, s>>>((const bf16*)p.in, p.stats, per);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- F.interpolate(cond[:, c0:c0+c], size, 'bilinear', align_corners=False) (sr3_dwt.py:661-663) ----------
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.0f - l1;
+}
+__global__ void resize_kernel(ddif_resize_t p) {
+  const int64_t items = p.batch * p.out_h * p.out_w;
+  const float sh = (float)p.h / (float)p.out_h, sw = (float)p.w / (float)p.out_w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % p.out_w);
+    const int oy = (int)((i / p.out_w) % p.out_h);
+    const int b = (int)(i / (p.out_w * p.out_h));
+    int y0, y1, x0, x1;
+    float hy0, hy1, wx0, wx1;
+    bilinear_src(oy, sh, (int)p.h, y0, y1, hy0, hy1);
+    bilinear_src(ox, sw, (int)p.w, x0, x1, wx0, wx1);
+    bf16* dn = p.dst_nhwc ? (bf16*)p.dst_nhwc + (size_t)i * p.c_pad : nullptr;
+    for (int c = 0; c < (int)p.c; ++c) {
+      const float* pl = p.src + ((size_t)b * p.c_total + p.c0 + c) * p.h * p.w;
+      float v;
+      if (p.h == p.out_h && p.w == p.out_w) {
+        v = pl[(size_t)oy * p.w + ox];
+      } else {
+        v = hy0 * (wx0 * pl[(size_t)y0 * p.w + x0] + wx1 * pl[(size_t)y0 * p.w + x1]) +
+            hy1 * (wx0 * pl[(size_t)y1 * p.w + x0] + wx1 * pl[(size_t)y1 * p.w + x1]);
+      }
+      if (dn) dn[c] = __float2bfloat16(v);
+      if (p.dst_nchw) p.dst_nchw[(((size_t)b * p.c + c) * p.out_h + oy) * p.out_w + ox] = v;
+    }
+    if (dn)
+      for (int c = (int)p.c; c < (int)p.c_pad; ++c) dn[c] = __float2bfloat16(0.f);
+  }
+}
+int launch_resize(const ddif_resize_t& p, cudaStream_t s) {
+  if (p.dst_nhwc && p.c_pad < p.c) return DDIF_ERR_SHAPE;
+  resize_kernel<<<grid_for(p.batch * p.out_h * p.out_w, 128), 128, 0, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- FWM cond-only context (sr3_dwt.py:541,546,563): one block per (b, head) --------------------------------
+//  kv = Conv1x1(DW3x3(c));  k.softmax over W;  ctx[d][e] = sum_n k[d,n] v[e,n]
+__global__ void fwm_context_kernel(ddif_fwm_context_t p) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.y, head = blockIdx.x;
+  const int H = (int)p.h, W = (int)p.w, cd = (int)p.cd, dim = (int)p.dim;
+  const int d = dim / (int)p.heads;
+  float* dwb = sm;               // [cd][W]
+  float* kb = dwb + cd * W;      // [d][W]
+  float* vb = kb + d * W;        // [d][W]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};  // pairs tid, tid+nt, ... of the d*d context (d <= 32, nt = 256)
+  const float* cb = p.c_dec + (size_t)b * cd * H * W;
+  for (int y = 0; y < H; ++y) {
+    for (int i = tid; i < cd * W; i += nt) {
+      const int cc = i / W, x = i - cc * W;
+      float a = 0.f;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        a += p.kv0_w[cc * 9 + tap] * cb[((size_t)cc * H + yy) * W + xx];
+      }
+      dwb[i] = a;
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * d * W; i += nt) {
+      const int r = i / W, x = i - r * W;
+      const int row = r < d ? head * d + r : dim + head * d + (r - d);
+      float a = p.kv1_b[row];
+      for (int cc = 0; cc < cd; ++cc) a += p.kv1_w[row * cd + cc] * dwb[cc * W + x];
+      if (r < d) kb[r * W + x] = a; else vb[(r - d) * W + x] = a;
+    }
+    __syncthreads();
+    // softmax over W for each k row: one warp per row
+    for (int r = tid >> 5; r < d; r += nt >> 5) {
+      float mx = -INFINITY;
+      for (int x = tid & 31; x < W; x += 32) mx = fmaxf(mx, kb[r * W + x]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int x = tid & 31; x < W; x += 32) {
+        const float e = expf(kb[r * W + x] - mx);
+        kb[r * W + x] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+      for (int x = tid & 31; x < W; x += 32) kb[r * W + x] *= inv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int pr = tid + k * nt;
+      if (pr < d * d) {
+        const int dd = pr / d, e = pr - dd * d;
+        float a = 0.f;
+        for (int x = 0; x < W; ++x) a += kb[dd * W + x] * vb[e * W + x];
+        acc[k] += a;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int pr = tid + k * nt;
+    if (pr < d * d) p.ctx[((size_t)b * p.heads + head) * d * d + pr] = acc[k];
+  }
+}
+int launch_fwm_context(const ddif_fwm_context_t& p, cudaStream_t s) {
+  if (p.dim % p.heads != 0) return DDIF_ERR_SHAPE;
+  const int d = (int)(p.dim / p.heads);
+  if (d > 32) return DDIF_ERR_SHAPE;
+  const size_t smem = (size_t)(p.cd + 2 * d) * p.w * sizeof(float);
+  if (smem > 220 * 1024) return DDIF_ERR_SHAPE;
+  if (smem > 48 * 1024) DDIF_CUDA_CHECK(cudaFuncSetAttribute(fwm_context_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fwm_context_kernel<<<dim3((unsigned)p.heads, (unsigned)p.batch), 256, smem, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- W_eff[b][o][h*d+dd] = scale * sum_e W_out[o][h*d+e] * ctx[b][h][dd][e]   (sr3_dwt.py:561-573) ----------
+__global__ void fwm_weff_kernel(ddif_fwm_weff_t p) {
+  const int dim = (int)p.dim, d = dim / (int)p.heads;
+  const int64_t items = p.batch * p.o * dim;
+  bf16* out = (bf16*)p.weff;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % dim);
+    const int o = (int)((i / dim) % p.o);
+    const int b = (int)(i / ((int64_t)dim * p.o));
+    const int h = col / d, dd = col - h * d;
+    const float* cx = p.ctx + (((size_t)b * p.heads + h) * d + dd) * d;
+    const float* wo = p.w_out + (size_t)o * dim + h * d;
+    float a = 0.f;
+    for (int e = 0; e < d; ++e) a += wo[e] * cx[e];
+    out[((size_t)b * p.o_pad + o) * p.k_pad + col] = __float2bfloat16(a * (float)p.scale);
+  }
+}
+int launch_fwm_weff(const ddif_fwm_weff_t& p, cudaStream_t s) {
+  if (p.o_pad < p.o || p.k_pad < p.dim) return DDIF_ERR_SHAPE;
+  fwm_weff_kernel<<<grid_for(p.batch * p.o * p.dim, 256), 256, 0, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+}  // namespace ddif

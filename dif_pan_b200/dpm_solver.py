@@ -1,0 +1,261 @@
+"""NoiseScheduleVP / model_wrapper / DPM_Solver — drop-in for /root/reference/solver/dpm_solver.py ("dpm.py").
+
+Same class / function signatures.  Schedule scalars (log-alpha interpolation, lambda, sigma, expm1 ...) are a few
+floats per step and are computed on the HOST with fp32 torch-CPU arithmetic using the reference's formulas
+(dpm.py:126-175, 555-588, 804-912); the per-element work of one solver step — the reference's
+x_start -> noise -> x_start round trip (dpm.py:299-300, 446-447) plus the multistep update — is ONE fused CUDA
+kernel (`ddif_dpmpp_step_f32`, csrc/sampler.cu).  With a `dif_pan_b200.UNetSR3` denoiser the loop runs in place
+on the model's device buffers: per step one CUDA-graph launch + one fused kernel.
+
+Implemented: algorithm_type 'dpmsolver++', method 'multistep' (orders 1-3, lower_order_final), skip types
+time_uniform / time_quadratic / logSNR, model types x_start / noise / v, guidance 'uncond' or 'classifier-free'
+with scale 1 (the wiring SURVEY.md §3.3 names).  The single-step / adaptive variants (dpm.py:602-802,964-1018;
+not used by any BASELINE config) raise NotImplementedError.
+
+Reference quirk kept out: model_wrapper multiplies `[B]`-shaped alpha_t against `[B,C,H,W]` (dpm.py:299-300),
+which only broadcasts for B == 1 or B == W; all entries are equal, so a scalar multiply is the same arithmetic and
+works for every batch size.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from .unet import UNetSR3
+
+MODEL_TYPES = {"x_start": 0, "noise": 1, "v": 2}
+
+
+def interpolate_fn(x: torch.Tensor, xp: torch.Tensor, yp: torch.Tensor) -> torch.Tensor:
+    """Piecewise-linear interpolation with linear extrapolation, x:[N,1], xp/yp:[1,K] (dpm.py:1261-1300),
+    via searchsorted instead of the reference's sort+gather."""
+    xs, xk, yk = x.reshape(-1), xp.reshape(-1), yp.reshape(-1)
+    K = xk.shape[0]
+    lo = torch.clamp(torch.searchsorted(xk, xs, right=False) - 1, 0, K - 2)
+    x0, x1, y0, y1 = xk[lo], xk[lo + 1], yk[lo], yk[lo + 1]
+    return (y0 + (xs - x0) * (y1 - y0) / (x1 - x0)).reshape(-1, 1)
+
+
+class NoiseScheduleVP:
+    def __init__(self, schedule="discrete", betas=None, alphas_cumprod=None, continuous_beta_0=0.1, continuous_beta_1=20.0,
+                 dtype=torch.float32):
+        if schedule not in ["discrete", "linear", "cosine"]:
+            raise ValueError("Unsupported noise schedule {}. The schedule needs to be 'discrete' or 'linear' or 'cosine'".format(schedule))
+        self.schedule = schedule
+        if schedule == "discrete":
+            if betas is not None:
+                log_alphas = 0.5 * torch.log(1 - betas.detach().cpu()).cumsum(dim=0)
+            else:
+                assert alphas_cumprod is not None
+                log_alphas = 0.5 * torch.log(alphas_cumprod.detach().cpu())
+            self.total_N = len(log_alphas)
+            self.T = 1.0
+            self.t_array = torch.linspace(0.0, 1.0, self.total_N + 1)[1:].reshape((1, -1)).to(dtype=dtype)
+            self.log_alpha_array = log_alphas.reshape((1, -1)).to(dtype=dtype)
+        else:
+            self.total_N = 1000
+            self.beta_0, self.beta_1 = continuous_beta_0, continuous_beta_1
+            self.cosine_s, self.cosine_beta_max = 0.008, 999.0
+            self.cosine_t_max = (math.atan(self.cosine_beta_max * (1.0 + self.cosine_s) / math.pi) * 2.0 * (1.0 + self.cosine_s)
+                                 / math.pi - self.cosine_s)
+            self.cosine_log_alpha_0 = math.log(math.cos(self.cosine_s / (1.0 + self.cosine_s) * math.pi / 2.0))
+            self.T = 0.9946 if schedule == "cosine" else 1.0
+
+    def marginal_log_mean_coeff(self, t):
+        t = torch.as_tensor(t, dtype=torch.float32).cpu()
+        if self.schedule == "discrete":
+            return interpolate_fn(t.reshape((-1, 1)), self.t_array, self.log_alpha_array).reshape((-1))
+        if self.schedule == "linear":
+            return -0.25 * t ** 2 * (self.beta_1 - self.beta_0) - 0.5 * t * self.beta_0
+        return torch.log(torch.cos((t + self.cosine_s) / (1.0 + self.cosine_s) * math.pi / 2.0)) - self.cosine_log_alpha_0
+
+    def marginal_alpha(self, t):
+        return torch.exp(self.marginal_log_mean_coeff(t))
+
+    def marginal_std(self, t):
+        return torch.sqrt(1.0 - torch.exp(2.0 * self.marginal_log_mean_coeff(t)))
+
+    def marginal_lambda(self, t):
+        lm = self.marginal_log_mean_coeff(t)
+        return lm - 0.5 * torch.log(1.0 - torch.exp(2.0 * lm))
+
+    def inverse_lambda(self, lamb):
+        lamb = torch.as_tensor(lamb, dtype=torch.float32).cpu()
+        if self.schedule == "linear":
+            tmp = 2.0 * (self.beta_1 - self.beta_0) * torch.logaddexp(-2.0 * lamb, torch.zeros((1,)))
+            delta = self.beta_0 ** 2 + tmp
+            return tmp / (torch.sqrt(delta) + self.beta_0) / (self.beta_1 - self.beta_0)
+        if self.schedule == "discrete":
+            log_alpha = -0.5 * torch.logaddexp(torch.zeros((1,)), -2.0 * lamb)
+            t = interpolate_fn(log_alpha.reshape((-1, 1)), torch.flip(self.log_alpha_array, [1]), torch.flip(self.t_array, [1]))
+            return t.reshape((-1,))
+        log_alpha = -0.5 * torch.logaddexp(-2.0 * lamb, torch.zeros((1,)))
+        return torch.arccos(torch.exp(log_alpha + self.cosine_log_alpha_0)) * 2.0 * (1.0 + self.cosine_s) / math.pi - self.cosine_s
+
+
+class _WrappedModel:
+    """What model_wrapper returns: callable like the reference's closure, plus the fields the fused path needs."""
+
+    def __init__(self, model, noise_schedule, model_type, model_kwargs, guidance_type, condition, unconditional_condition,
+                 guidance_scale, classifier_fn, classifier_kwargs):
+        self.model, self.noise_schedule, self.model_type = model, noise_schedule, model_type
+        self.model_kwargs, self.guidance_type, self.condition = model_kwargs, guidance_type, condition
+        self.unconditional_condition, self.guidance_scale = unconditional_condition, guidance_scale
+        if guidance_type == "classifier" or (guidance_type == "classifier-free" and guidance_scale != 1.0
+                                             and unconditional_condition is not None):
+            raise NotImplementedError("classifier guidance / classifier-free guidance with scale != 1 are not wired on the CUDA "
+                                      "path (the DDIF wiring uses guidance_scale=1., SURVEY.md §3.3)")
+
+    def input_time(self, t_continuous):
+        if self.noise_schedule.schedule == "discrete":  # dpm.py:285-288
+            return (t_continuous - 1.0 / self.noise_schedule.total_N) * 1000.0
+        return t_continuous
+
+    def raw(self, x, t_continuous):
+        """The denoiser's raw output at continuous time t (dpm.py:290-295)."""
+        t_in = self.input_time(t_continuous)
+        if self.guidance_type == "uncond" or self.condition is None:
+            return self.model(x, t_in, **self.model_kwargs)
+        return self.model(x, t_in, self.condition, **self.model_kwargs)
+
+    def __call__(self, x, t_continuous):
+        """Noise prediction, like the reference closure (kept for API compatibility; the solver uses the fused kernel)."""
+        out = self.raw(x, t_continuous)
+        ns = self.noise_schedule
+        t0 = torch.as_tensor(t_continuous).reshape(-1)[:1]
+        a, s = float(ns.marginal_alpha(t0)), float(ns.marginal_std(t0))
+        if self.model_type == "noise":
+            return out
+        if self.model_type == "x_start":
+            return (x - a * out) / s
+        if self.model_type == "v":
+            return a * out + s * x
+        return -s * out
+
+
+def model_wrapper(model, noise_schedule, model_type="noise", model_kwargs={}, guidance_type="uncond", condition=None,
+                  unconditional_condition=None, guidance_scale=1.0, classifier_fn=None, classifier_kwargs={}):
+    assert model_type in ["noise", "x_start", "v", "score"]
+    assert guidance_type in ["uncond", "classifier", "classifier-free"]
+    return _WrappedModel(model, noise_schedule, model_type, model_kwargs, guidance_type, condition, unconditional_condition,
+                         guidance_scale, classifier_fn, classifier_kwargs)
+
+
+class DPM_Solver:
+    def __init__(self, model_fn, noise_schedule, algorithm_type="dpmsolver++", correcting_x0_fn=None, correcting_xt_fn=None,
+                 thresholding_max_val=1.0, dynamic_thresholding_ratio=0.995):
+        assert algorithm_type in ["dpmsolver", "dpmsolver++"]
+        if algorithm_type != "dpmsolver++":
+            raise NotImplementedError("only algorithm_type='dpmsolver++' (the default) is on the CUDA path")
+        if correcting_x0_fn is not None or correcting_xt_fn is not None:
+            raise NotImplementedError("correcting_x0_fn / correcting_xt_fn (torch.quantile thresholding) are not on the CUDA path")
+        if not isinstance(model_fn, _WrappedModel) or model_fn.model_type not in MODEL_TYPES:
+            raise NotImplementedError("DPM_Solver needs the callable returned by dif_pan_b200.model_wrapper "
+                                      "(model_type noise / x_start / v)")
+        self.wrapped = model_fn
+        self.model = lambda x, t: model_fn(x, t.expand((x.shape[0])))
+        self.noise_schedule = noise_schedule
+        self.algorithm_type = algorithm_type
+
+    def get_time_steps(self, skip_type, t_T, t_0, N, device=None):
+        """dpm.py:461-488 (host tensors)."""
+        if skip_type == "logSNR":
+            lT = self.noise_schedule.marginal_lambda(torch.tensor(t_T))
+            l0 = self.noise_schedule.marginal_lambda(torch.tensor(t_0))
+            return self.noise_schedule.inverse_lambda(torch.linspace(lT.item(), l0.item(), N + 1))
+        if skip_type == "time_uniform":
+            return torch.linspace(t_T, t_0, N + 1)
+        if skip_type == "time_quadratic":
+            return torch.linspace(t_T ** 0.5, t_0 ** 0.5, N + 1).pow(2)
+        raise ValueError("Unsupported skip_type {}, need to be 'logSNR' or 'time_uniform' or 'time_quadratic'".format(skip_type))
+
+    def _coefficients(self, t_hist: List[torch.Tensor], t_next: torch.Tensor, order: int) -> dict:
+        """fp32 scalars of one multistep update (dpm.py:569-584, 820-839, 876-901)."""
+        ns = self.noise_schedule
+        lam = ns.marginal_lambda
+        t0 = t_hist[-1]
+        h = lam(t_next) - lam(t0)
+        alpha_t = torch.exp(ns.marginal_log_mean_coeff(t_next))
+        phi_1 = torch.expm1(-h)
+        c = dict(cx=ns.marginal_std(t_next) / ns.marginal_std(t0), ca=alpha_t * phi_1)
+        if order == 2:
+            r0 = (lam(t0) - lam(t_hist[-2])) / h
+            c.update(cb=0.5 * (alpha_t * phi_1), inv_r0=1.0 / r0)
+        elif order == 3:
+            r0 = (lam(t0) - lam(t_hist[-2])) / h
+            r1 = (lam(t_hist[-2]) - lam(t_hist[-3])) / h
+            phi_2 = phi_1 / h + 1.0
+            phi_3 = phi_2 / h - 0.5
+            c.update(cb=alpha_t * phi_2, cc=alpha_t * phi_3, inv_r0=1.0 / r0, inv_r1=1.0 / r1, k1=r0 / (r0 + r1), k2=1.0 / (r0 + r1))
+        return {k: float(v) for k, v in c.items()}
+
+    def sample(self, x, steps=20, t_start=None, t_end=None, order=2, skip_type="time_uniform", method="multistep",
+               lower_order_final=True, denoise_to_zero=False, solver_type="dpmsolver", atol=0.0078, rtol=0.05,
+               return_intermediate=False):
+        """dpm.py:1055-1253, multistep branch (:1179-1221)."""
+        ns = self.noise_schedule
+        t_0 = 1.0 / ns.total_N if t_end is None else t_end
+        t_T = ns.T if t_start is None else t_start
+        assert t_0 > 0 and t_T > 0, "Time range needs to be greater than 0. For discrete-time DPMs, it needs to be in [1 / N, 1], where N is the length of betas array"
+        if method != "multistep":
+            if method in ("singlestep", "singlestep_fixed", "adaptive"):
+                raise NotImplementedError(f"method={method!r} is not on the CUDA path (multistep only)")
+            raise ValueError("Got wrong method {}".format(method))
+        if solver_type != "dpmsolver":
+            if solver_type == "taylor":
+                raise NotImplementedError("solver_type='taylor' is not on the CUDA path")
+            raise ValueError("'solver_type' must be either 'dpmsolver' or 'taylor', got {}".format(solver_type))
+        if denoise_to_zero:
+            raise NotImplementedError("denoise_to_zero is not on the CUDA path")
+        if order not in (1, 2, 3):
+            raise ValueError("Solver order must be 1 or 2 or 3, got {}".format(order))
+        assert steps >= order
+        if not x.is_cuda:
+            raise RuntimeError("dif_pan_b200 sampler kernels run on CUDA only (no CPU fallback)")
+        wm = self.wrapped
+        ts = self.get_time_steps(skip_type, t_T, t_0, steps)
+        assert ts.shape[0] - 1 == steps
+        B = x.shape[0]
+        dev = x.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        fast = isinstance(wm.model, UNetSR3) and wm.condition is not None and not wm.model_kwargs
+        with torch.no_grad():
+            if fast:
+                rt = wm.model.runtime(B, x.shape[2], x.shape[3])
+                rt.set_cond(wm.condition)
+                xb, out, tbuf = rt.x_buf, rt.out_buf, rt.t_buf
+                xb.copy_(x)
+                tbuf.fill_(float(wm.input_time(ts[0])))
+            else:
+                xb = x.clone().contiguous()
+                tbuf = None
+            m = [torch.empty_like(xb) for _ in range(3)]
+            inter = [xb.clone()] if return_intermediate else []
+            for s in range(steps):
+                t_cur = ts[s]
+                if fast:
+                    rt.step()
+                else:
+                    out = wm.raw(xb, t_cur.to(dev).expand(B)).contiguous()
+                nxt = s + 1
+                if nxt < order:
+                    o = nxt
+                elif lower_order_final and steps < 10:
+                    o = min(order, steps + 1 - nxt)
+                else:
+                    o = order
+                coef = self._coefficients([ts[i] for i in range(max(0, s - 2), s + 1)], ts[nxt], o)
+                last_eval = nxt == steps
+                _lib.launch(
+                    "ddif_dpmpp_step_t", stream, x=xb.data_ptr(), model_out=out.data_ptr(), m_cur=m[s % 3].data_ptr(),
+                    m_prev1=m[(s - 1) % 3].data_ptr(), m_prev2=m[(s - 2) % 3].data_ptr(),
+                    time_out=tbuf.data_ptr() if (fast and not last_eval) else None, n=xb.numel(), batch=B, order=o,
+                    model_type=MODEL_TYPES[wm.model_type], alpha_t=float(ns.marginal_alpha(t_cur)), sigma_t=float(ns.marginal_std(t_cur)),
+                    t_next_in=float(wm.input_time(ts[nxt])), **coef)
+                if return_intermediate:
+                    inter.append(xb.clone())
+            res = xb.clone()
+        return (res, inter) if return_intermediate else res

@@ -1,0 +1,191 @@
+/*
+ * ddif_b200 — C ABI of the B200-native DDIF (Dif-PAN) denoising hot path.
+ *
+ * The reference (294coder/Dif-PAN) is 100 % Python/PyTorch and has no FFI layer; the entry points below are what
+ * a binding for this path replaces.  Each one cites the reference code whose arithmetic it executes.  All
+ * functions: plain pointers and sizes, no torch types; device pointers are BORROWED for the call; nothing is
+ * allocated on the device by the library (workspace comes from the caller); work is enqueued on the given
+ * cudaStream_t (pass torch.cuda.current_stream().cuda_stream) and the device is never synchronised.
+ * Return value: 0 = ok, >0 = cudaError_t, <0 = DDIF_ERR_* (argument / shape / driver / state).
+ *
+ * Activations inside the UNet are NHWC bf16 ("pixels x channels", channel pitch = `*_ld` elements);
+ * sampler state, conditioning and UNet inputs/outputs at the boundary are NCHW fp32 like the reference.
+ *
+ * Every kernel is described by a plain parameter struct whose fields are all 8 bytes wide (pointers, int64_t,
+ * double) so that ctypes / cgo / JNI mirrors cannot get the padding wrong.  A struct can be
+ *   - launched immediately:            ddif_launch(kind, &params, stream)
+ *   - recorded into a plan (op list):  ddif_plan_add(plan, kind, &params)
+ * A plan is the per-step schedule of one UNet forward (~280 ops); ddif_plan_run replays it with one C call and
+ * ddif_plan_graph_launch with one CUDA-graph launch.
+ */
+#ifndef DDIF_B200_H
+#define DDIF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ddif_stream_t; /* cudaStream_t */
+typedef struct ddif_plan ddif_plan_t;
+
+enum ddif_op_kind {
+  DDIF_OP_GEMM = 1,          /* tcgen05 implicit-GEMM conv (3x3 / 1x1, stride 1|2, <=2 K-segments, fused epilogue) */
+  DDIF_OP_IN_CONVERT = 2,    /* NCHW fp32 x (+self_cond) -> NHWC bf16 concat                       sr3_dwt.py:172-174 */
+  DDIF_OP_TIME_EMBED = 3,    /* PositionalEncoding + noise_level_mlp + all FiLM Linears           sr3_dwt.py:57-64,223-258 */
+  DDIF_OP_GN_APPLY = 4,      /* GroupNorm(1 group) affine (+Swish) (+depthwise 3x3), 1 or 2 sources sr3_dwt.py:292-294,507-512 */
+  DDIF_OP_SOFTMAX_H = 5,     /* q.softmax(dim=-2) * scale                                          sr3_dwt.py:545,561 */
+  DDIF_OP_ATTN = 6,          /* fused multi-head self-attention core                               sr3_dwt.py:347-357 */
+  DDIF_OP_UPSAMPLE2X = 7,    /* nearest x2                                                         sr3_dwt.py:269 */
+  DDIF_OP_CONV_DIRECT = 8,   /* CUDA-core direct conv (checker for the tcgen05 path; tiny layers)  */
+  DDIF_OP_STATS = 9,         /* per-sample sum / sum of squares of an NHWC bf16 tensor             */
+  DDIF_OP_MEMSET = 10,
+  DDIF_OP_RESIZE = 11,       /* F.interpolate(cond, size, 'bilinear')                              sr3_dwt.py:661-663 */
+  DDIF_OP_FWM_CONTEXT = 12,  /* kv = 1x1(dw3x3(c)); k.softmax(W); context = k v^T                  sr3_dwt.py:541,546,563 */
+  DDIF_OP_FWM_WEFF = 13,     /* W_eff[b] = scale * attn_out.weight @ blockdiag(context[b]^T)       sr3_dwt.py:561-573 */
+  DDIF_OP_DDPM_STEP = 14,    /* p_mean_variance + p_sample                                         diffusion_ddpm_pan.py:346-442 */
+  DDIF_OP_DDIM_STEP = 15,    /* ddim_sample                                                        diffusion_ddpm_pan.py:594-621 */
+  DDIF_OP_DPMPP_STEP = 16,   /* model_wrapper + data_prediction_fn + multistep update (orders 1-3)  dpm_solver.py:286-300,441-450,555-588,804-912 */
+  DDIF_OP_Q_SAMPLE = 17,     /* q_sample                                                           diffusion_ddpm_pan.py:668-681 */
+  DDIF_OP_HAAR_DWT2 = 18,    /* pywt.wavedec2(x,'db1',level=1)                                     dataset/pan_dataset.py:75-80 */
+  DDIF_OP_HAAR_IDWT2 = 19,   /* inverse of the above (no reference call site)                      */
+  DDIF_OP_COND_ASSEMBLE = 20,/* cond = cat[lms, pan, bilinear(wavelets)]                           diffusion_engine.py:221-228 */
+  DDIF_OP_RANDN = 21,        /* Philox4x32-10 + Box-Muller standard normal (replaces torch.randn)  diffusion_ddpm_pan.py:86,484 */
+  DDIF_OP_AXPBY_CLIP = 22    /* sr = clip(sample + lms, 0, 1)                                      diffusion_engine.py:446-447 */
+};
+
+/* ---- DDIF_OP_GEMM ------------------------------------------------------------------------------------------
+ * out[b,y,x,n] = epilogue( sum_seg sum_tap sum_c  a_seg[b, y*stride+dy-pad, x*stride+dx-pad, c] * w_seg[z, n, c] )
+ * z = tap (shared weights) or b (per-sample weights, 1x1 only).  Zero padding comes from TMA out-of-bounds fill.
+ * epilogue: v = acc + bias[n] + film[b*film_ld + n];  v = v*(1+mod[..,n]) + mod[..,n_valid+n];  v += residual;
+ *           v = silu(v) if act;  stats[b] += (sum v, sum v^2);  store bf16 NHWC and/or fp32 NCHW.              */
+typedef struct {
+  const void* a[2];     int64_t a_ld[2];  int64_t a_c[2];  int64_t a_h[2];  int64_t a_w[2];
+  const void* w[2];     int64_t w_s[2];   int64_t w_k[2];  int64_t taps[2]; int64_t w_per_sample[2];
+  int64_t nseg, stride, batch, out_h, out_w, n_pad, n_valid;
+  const float* bias;
+  const float* film;    int64_t film_ld;
+  const void* mod;
+  const void* residual; int64_t res_ld;
+  int64_t act;
+  void* out;            int64_t out_ld;
+  float* out_nchw;
+  double* stats;
+} ddif_gemm_t;
+
+typedef struct { const float* x; const float* self_cond; void* out; int64_t batch, c, h, w, c_pad; } ddif_in_convert_t;
+
+typedef struct {
+  const float* time; const float* w1; const float* b1; const float* w2; const float* b2;
+  const float* wf; const float* bf; float* film; int64_t batch, inner, nfilm;
+} ddif_time_embed_t;
+
+/* y = act( (x - mean_b) * rstd_b * gamma[c] + beta[c] ), x = concat(src1[c1], src2[c2]) along channels.
+ * stats1/stats2: per-sample (sum, sumsq) of src1/src2 over count1/count2 elements.
+ * If dw_w != NULL also out_dw = depthwise3x3(y) with dw_w laid out [9][c1+c2] fp32 (zero padding of y). */
+typedef struct {
+  const void* src1; int64_t c1; const void* src2; int64_t c2;
+  const double* stats1; const double* stats2;
+  const float* gamma; const float* beta;
+  void* out; const float* dw_w; void* out_dw;
+  int64_t batch, h, w, act; double eps;
+} ddif_gn_apply_t;
+
+typedef struct { const void* in; void* out; int64_t batch, h, w, c; double scale; } ddif_softmax_h_t;
+/* qkv: [B, ntok, 3*C] with per-head channel blocks [q(hd) k(hd) v(hd)]; out: [B, ntok, C] */
+typedef struct { const void* qkv; void* out; int64_t batch, ntok, c, heads; double scale; } ddif_attn_t;
+typedef struct { const void* in; void* out; int64_t batch, h, w, c; } ddif_upsample2x_t;
+typedef struct {
+  const void* in; int64_t in_ld, cin, in_h, in_w; const void* w; int64_t w_k, taps, stride;
+  const float* bias; void* out; int64_t out_ld, batch, out_h, out_w, n_valid, n_pad; int64_t act;
+} ddif_conv_direct_t;
+typedef struct { const void* in; double* stats; int64_t batch, hw, c; } ddif_stats_t;
+typedef struct { void* ptr; int64_t bytes; } ddif_memset_t;
+/* src: fp32 NCHW [B, c_total, h, w]; channels [c0, c0+c) resized to out_h x out_w into a bf16 NHWC tensor with
+ * c_pad channels (zero padded) and/or an fp32 NCHW tensor. */
+typedef struct {
+  const float* src; int64_t batch, c_total, c0, c, h, w, out_h, out_w;
+  void* dst_nhwc; int64_t c_pad; float* dst_nchw;
+} ddif_resize_t;
+typedef struct {
+  const float* c_dec; const float* kv0_w; const float* kv1_w; const float* kv1_b; float* ctx;
+  int64_t batch, h, w, cd, dim, heads;
+} ddif_fwm_context_t;
+typedef struct {
+  const float* ctx; const float* w_out; void* weff; int64_t batch, o, dim, heads, o_pad, k_pad; double scale;
+} ddif_fwm_weff_t;
+
+/* x0 = model_out (x_start) | sra*x - srm1*out (noise) | sa*x - s1ma*out (pred_v); clamp(x0+lms)-lms; posterior.
+ * coef: fp32 device table [T][8] = {c1, c2, logvar, sqrt_recip_ac, sqrt_recipm1_ac, sqrt_ac, sqrt_1m_ac, 0}.
+ * t: timestep index (same for the whole batch, like the reference loop).  noise: injected tensor or NULL
+ * (then Philox(seed, offset)).  lms is read from `cond` (first c channels, cond_c channel count).
+ * time_out (optional): float[batch] receives t-1 for the next UNet call. */
+typedef struct {
+  float* x; const float* model_out; const float* cond; const float* noise; const float* coef; float* time_out;
+  int64_t batch, c, hw, cond_c, t, pred_mode, clip; double clamp_lo, clamp_hi; int64_t seed, offset;
+} ddif_ddpm_step_t;
+/* coef: [T][8] = {alphas_cumprod, alphas_cumprod_prev, sqrt_recip_ac, sqrt_recipm1_ac, sqrt_ac, sqrt_1m_ac, 0, 0} */
+typedef struct {
+  float* x; const float* model_out; const float* cond; const float* noise; const float* coef; float* time_out;
+  int64_t batch, c, hw, cond_c, t, pred_mode, clip; double clamp_lo, clamp_hi, eta; int64_t seed, offset;
+} ddif_ddim_step_t;
+/* m0 = data prediction from the UNet output through the reference's x_start->noise->x_start round trip
+ * (noise = (x - alpha_t*out)/sigma_t; m0 = (x - sigma_t*noise)/alpha_t, alpha/sigma of the CURRENT time), stored
+ * to m_cur.  Then the multistep update to the NEXT time, with host-computed fp32 scalars and the reference's
+ * operation order:
+ *   order 0: no update (last evaluation only stores m_cur)
+ *   order 1: x = cx*x - ca*m0                                                         (dpm_solver.py:581-584)
+ *   order 2: x = cx*x - ca*m0 - cb*(inv_r0*(m0-m1))              cb = 0.5*ca           (dpm_solver.py:831-839)
+ *   order 3: D10 = inv_r0*(m0-m1); D11 = inv_r1*(m1-m2); D1 = D10 + k1*(D10-D11); D2 = k2*(D10-D11);
+ *            x = cx*x - ca*m0 + cb*D1 - cc*D2                                          (dpm_solver.py:888-901)
+ * time_out (optional): float[batch] receives t_next_in (the UNet time label of the next evaluation). */
+typedef struct {
+  float* x; const float* model_out; float* m_cur; const float* m_prev1; const float* m_prev2; float* time_out;
+  int64_t n, batch, order, model_type; /* model_type: 0 x_start, 1 noise, 2 v (dpm_solver.py:296-303) */
+  double alpha_t, sigma_t, cx, ca, cb, cc, inv_r0, inv_r1, k1, k2, t_next_in;
+} ddif_dpmpp_step_t;
+typedef struct { const float* x0; const float* noise; float* out; const float* sa; const float* s1ma; const int64_t* t; int64_t batch, chw; } ddif_q_sample_t;
+/* x: [planes, h, w] fp32 (output for IDWT); 4 sub-bands each [planes, h/2, w/2] (LL, cH, cV, cD).
+ * DWT: every coefficient is divided by `divisor` (the dataset "division", pan_dataset.py:127-134); IDWT ignores it. */
+typedef struct { float* x; float* ll; float* ch; float* cv; float* cd; int64_t planes, h, w; double divisor; } ddif_haar_t;
+/* cond[b] = cat(lms[b] (c), pan[b] (p), bilinear_up(wavelets[b] (cw), h x w)); wavelets at h/2 x w/2 (any size) */
+typedef struct { const float* lms; const float* pan; const float* wav; float* cond; int64_t batch, c, p, cw, h, w, wh, ww; } ddif_cond_assemble_t;
+typedef struct { float* out; int64_t n, seed, offset; } ddif_randn_t;
+typedef struct { const float* x; const float* cond; float* out; int64_t batch, c, hw, cond_c; double lo, hi; } ddif_axpby_clip_t;
+
+/* ---- entry points ---------------------------------------------------------------------------------------- */
+int ddif_version(void);
+const char* ddif_error_string(int code);
+/* Launch one op now on `stream`. */
+int ddif_launch(int kind, const void* params, ddif_stream_t stream);
+
+ddif_plan_t* ddif_plan_create(void);
+void ddif_plan_destroy(ddif_plan_t* plan);
+/* Record an op (parameters are copied; GEMM tensor maps are encoded once here). Returns op index or <0. */
+int ddif_plan_add(ddif_plan_t* plan, int kind, const void* params);
+int ddif_plan_size(const ddif_plan_t* plan);
+/* Enqueue ops [first, last) on `stream` (last<0 = all). */
+int ddif_plan_run(ddif_plan_t* plan, int first, int last, ddif_stream_t stream);
+/* Capture the whole plan into a CUDA graph once, then replay it. */
+int ddif_plan_graph_build(ddif_plan_t* plan, ddif_stream_t stream);
+int ddif_plan_graph_launch(ddif_plan_t* plan, ddif_stream_t stream);
+/* Profiling: run the plan with a CUDA event pair around every op; ms[i] = duration of op i, kinds[i] = its kind. */
+int ddif_plan_profile(ddif_plan_t* plan, ddif_stream_t stream, float* ms, int* kinds, int capacity);
+/* Number of kernel launches the plan issues per run. */
+int ddif_plan_launches(const ddif_plan_t* plan);
+
+/* Named convenience wrappers (same structs), the symbols a reference-side binding would call directly. */
+int ddif_haar_dwt2_f32(const ddif_haar_t* p, ddif_stream_t s);
+int ddif_haar_idwt2_f32(const ddif_haar_t* p, ddif_stream_t s);
+int ddif_cond_assemble_f32(const ddif_cond_assemble_t* p, ddif_stream_t s);
+int ddif_ddpm_step_f32(const ddif_ddpm_step_t* p, ddif_stream_t s);
+int ddif_ddim_step_f32(const ddif_ddim_step_t* p, ddif_stream_t s);
+int ddif_dpmpp_step_f32(const ddif_dpmpp_step_t* p, ddif_stream_t s);
+int ddif_q_sample_f32(const ddif_q_sample_t* p, ddif_stream_t s);
+int ddif_conv_igemm_bf16(const ddif_gemm_t* p, ddif_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDIF_B200_H */

@@ -1,0 +1,62 @@
+"""Helpers shared by the `-m gpu` tests: NHWC bf16 tensors, op launches through the C ABI, error metrics."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from dif_pan_b200 import _lib
+
+DEV = "cuda:0"
+
+
+def stream() -> int:
+    return torch.cuda.current_stream(torch.device(DEV)).cuda_stream
+
+
+def nhwc_bf16(x_nchw: torch.Tensor, c_pad: int = None) -> torch.Tensor:
+    """fp32 NCHW -> contiguous NHWC bf16 (optionally zero-padded channels)."""
+    x = x_nchw.permute(0, 2, 3, 1)
+    if c_pad is not None and c_pad > x.shape[-1]:
+        x = F.pad(x, (0, c_pad - x.shape[-1]))
+    return x.contiguous().to(torch.bfloat16)
+
+
+def to_nchw_f32(x_nhwc: torch.Tensor) -> torch.Tensor:
+    return x_nhwc.float().permute(0, 3, 1, 2).contiguous()
+
+
+def pack_w(w_oihw: torch.Tensor, cin_pad: int = None) -> torch.Tensor:
+    from dif_pan_b200.unet import _pack_conv
+    return _pack_conv(w_oihw, cin_pad)
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def gemm(srcs, weights, n_valid, *, taps, stride=1, bias=None, film=None, mod=None, residual=None, act=0,
+         per_sample=None, want_nchw=False, want_stats=False, out_hw=None):
+    """Run DDIF_OP_GEMM on NHWC bf16 tensors; returns (out_nhwc_bf16 | out_nchw_f32, stats | None)."""
+    a0 = srcs[0]
+    B, H, W, _ = a0.shape
+    oh, ow = out_hw if out_hw else (H // stride, W // stride)
+    nseg = len(srcs)
+    n_pad = (n_valid + 15) // 16 * 16
+    out = torch.zeros(B, oh, ow, n_valid if n_valid % 8 == 0 else n_pad, dtype=torch.bfloat16, device=DEV) if not want_nchw else None
+    out_nchw = torch.zeros(B, n_valid, oh, ow, dtype=torch.float32, device=DEV) if want_nchw else None
+    stats = torch.zeros(B, 2, dtype=torch.float64, device=DEV) if want_stats else None
+    ps = list(per_sample) if per_sample else [0] * nseg
+    pad2 = lambda lst, fill: list(lst) + [fill] * (2 - nseg)
+    _lib.launch(
+        "ddif_gemm_t", stream(),
+        a=pad2([s.data_ptr() for s in srcs], None), a_ld=pad2([s.shape[3] for s in srcs], 0), a_c=pad2([s.shape[3] for s in srcs], 0),
+        a_h=pad2([s.shape[1] for s in srcs], 0), a_w=pad2([s.shape[2] for s in srcs], 0), w=pad2([w.data_ptr() for w in weights], None),
+        w_s=pad2([w.shape[0] for w in weights], 0), w_k=pad2([w.shape[2] for w in weights], 0), taps=pad2(taps, 0),
+        w_per_sample=pad2(ps, 0), nseg=nseg, stride=stride, batch=B, out_h=oh, out_w=ow, n_pad=n_pad, n_valid=n_valid,
+        bias=bias.data_ptr() if bias is not None else None, film=film.data_ptr() if film is not None else None,
+        film_ld=film.shape[1] if film is not None else 0, mod=mod.data_ptr() if mod is not None else None,
+        residual=residual.data_ptr() if residual is not None else None, res_ld=residual.shape[3] if residual is not None else 0,
+        act=act, out=out.data_ptr() if out is not None else None, out_ld=out.shape[3] if out is not None else 0,
+        out_nchw=out_nchw.data_ptr() if out_nchw is not None else None, stats=stats.data_ptr() if stats is not None else None)
+    torch.cuda.synchronize()
+    return (out_nchw if want_nchw else out), stats

@@ -1,0 +1,122 @@
+"""GPU parity of the tcgen05 implicit-GEMM conv kernel (csrc/gemm_tc.cu) against torch fp32 convolution of the
+same bf16-rounded operands and against the CUDA-core direct conv checker.  Tolerance: the output is stored in bf16
+(relative rounding 2^-9), accumulation is fp32 -> |err| <= 2^-7 |ref| + 2e-3 * max|ref|."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import DEV, gemm, nhwc_bf16, pack_w, rel_err, stream, to_nchw_f32  # noqa: E402
+from dif_pan_b200 import _lib  # noqa: E402
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _close(got, ref, what=""):
+    tol = (ref.abs() * 2 ** -7 + 2e-3 * ref.abs().max()).double()
+    err = (got.double() - ref.double()).abs()
+    bad = int((err > tol).sum())
+    assert bad == 0, f"{what}: {bad}/{err.numel()} elements off, max err {float(err.max()):.4g}, rel {rel_err(got, ref):.3g}"
+
+
+CASES = [
+    # name,        B,  H,  W, Cin, Cout, k, stride
+    ("c32_sw64",   2, 16, 16,  32,  32, 3, 1),
+    ("c64_sw128",  2, 32, 32,  64,  64, 3, 1),
+    ("c16_sw32",   1, 64, 64,  16,  32, 3, 1),
+    ("c96_k32",    1, 64, 64,  96,  64, 1, 1),
+    ("c128_n384",  3,  8,  8, 128, 384, 1, 1),
+    ("c128_3x3_8", 5,  8,  8, 128, 128, 3, 1),
+    ("c256_n128",  2,  8,  8, 256, 128, 3, 1),
+    ("s2_64",      2, 32, 32,  64,  64, 3, 2),
+    ("s2_32_big",  3, 64, 64,  32,  32, 3, 2),
+    ("n512",       1,  8,  8,  16, 512, 3, 1),
+    ("rect",       1, 64, 128, 32,  64, 3, 1),
+]
+
+
+@pytest.mark.parametrize("name,B,H,W,Cin,Cout,k,stride", CASES, ids=[c[0] for c in CASES])
+def test_conv_matches_torch(name, B, H, W, Cin, Cout, k, stride):
+    x = _rand(B, Cin, H, W, seed=1)
+    w = _rand(Cout, Cin, k, k, seed=2, scale=1.0 / math.sqrt(Cin * k * k))
+    bias = _rand(Cout, seed=3)
+    xa = nhwc_bf16(x)
+    wp = pack_w(w)
+    out, _ = gemm([xa], [wp], Cout, taps=[k * k], stride=stride, bias=bias)
+    ref = F.conv2d(to_nchw_f32(xa), w.to(torch.bfloat16).float(), bias, stride=stride, padding=k // 2)
+    _close(to_nchw_f32(out), ref, name)
+
+
+def test_direct_conv_checker_agrees():
+    B, H, W, Cin, Cout = 2, 16, 16, 32, 48
+    x, w, bias = _rand(B, Cin, H, W, seed=4), _rand(Cout, Cin, 3, 3, seed=5, scale=0.06), _rand(Cout, seed=6)
+    xa, wp = nhwc_bf16(x), pack_w(w)
+    out = torch.zeros(B, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    _lib.launch("ddif_conv_direct_t", stream(), **{"in": xa.data_ptr()}, in_ld=Cin, cin=Cin, in_h=H, in_w=W, w=wp.data_ptr(), w_k=Cin,
+                taps=9, stride=1, bias=bias.data_ptr(), out=out.data_ptr(), out_ld=Cout, batch=B, out_h=H, out_w=W, n_valid=Cout,
+                n_pad=48, act=0)
+    tc, _ = gemm([xa], [wp], Cout, taps=[9], bias=bias)
+    torch.cuda.synchronize()
+    _close(to_nchw_f32(out), to_nchw_f32(tc), "direct vs tcgen05")
+
+
+def test_epilogue_all_options():
+    """bias + FiLM + CSM modulation + residual + SiLU + GroupNorm statistics, and the fp32 NCHW store."""
+    B, H, W, Cin, Cout = 3, 16, 16, 64, 32
+    x, w = _rand(B, Cin, H, W, seed=7), _rand(Cout, Cin, 1, 1, seed=8, scale=0.12)
+    bias, film = _rand(Cout, seed=9), _rand(B, 100, seed=10)
+    mod = nhwc_bf16(_rand(B, 2 * Cout, H, W, seed=11, scale=0.5))
+    res = nhwc_bf16(_rand(B, Cout, H, W, seed=12))
+    xa, wp = nhwc_bf16(x), pack_w(w)
+    film_view = film[:, 20:]  # offset view with row pitch 100: pass base pointer of the slice and ld=100
+
+    class _F:  # tiny shim so gemm() sees data_ptr()/shape of the strided view
+        def __init__(self, t, ld):
+            self.t, self.shape = t, (t.shape[0], ld)
+
+        def data_ptr(self):
+            return self.t.data_ptr()
+
+    conv = F.conv2d(to_nchw_f32(xa), w.to(torch.bfloat16).float(), bias) + film[:, 20:20 + Cout, None, None]
+    sc, sh = to_nchw_f32(mod)[:, :Cout], to_nchw_f32(mod)[:, Cout:]
+    pre = conv * (1 + sc) + sh + to_nchw_f32(res)
+    for act in (0, 1):
+        ref = F.silu(pre) if act else pre
+        out, stats = gemm([xa], [wp], Cout, taps=[1], bias=bias, film=_F(film_view, 100), mod=mod, residual=res, act=act, want_stats=True)
+        _close(to_nchw_f32(out), ref, f"epilogue act={act}")
+        s_ref = torch.stack([ref.double().sum(dim=(1, 2, 3)), (ref.double() ** 2).sum(dim=(1, 2, 3))], dim=1)
+        assert torch.allclose(stats, s_ref, rtol=2e-3, atol=0.5), (stats, s_ref)
+    out, _ = gemm([xa], [pack_w(w[:8])], 8, taps=[1], bias=bias[:8], want_nchw=True)
+    ref8 = F.conv2d(to_nchw_f32(xa), w[:8].to(torch.bfloat16).float(), bias[:8])
+    assert rel_err(out, ref8) < 1e-4  # fp32 store: only accumulation-order error
+
+
+@pytest.mark.parametrize("H", [8, 16, 32])
+def test_dual_segment_per_sample_weights(H):
+    """attn_out(W_eff[b] q) + attn_res(x_hat): two K segments, first with per-sample weights (64- and 128-row tiles)."""
+    B, dim, o = 3, 96, 64
+    q, xh = _rand(B, dim, H, H, seed=13), _rand(B, dim, H, H, seed=14)
+    weff = (_rand(B, o, dim, seed=15, scale=0.1)).to(torch.bfloat16).contiguous()
+    wres = _rand(o, dim, 1, 1, seed=16, scale=0.1)
+    bias = _rand(o, seed=17)
+    qa, xa = nhwc_bf16(q), nhwc_bf16(xh)
+    out, _ = gemm([qa, xa], [weff, pack_w(wres)], o, taps=[1, 1], bias=bias, per_sample=[1, 0])
+    ref = torch.einsum("bok,bkhw->bohw", weff.float(), to_nchw_f32(qa)) + F.conv2d(to_nchw_f32(xa), wres.to(torch.bfloat16).float(), bias)
+    _close(to_nchw_f32(out), ref, f"dual H={H}")
+
+
+def test_bad_arguments_return_errors():
+    x = nhwc_bf16(_rand(1, 32, 16, 16))
+    w = pack_w(_rand(32, 32, 3, 3))
+    with pytest.raises(RuntimeError):
+        gemm([x], [w], 32, taps=[4])           # taps must be 1 or 9
+    with pytest.raises(RuntimeError):
+        gemm([x], [w], 32, taps=[9], stride=3)  # stride 1|2
+    with pytest.raises(RuntimeError):
+        gemm([nhwc_bf16(_rand(1, 24, 16, 16))], [w], 32, taps=[9])  # Cin % 16

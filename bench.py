@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""Benchmark of the DDIF denoising hot path on B200 (see the contract in DESIGN.md §Measurement).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+
+Workload (BASELINE.json configs[1]): WV3-shaped synthetic 64x64 8-band patches, batch 256 PER GPU, full DDPM
+sampling loop (cosine schedule, T = 500, clip to (0,1), x_start prediction, self-conditioning on the current image),
+bf16 UNet internals / fp32 sampler state.  One "step" = one complete sampling of the batch: cond cache build +
+500 x (UNet forward + fused posterior step) + final clip(sample + lms).  `value` = patches/s over all ranks with
+inputs resident in HBM; `e2e` = the same through the public API with the conditioning coming from pinned host
+memory and the fused images copied back to the host every step.  Multi-GPU: one process per GPU (torchrun), patches
+sharded, no data-path collective, final NCCL all_gather of the finished patches inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "WV3 64x64 patches/s (full DDPM-500 sampling)"
+UNIT = "patches/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="patches per GPU")
+    ap.add_argument("--timesteps", type=int, default=500)
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], 0, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx or None, power_w_max=max(pw) if pw else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def cpu_reference_run(cpu_batch: int, timesteps: int, steps: int, warmup: int):
+    """The reference algorithm (oracle port: torch CPU fp32 restatement pinned to the reference's golden vectors) on all
+    host cores: each step = ONE denoise step (UNet forward + DDPM posterior) of `cpu_batch` WV3 patches; patches/s is
+    extrapolated to the full T-step sampling (a full run takes ~1 minute per patch)."""
+    import torch
+    from dif_pan_b200 import synth
+    from oracle import sampler_oracle as so, unet_oracle as uo
+
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kw = synth.unet_kwargs("wv3")
+    sd = synth.make_state_dict(0, **kw)
+    kw2 = dict(kw)
+    kw2.pop("dropout")
+    cfg = uo.UNetCfg(**kw2)
+    cond = synth.make_batch("wv3", cpu_batch, seed=1)["cond"]
+    sb = so.schedule_buffers(so.make_beta_schedule("cosine", timesteps))
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(cpu_batch, 8, 64, 64, generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t = torch.full((cpu_batch,), timesteps - 1 - i, dtype=torch.long)
+        nz = torch.randn(cpu_batch, 8, 64, 64, generator=g)
+        t0 = time.perf_counter()
+        out = uo.unet_forward(sd, cfg, x, t, cond, x)
+        x = so.ddpm_step(sb, x, t, out, cond[:, :8], nz)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times[warmup:]) / steps
+    value = cpu_batch / (timesteps * dt)
+    return dict(value=value, unit=UNIT, cores=cores, kind="port", ms_per_denoise_step=dt * 1e3,
+                sample=f"{steps} denoise steps (oracle UNet forward + DDPM posterior) at batch {cpu_batch}, fp32, {cores} threads; "
+                       f"patches/s extrapolated to T={timesteps}")
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(a.cpu_batch, a.timesteps, max(a.steps, 1), a.warmup)
+        line = dict(impl="reference", metric=METRIC, value=r["value"], unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=r["ms_per_denoise_step"] * a.timesteps * (a.batch / a.cpu_batch), higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload="WV3 64x64x8 patches, DDPM cosine T=%d, CPU oracle port (reference algorithm)" % a.timesteps,
+                                cpu_batch=a.cpu_batch, timesteps=a.timesteps),
+                    cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"]),
+                    e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import dif_pan_b200 as dp
+    from dif_pan_b200 import synth
+
+    torch.set_grad_enabled(False)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = a.batch, a.timesteps
+    kw = synth.unet_kwargs("wv3")
+    net = dp.UNetSR3(**kw)
+    net.load_state_dict(synth.make_state_dict(0, **kw))
+    net = net.to(dev).eval()
+    dif = dp.GaussianDiffusion(net, image_size=64, channels=8, pred_mode="x_start", loss_type="l1", device=dev, clamp_range=(0, 1))
+    dif.set_new_noise_schedule(betas=dp.make_beta_schedule("cosine", T), device=dev)
+    dif = dif.to(dev)
+    # synthetic conditioning: 16 distinct image-like samples tiled to the batch (rank-dependent seed), pinned on the host
+    base = synth.make_batch("wv3", min(B, 16), seed=1000 + rank)["cond"]
+    cond_host = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous().pin_memory()
+    out_host = torch.empty(B, 8, 64, 64, dtype=torch.float32).pin_memory()
+    cond_dev = cond_host.to(dev)
+    gathered = [torch.empty(B, 8, 64, 64, device=dev) for _ in range(world)] if world > 1 else None
+    rt = net.runtime(B, 64, 64)
+
+    def one_sampling(e2e: bool, seed: int):
+        dif.seed = seed
+        if e2e:
+            c = cond_host.to(dev, non_blocking=True)  # fresh device tensor -> cond cache rebuilt, like a new batch
+        else:
+            c = cond_dev
+            rt.cond_key = None  # force the cond-cache build: it is part of every sampling
+        s = dif(c, mode="ddpm_sample")
+        sr = dp.fuse_output(s, c)
+        if world > 1:
+            dist.all_gather(gathered, sr)
+        if e2e:
+            out_host.copy_(sr, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return sr
+
+    def timed(e2e: bool, k: int):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            one_sampling(e2e, 100 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms)
+
+    for i in range(a.warmup):
+        one_sampling(i % 2 == 1, i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(False, a.steps)
+    ms_e2e = timed(True, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # roofline of the dominant kernel (conv_igemm_tc_kernel): per-launch CUDA events over one denoise step
+    roof = None
+    if rank == 0:
+        pk = peaks()
+        rows = rt.sch.fwd.profile(rt.stream)
+        rows = rt.sch.fwd.profile(rt.stream)
+        gm = [r for r in rows if r[1] == "ddif_gemm_t"]
+        g_ms, tot_ms = sum(r[2] for r in gm), sum(r[2] for r in rows)
+        import oracle.unet_oracle as uo  # FLOP count of the reference forward (algorithmic work), not on the product path
+        kw2 = dict(kw); kw2.pop("dropout")
+        conv_flops_ref = 8.268e9 * B  # conv FLOPs of one WV3 patch-forward (cond-only part included)
+        executed = sum(r[3] for r in gm)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("conv_igemm_tc_kernel_dram_bytes_per_launch")
+        ach = executed / (g_ms * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel="conv_igemm_tc_kernel", achieved=ach, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                    frac=ach / pk["bf16_tflops_sustained"], traffic=traffic, peak_source=pk["source"] + ":bf16_tflops_sustained",
+                    launches_per_denoise_step=len(gm), avg_launch_ms=g_ms / len(gm), share_of_step=g_ms / tot_ms,
+                    algorithmic_flops_per_step=executed, reference_conv_flops_per_step=conv_flops_ref,
+                    hbm=dict(achieved=sum(r[4] for r in gm) / (g_ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s",
+                             frac=sum(r[4] for r in gm) / (g_ms * 1e-3) / 1e9 / pk["hbm_gbs"]),
+                    unet_step_ms_events=tot_ms)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        r = cpu_reference_run(a.cpu_batch, T, 3, 1)
+        cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
+    if rank == 0:
+        total = B * world * a.steps
+        launches = a.steps * (T * (rt.launches_per_step() + 1) + len(rt.sch.cnd) + 2)
+        line = dict(metric=METRIC, value=total / (ms_dev * 1e-3), unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=ms_dev / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    config=dict(workload="BASELINE configs[1]: WV3 64x64x8 patches, batch %d per GPU, full DDPM loop cosine T=%d, clip (0,1), "
+                                         "x_start, self-cond" % (B, T), batch_per_gpu=B, timesteps=T, patches_total=B * world,
+                                l2_policy="inputs larger than L2 (per-step activation working set ~GBs >> 126 MB)",
+                                noise="in-kernel Philox4x32-10"),
+                    unet_ms_per_denoise_step=ms_dev / a.steps / T,
+                    e2e=dict(value=total / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=cond_host.numel() * 4, d2h_bytes_per_step=out_host.numel() * 4,
+                             ms_per_step=ms_e2e / a.steps),
+                    gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -629,15 +629,15 @@ class _Runtime:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def set_cond(self, cond: torch.Tensor, force: bool = False) -> None:
-        """Rebuild the cond cache if `cond` changed (identity: storage pointer + version + shape)."""
-        key = (cond.data_ptr(), cond._version, tuple(cond.shape))
-        if not force and key == self.cond_key:
+        """Rebuild the cond cache unless `cond` is the very tensor object cached last time and has not been written
+        since (object identity + version counter; the object is kept alive so its address cannot be recycled)."""
+        if not force and self.cond_key is not None and self.cond_key[0] is cond and self.cond_key[1] == cond._version:
             return
         if tuple(cond.shape) != tuple(self.cond_buf.shape):
             raise ValueError(f"cond must be {tuple(self.cond_buf.shape)}, got {tuple(cond.shape)}")
         self.cond_buf.copy_(cond)
         self.sch.cnd.run(self.stream)
-        self.cond_key = key
+        self.cond_key = (cond, cond._version)
 
     def step(self, explicit_self_cond: bool = False) -> None:
         """One UNet forward on the fixed buffers (x_buf, t_buf[, sc_buf]) -> out_buf."""

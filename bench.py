@@ -154,6 +154,7 @@ def main():
 
     import dif_pan_b200 as dp
     from dif_pan_b200 import synth
+    from dif_pan_b200.sharding import gather_patches
 
     torch.set_grad_enabled(False)
     torch.cuda.set_device(local)
@@ -173,7 +174,6 @@ def main():
     cond_host = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous().pin_memory()
     out_host = torch.empty(B, 8, 64, 64, dtype=torch.float32).pin_memory()
     cond_dev = cond_host.to(dev)
-    gathered = [torch.empty(B, 8, 64, 64, device=dev) for _ in range(world)] if world > 1 else None
     rt = net.runtime(B, 64, 64)
 
     def one_sampling(e2e: bool, seed: int):
@@ -186,7 +186,7 @@ def main():
         s = dif(c, mode="ddpm_sample")
         sr = dp.fuse_output(s, c)
         if world > 1:
-            dist.all_gather(gathered, sr)
+            sr = gather_patches(sr, B * world)[rank * B:(rank + 1) * B]  # final NCCL all_gather of the finished patches
         if e2e:
             out_host.copy_(sr, non_blocking=True)
             torch.cuda.current_stream().synchronize()

@@ -109,12 +109,16 @@ __device__ __forceinline__ void gn_norm8(const bf16* src, const float* a, const 
   }
 }
 
-__global__ void gn_apply_kernel(GnK p) {
+// One thread owns one 8-channel chunk for its whole lifetime (the grid-stride is a multiple of the chunk count), so
+// the per-channel affine (rstd*gamma, beta - mean*rstd*gamma) lives in registers and the loop has no division.
+static constexpr int kGnThreads = 192;  // divisible by every chunk count the UNet uses (4,8,12,16,24,32,64)
+
+template <bool DW>
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(GnK p) {
   const int b = blockIdx.y;
   const int C = p.c1 + p.c2;
   const int nchunk = C >> 3;
   const int HW = p.H * p.W;
-  // per-sample statistics of the (virtually) concatenated tensor
   double s = p.st1[2 * b], ss = p.st1[2 * b + 1];
   double n = (double)p.c1 * HW;
   if (p.c2) {
@@ -127,26 +131,57 @@ __global__ void gn_apply_kernel(GnK p) {
   if (var_d < 0) var_d = 0;
   const float mean = (float)mean_d;
   const float rstd = rsqrtf((float)var_d + p.eps);
-  const int64_t items = (int64_t)HW * nchunk;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
-    const int pix = (int)(i / nchunk);
-    const int ch = (int)(i - (int64_t)pix * nchunk) << 3;
-    float a[8], d[8];
+  const uint32_t stride_items = gridDim.x * kGnThreads;  // multiple of nchunk (checked on the host)
+  const uint32_t i0 = blockIdx.x * kGnThreads + threadIdx.x;
+  const int ch = (int)(i0 % (uint32_t)nchunk) << 3;
+  uint32_t pix = i0 / (uint32_t)nchunk;
+  const uint32_t dpix = stride_items / (uint32_t)nchunk;
+  float a[8], d[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a[j] = rstd * __ldg(p.gamma + ch + j);
-      d[j] = __ldg(p.beta + ch + j) - mean * a[j];
+  for (int j = 0; j < 8; ++j) {
+    a[j] = rstd * __ldg(p.gamma + ch + j);
+    d[j] = __ldg(p.beta + ch + j) - mean * a[j];
+  }
+  const bool first = ch < p.c1;
+  const int ld = first ? p.c1 : p.c2;
+  const bf16* src = (first ? p.src1 : p.src2) + (size_t)b * HW * ld + (first ? ch : ch - p.c1);
+  bf16* dst = p.out + (size_t)b * HW * C + ch;
+  bf16* dst_dw = p.out_dw ? p.out_dw + (size_t)b * HW * C + ch : nullptr;
+  float w[DW ? 9 : 1][8];
+  if (DW) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.dw_w + (size_t)tap * C + ch));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.dw_w + (size_t)tap * C + ch + 4));
+      w[tap][0] = w0.x; w[tap][1] = w0.y; w[tap][2] = w0.z; w[tap][3] = w0.w;
+      w[tap][4] = w1.x; w[tap][5] = w1.y; w[tap][6] = w1.z; w[tap][7] = w1.w;
     }
-    const bool first = ch < p.c1;
-    const bf16* base = first ? p.src1 : p.src2;
-    const int ld = first ? p.c1 : p.c2;
-    const int cc = first ? ch : ch - p.c1;
-    const size_t img = (size_t)b * HW;
+  }
+  if (!DW) {
+    // 4 independent 16-byte loads in flight per thread before any use
+    for (; pix + 3 * dpix < (uint32_t)HW; pix += 4 * dpix) {
+      bf16x8 in[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) in[u] = *reinterpret_cast<const bf16x8*>(src + (size_t)(pix + u * dpix) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8], y[8];
+        unpack8(in[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = v[j] * a[j] + d[j];
+          y[j] = p.act ? __fdividef(t, 1.0f + __expf(-t)) : t;
+        }
+        *reinterpret_cast<bf16x8*>(dst + (size_t)(pix + u * dpix) * C) = pack8(y);
+      }
+    }
+  }
+  for (; pix < (uint32_t)HW; pix += dpix) {
     float y[8];
-    gn_norm8(base + (img + pix) * ld + cc, a, d, p.act, y);
-    *reinterpret_cast<bf16x8*>(p.out + (img + pix) * C + ch) = pack8(y);
-    if (p.dw_w) {
-      const int py = pix / p.W, px = pix - py * p.W;
+    gn_norm8(src + (size_t)pix * ld, a, d, p.act, y);
+    *reinterpret_cast<bf16x8*>(dst + (size_t)pix * C) = pack8(y);
+    if (DW) {
+      const int py = (int)(pix / (uint32_t)p.W), px = (int)pix - py * p.W;
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -159,14 +194,12 @@ __global__ void gn_apply_kernel(GnK p) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) z[j] = y[j];
         } else {
-          gn_norm8(base + (img + (size_t)yy * p.W + xx) * ld + cc, a, d, p.act, z);
+          gn_norm8(src + ((size_t)yy * p.W + xx) * ld, a, d, p.act, z);
         }
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.dw_w + (size_t)tap * C + ch));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.dw_w + (size_t)tap * C + ch + 4));
-        acc[0] += w0.x * z[0]; acc[1] += w0.y * z[1]; acc[2] += w0.z * z[2]; acc[3] += w0.w * z[3];
-        acc[4] += w1.x * z[4]; acc[5] += w1.y * z[5]; acc[6] += w1.z * z[6]; acc[7] += w1.w * z[7];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += w[tap][j] * z[j];
       }
-      *reinterpret_cast<bf16x8*>(p.out_dw + (img + pix) * C + ch) = pack8(acc);
+      *reinterpret_cast<bf16x8*>(dst_dw + (size_t)pix * C) = pack8(acc);
     }
   }
 }
@@ -174,13 +207,20 @@ int launch_gn_apply(const ddif_gn_apply_t& p, cudaStream_t s) {
   if (p.c1 % 8 != 0 || p.c2 % 8 != 0 || p.c1 <= 0) return DDIF_ERR_SHAPE;
   if (p.c2 && (!p.src2 || !p.stats2)) return DDIF_ERR_ARG;
   if (p.dw_w && !p.out_dw) return DDIF_ERR_ARG;
+  const int nchunk = (int)((p.c1 + p.c2) / 8);
+  if (kGnThreads % nchunk != 0) return DDIF_ERR_SHAPE;  // channel counts are multiples of 8 dividing 1536
   GnK k{(const bf16*)p.src1, (const bf16*)p.src2, (int)p.c1, (int)p.c2, p.stats1, p.stats2, p.gamma, p.beta,
         (bf16*)p.out, p.dw_w, (bf16*)p.out_dw, (int)p.h, (int)p.w, (int)p.act, (float)p.eps};
-  const int64_t items = p.h * p.w * ((p.c1 + p.c2) / 8);
-  int gx = grid_for(items, 256, 148 * 8);
-  int cap = (int)ceil_div(148 * 16, p.batch);
-  if (gx > cap && cap >= 1) gx = cap;
-  gn_apply_kernel<<<dim3(gx, (unsigned)p.batch), 256, 0, s>>>(k);
+  const int64_t items = p.h * p.w * nchunk;
+  // ~8 items per thread, at most ~32 CTAs per SM over the whole launch
+  int64_t gx = ceil_div(items, (int64_t)kGnThreads * 8);
+  const int64_t cap = ceil_div((int64_t)148 * 32, p.batch);
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  if (p.dw_w)
+    gn_apply_kernel<true><<<dim3((unsigned)gx, (unsigned)p.batch), kGnThreads, 0, s>>>(k);
+  else
+    gn_apply_kernel<false><<<dim3((unsigned)gx, (unsigned)p.batch), kGnThreads, 0, s>>>(k);
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }

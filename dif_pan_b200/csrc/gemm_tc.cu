@@ -26,15 +26,18 @@ struct alignas(64) GemmKParams {
   int batch, out_h, out_w;
   int tw, th, tn;          // pixel box
   int tiles_x, tiles_y;    // tiles per image
+  int num_m_tiles;         // tiles_x * tiles_y * ceil(batch / tn)
   int a_rows;              // rows TMA fills per stage (tw*th*tn, 64 or 128)
   int bn;                  // N per CTA
   int n_valid;
   int bk;                  // K elements per stage (16/32/64)
   int span;                // bytes per smem row = bk*2
-  int stages;
+  int stages;              // A (and streamed-B) ring depth
+  int resident_b;          // 1: all weight slabs of this CTA's N tile stay in smem for the CTA's lifetime
+  int b_slots;             // resident_b ? total K iterations : stages
   uint32_t idesc;
   uint32_t layout_type;
-  uint32_t tmem_cols;
+  uint32_t tmem_cols;      // 2 accumulators of bn columns, rounded to a power of two >= 32
   const float* bias;
   const float* film;
   int film_ld;
@@ -48,36 +51,54 @@ struct alignas(64) GemmKParams {
   double* stats;
 };
 
-static constexpr int kGemmThreads = 192;
+static constexpr int kEpiWarps = 16;                      // 4 TMEM lane quarters x 4 column groups
+static constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warps 2..17 epilogue
 
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+               "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void unpack16(const uint32_t* r, float* f) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r[i]));
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent, warp-specialised: each CTA owns one N tile (blockIdx.y) and walks M tiles blockIdx.x, +gridDim.x, ...
+// Three pipelines: smem full/empty ring (TMA <-> MMA) running ACROSS tiles, TMEM full/empty (MMA <-> epilogue, two
+// accumulators so tile i's epilogue overlaps tile i+1's MMAs), and the static tile walk.
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // carve: [barriers | pad to 1024 | A stages | B stages]
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const int a_stage_bytes = 128 * p.span;
-  const int b_stage_bytes = p.bn * p.span;
+  const int b_slot_bytes = p.bn * p.span;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.stages * a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_slots * b_slot_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
-  uint64_t* tmem_full_bar = bars + 2 * p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+  uint64_t* tmem_full_bar = bars + 2 * p.stages;       // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * p.stages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int m_tile = blockIdx.x;
   const int n_tile = blockIdx.y;
-  const int img_grp = m_tile / tiles_per_img;
-  const int t_in = m_tile - img_grp * tiles_per_img;
-  const int ty0 = (t_in / p.tiles_x) * p.th;
-  const int tx0 = (t_in % p.tiles_x) * p.tw;
-  const int n0 = img_grp * p.tn;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
@@ -91,7 +112,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
         mbar_init(&full_bar[i], 1);
         mbar_init(&empty_bar[i], 1);
       }
-      mbar_init(tmem_full_bar, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full_bar[i], 1);
+        mbar_init(&tmem_empty_bar[i], kEpiWarps);  // one arrive per epilogue warp
+      }
       mbar_fence_init();
     }
     __syncwarp();
@@ -109,22 +133,35 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)(p.a_rows * p.span + b_stage_bytes);
-      int it = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        for (int tap = 0; tap < p.taps[s]; ++tap) {
-          const int dy = (p.taps[s] == 9) ? tap / 3 : 0;
-          const int dx = (p.taps[s] == 9) ? tap % 3 : 0;
-          const int cw = tx0 * p.stride + dx - p.pad[s];
-          const int ch = ty0 * p.stride + dy - p.pad[s];
-          const int bz = p.b_per_sample[s] ? n0 : tap;
-          for (int kc = 0; kc < p.kchunks[s]; ++kc, ++it) {
-            const int stage = it % p.stages;
-            const uint32_t phase = (uint32_t)(it / p.stages) & 1u;
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_expect_tx(&full_bar[stage], tx_bytes);
-            tma_load_4d(&p.tmA[s], &full_bar[stage], smem_a + (size_t)stage * a_stage_bytes, kc * p.bk, cw, ch, n0);
-            tma_load_3d(&p.tmB[s], &full_bar[stage], smem_b + (size_t)stage * b_stage_bytes, kc * p.bk, n_tile * p.bn, bz);
+      const uint32_t a_bytes = (uint32_t)(p.a_rows * p.span);
+      uint32_t it = 0;
+      bool first = true;
+      for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x, first = false) {
+        const int img_grp = m_tile / tiles_per_img;
+        const int t_in = m_tile - img_grp * tiles_per_img;
+        const int ty0 = (t_in / p.tiles_x) * p.th;
+        const int tx0 = (t_in % p.tiles_x) * p.tw;
+        const int n0 = img_grp * p.tn;
+        const bool load_b = !p.resident_b || first;
+        int j = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          for (int tap = 0; tap < p.taps[s]; ++tap) {
+            const int dy = (p.taps[s] == 9) ? tap / 3 : 0;
+            const int dx = (p.taps[s] == 9) ? tap % 3 : 0;
+            const int cw = tx0 * p.stride + dx - p.pad[s];
+            const int ch = ty0 * p.stride + dy - p.pad[s];
+            const int bz = p.b_per_sample[s] ? n0 : tap;
+            for (int kc = 0; kc < p.kchunks[s]; ++kc, ++it, ++j) {
+              const uint32_t stage = it % (uint32_t)p.stages;
+              const uint32_t phase = (it / (uint32_t)p.stages) & 1u;
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_expect_tx(&full_bar[stage], a_bytes + (load_b ? (uint32_t)b_slot_bytes : 0u));
+              tma_load_4d(&p.tmA[s], &full_bar[stage], smem_a + (size_t)stage * a_stage_bytes, kc * p.bk, cw, ch, n0);
+              if (load_b) {
+                const int slot = p.resident_b ? j : (int)stage;
+                tma_load_3d(&p.tmB[s], &full_bar[stage], smem_b + (size_t)slot * b_slot_bytes, kc * p.bk, n_tile * p.bn, bz);
+              }
+            }
           }
         }
       }
@@ -134,88 +171,143 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
     if (lane == 0) {
       const uint32_t sbo = 8u * (uint32_t)p.span;
       const int ksteps = p.bk / 16;
-      for (int it = 0; it < total_iters; ++it) {
-        const int stage = it % p.stages;
-        const uint32_t phase = (uint32_t)(it / p.stages) & 1u;
-        mbar_wait(&full_bar[stage], phase);
+      uint32_t it = 0, tcount = 0;
+      for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1u, acc_phase = (tcount >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint64_t da = make_smem_desc(smem_u32(smem_a + (size_t)stage * a_stage_bytes), sbo, p.layout_type);
-        const uint64_t db = make_smem_desc(smem_u32(smem_b + (size_t)stage * b_stage_bytes), sbo, p.layout_type);
-        for (int k = 0; k < ksteps; ++k) {
-          // advance 16 K-elements = 32 bytes inside the swizzle span (start address field is in 16-byte units)
-          umma_bf16_ss(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (it | k) != 0 ? 1u : 0u);
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.bn;
+        for (int j = 0; j < total_iters; ++j, ++it) {
+          const uint32_t stage = it % (uint32_t)p.stages;
+          const uint32_t phase = (it / (uint32_t)p.stages) & 1u;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const int slot = p.resident_b ? j : (int)stage;
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + (size_t)stage * a_stage_bytes), sbo, p.layout_type);
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + (size_t)slot * b_slot_bytes), sbo, p.layout_type);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (j | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full_bar[acc]);
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..17) =====================
+    // warp -> (TMEM lane quarter q = warp % 4, column group cg): thread = one output pixel x (bn / ngroups) channels.
+    // Global operands of the first 16-column chunk (residual / CSM scale+shift) are fetched BEFORE waiting for the
+    // accumulator, so their latency hides behind the MMAs of the tile.
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int nchunks = p.bn >> 4;  // 16-column chunks of the accumulator; group cg owns chunks cg, cg+4, cg+8, ...
     const int row = q * 32 + lane;
     const int px_per_img = p.tw * p.th;
     const int tn_i = row / px_per_img;
     const int r_in = row - tn_i * px_per_img;
-    const int y = ty0 + r_in / p.tw;
-    const int x = tx0 + r_in % p.tw;
-    const int b = n0 + tn_i;
-    const bool row_ok = (row < p.a_rows) && (b < p.batch) && (y < p.out_h) && (x < p.out_w);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    float s1 = 0.f, s2 = 0.f;
-    const size_t pix = ((size_t)b * p.out_h + y) * p.out_w + x;
-    if (q * 32 < p.a_rows) {
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+    const int ry = r_in / p.tw, rx = r_in % p.tw;
+    const bool wide_io = (p.out_ld % 16 == 0) && (p.res_ld % 16 == 0) && (p.n_valid % 16 == 0);
+    const bool active = (cg < nchunks) && (q * 32 < p.a_rows);
+    uint32_t tcount = 0;
+    for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x, ++tcount) {
+      const int img_grp = m_tile / tiles_per_img;
+      const int t_in = m_tile - img_grp * tiles_per_img;
+      const int y = (t_in / p.tiles_x) * p.th + ry;
+      const int x = (t_in % p.tiles_x) * p.tw + rx;
+      const int n0 = img_grp * p.tn;
+      const int b = n0 + tn_i;
+      const bool row_ok = active && (row < p.a_rows) && (b < p.batch) && (y < p.out_h) && (x < p.out_w);
+      const size_t pix = ((size_t)b * p.out_h + y) * p.out_w + x;
+      const int c_first = cg * 16;
+      uint32_t pre_res[8], pre_sc[8], pre_sh[8];
+      {
+        const int ng = n_tile * p.bn + c_first;
+        const bool full16 = wide_io && row_ok && (p.n_valid - ng >= 16);
+        if (full16 && p.residual) ldg256(p.residual + pix * (size_t)p.res_ld + ng, pre_res);
+        if (full16 && p.mod) {
+          const bf16* m = p.mod + pix * (size_t)(2 * p.n_valid) + ng;
+          ldg256(m, pre_sc);
+          ldg256(m + p.n_valid, pre_sh);
+        }
+      }
+      const uint32_t acc = tcount & 1u, acc_phase = (tcount >> 1) & 1u;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      float s1 = 0.f, s2 = 0.f;
+      for (int cc = cg; cc < nchunks || cc == cg; cc += 4) {
+        const int c0 = cc * 16;
         uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        tmem_ld_wait();
+        if (active) {
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.bn + (uint32_t)c0, r);
+          tmem_ld_wait();
+        }
+        if (cc + 4 >= nchunks) {
+          // this warp's TMEM reads of the accumulator are done: hand it back to the MMA warp before the math/stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
         const int ng = n_tile * p.bn + c0;  // global output channel of r[0]
         if (row_ok && ng < p.n_valid) {
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
           const int nrem = p.n_valid - ng;  // >= 1
+          const bool full16 = wide_io && nrem >= 16;
           if (p.bias) {
+            if (nrem >= 16) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < nrem) v[j] += __ldg(p.bias + ng + j);
+              for (int j = 0; j < 16; j += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + ng + j));
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              }
+            } else {
+              for (int j = 0; j < nrem; ++j) v[j] += __ldg(p.bias + ng + j);
+            }
           }
           if (p.film) {
             const float* f = p.film + (size_t)b * p.film_ld + ng;
+            if (nrem >= 16 && (p.film_ld % 4 == 0)) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < nrem) v[j] += __ldg(f + j);
+              for (int j = 0; j < 16; j += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(f + j));
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              }
+            } else {
+              for (int j = 0; j < 16 && j < nrem; ++j) v[j] += __ldg(f + j);
+            }
           }
           if (p.mod) {
             const bf16* m = p.mod + pix * (size_t)(2 * p.n_valid) + ng;
-            if (nrem >= 16) {
+            if (full16) {
+              if (cc != cg) {
+                ldg256(m, pre_sc);
+                ldg256(m + p.n_valid, pre_sh);
+              }
               float sc[16], sh[16];
-              unpack8(*reinterpret_cast<const bf16x8*>(m), sc);
-              unpack8(*reinterpret_cast<const bf16x8*>(m + 8), sc + 8);
-              unpack8(*reinterpret_cast<const bf16x8*>(m + p.n_valid), sh);
-              unpack8(*reinterpret_cast<const bf16x8*>(m + p.n_valid + 8), sh + 8);
+              unpack16(pre_sc, sc);
+              unpack16(pre_sh, sh);
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = v[j] * (1.0f + sc[j]) + sh[j];
             } else {
-              for (int j = 0; j < nrem; ++j)
+              for (int j = 0; j < 16 && j < nrem; ++j)
                 v[j] = v[j] * (1.0f + __bfloat162float(m[j])) + __bfloat162float(m[p.n_valid + j]);
             }
           }
           if (p.residual) {
             const bf16* rs = p.residual + pix * (size_t)p.res_ld + ng;
-            if (nrem >= 16) {
+            if (full16) {
+              if (cc != cg) ldg256(rs, pre_res);
               float rr[16];
-              unpack8(*reinterpret_cast<const bf16x8*>(rs), rr);
-              unpack8(*reinterpret_cast<const bf16x8*>(rs + 8), rr + 8);
+              unpack16(pre_res, rr);
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] += rr[j];
             } else {
-              for (int j = 0; j < nrem; ++j) v[j] += __bfloat162float(rs[j]);
+              for (int j = 0; j < 16 && j < nrem; ++j) v[j] += __bfloat162float(rs[j]);
             }
           }
           if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+            for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
           }
           if (p.stats) {
 #pragma unroll
@@ -227,7 +319,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
           }
           if (p.out) {
             bf16* o = p.out + pix * (size_t)p.out_ld + ng;
-            if (nrem >= 16) {
+            if (full16) {
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&t);
+              }
+              stg256(o, w);
+            } else if (nrem >= 16) {
               *reinterpret_cast<bf16x8*>(o) = pack8(v);
               *reinterpret_cast<bf16x8*>(o + 8) = pack8(v + 8);
             } else {
@@ -241,7 +341,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
           }
         }
       }
-      if (p.stats) {
+      if (p.stats && active) {
         // all rows of one warp belong to one sample (px_per_img is 64 or 128)
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
@@ -334,19 +434,41 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   p.bn = bn;
   p.n_valid = (int)g.n_valid;
   uint32_t cols = 32;
-  while ((int)cols < bn) cols <<= 1;
+  while ((int)cols < 2 * bn) cols <<= 1;  // two accumulators
   p.tmem_cols = cols;
   // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at bit 17, M>>4 at bit 24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const int stage_bytes = (128 + bn) * p.span;
-  int stages = (96 * 1024) / stage_bytes;
-  if (stages < 3) stages = (200 * 1024) / stage_bytes;
+  int total_iters = 0;
+  for (int s = 0; s < g.nseg; ++s) total_iters += (int)(g.taps[s] * (g.a_c[s] / bk));
+  const int a_stage = 128 * p.span, b_slot = bn * p.span;
+  const int budget = 200 * 1024;
+  // weights of this N tile stay resident in smem when they fit next to >= 4 A stages (never for per-sample weights)
+  p.resident_b = (!per_sample && (int64_t)total_iters * b_slot + 4 * a_stage <= budget) ? 1 : 0;
+  int stages;
+  if (p.resident_b) {
+    p.b_slots = total_iters;
+    stages = (budget - total_iters * b_slot) / a_stage;
+  } else {
+    stages = budget / (a_stage + b_slot);
+    p.b_slots = stages;
+  }
   if (stages > 8) stages = 8;
   if (stages < 2) return DDIF_ERR_SHAPE;
+  if (!p.resident_b) p.b_slots = stages;
   p.stages = stages;
-  L.smem_bytes = stages * stage_bytes + (2 * stages + 2) * 8 + 1024;
-  L.grid_x = p.tiles_x * p.tiles_y * (int)ceil_div(B, tn);
+  p.num_m_tiles = p.tiles_x * p.tiles_y * (int)ceil_div(B, tn);
+  L.smem_bytes = stages * a_stage + p.b_slots * b_slot + (2 * stages + 6) * 8 + 1024;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      sms = n;
+    else
+      sms = 148;
+  }
   L.grid_y = (int)(g.n_pad / bn);
+  const int gx = (sms + L.grid_y - 1) / L.grid_y;  // persistent: ~one CTA per SM in total
+  L.grid_x = p.num_m_tiles < gx ? p.num_m_tiles : gx;
 
   const CUtensorMapSwizzle sw = swizzle_for_span(p.span);
   for (int s = 0; s < g.nseg; ++s) {

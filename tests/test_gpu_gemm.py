@@ -38,6 +38,10 @@ CASES = [
     ("s2_32_big",  3, 64, 64,  32,  32, 3, 2),
     ("n512",       1,  8,  8,  16, 512, 3, 1),
     ("rect",       1, 64, 128, 32,  64, 3, 1),
+    ("n96",        1, 64, 64,  64,  96, 1, 1),
+    ("n192",       2, 16, 16,  32, 192, 3, 1),
+    ("n48",        2, 16, 16,  32,  48, 3, 1),
+    ("many_tiles", 40, 32, 32, 32,  32, 3, 1),   # > 148 CTAs: every persistent CTA walks several tiles
 ]
 
 

@@ -13,7 +13,7 @@ from typing import Dict
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(_ROOT, "include", "ddif_b200.h")
-LIB_PATH = os.path.join(_HERE, "libddif_b200.so")
+LIB_PATH = os.environ.get("DDIF_LIB", os.path.join(_HERE, "libddif_b200.so"))  # DDIF_LIB: tuning variants (tools/)
 
 
 def _parse_header(path: str):

@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["gemm_tc.cu", "elementwise.cu", "sampler.cu", "capi.cu"]
+SOURCES = ["gemm_tc.cu", "conv3x3_tc.cu", "elementwise.cu", "sampler.cu", "capi.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libddif_b200.so")
 
 
@@ -19,12 +19,13 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """`defines` / `out` build tuning variants next to the product library (tools/ only)."""
+    if not force and not defines and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-           "-Xcompiler", "-fPIC", "--cudart", "shared", "-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
+           "-Xcompiler", "-fPIC", "--cudart", "shared", "-o", out] + [f"-D{d}" for d in defines] + [os.path.join(HERE, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -33,8 +34,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force=True, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else OUT))

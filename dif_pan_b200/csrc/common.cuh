@@ -50,6 +50,13 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
   return p;
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// swish(t) = t*sigmoid(t) = h*tanh(h) + h with h = t/2: ONE MUFU (tanh.approx, abs err ~2^-11) instead of EX2 + RCP.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float swish_half(float h) { return fmaf(h, tanh_approx(h), h); }  // argument is t/2
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -93,10 +100,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (kernel error) instead of hanging the GPU.
+// Bounded wait: a protocol bug must trap (kernel error) instead of hanging the GPU.  try_wait itself may block for a
+// driver-defined time slice, so the bound is wall-clock (%globaltimer, ns): 2 s without progress -> trap.
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 26)) __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_ns();
+  for (uint32_t spin = 1; !mbar_try_wait(bar, parity); ++spin) {
+    if ((spin & 255u) == 0u && global_ns() - t0 > 2000000000ull) __trap();
   }
 }
 
@@ -135,6 +150,41 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Lean issue path used by the conv kernels: the WHOLE warp executes these (converged), one elected lane issues.  KSTEPS
+// back-to-back K=16 MMAs on descriptors advanced by 32 bytes each; `acc_first` = accumulate flag of the first one.
+template <int KSTEPS>
+__device__ __forceinline__ void umma_bf16_ss_steps(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc_first) {
+  static_assert(KSTEPS == 1 || KSTEPS == 2 || KSTEPS == 4, "K steps per slab");
+  if constexpr (KSTEPS == 1) {
+    asm volatile(
+        "{\n\t.reg .pred pe, p;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc_first)
+        : "memory");
+  } else if constexpr (KSTEPS == 2) {
+    asm volatile(
+        "{\n\t.reg .pred pe, p, pt;\n\t.reg .b64 a1, b1;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 pt, %3, %3;\n\t"
+        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc_first)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred pe, p, pt;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\telect.sync _|pe, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 pt, %3, %3;\n\t"
+        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\tadd.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc_first)
+        : "memory");
+  }
+}
+// tcgen05.commit by one elected lane of a converged warp.
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
       : "memory");
 }
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.

@@ -104,8 +104,8 @@ __device__ __forceinline__ void gn_norm8(const bf16* src, const float* a, const 
   unpack8(*reinterpret_cast<const bf16x8*>(src), v);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float t = v[j] * a[j] + d[j];
-    y[j] = act ? t / (1.0f + __expf(-t)) : t;
+    const float t = fmaf(v[j], a[j], d[j]);  // a, d are pre-halved when act (see gn_apply_kernel)
+    y[j] = act ? swish_half(t) : t;
   }
 }
 
@@ -137,10 +137,11 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(GnK p) {
   uint32_t pix = i0 / (uint32_t)nchunk;
   const uint32_t dpix = stride_items / (uint32_t)nchunk;
   float a[8], d[8];
+  const float hs = p.act ? 0.5f : 1.0f;  // swish(t) = h*tanh(h) + h with h = t/2
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    a[j] = rstd * __ldg(p.gamma + ch + j);
-    d[j] = __ldg(p.beta + ch + j) - mean * a[j];
+    a[j] = hs * rstd * __ldg(p.gamma + ch + j);
+    d[j] = hs * __ldg(p.beta + ch + j) - mean * a[j];
   }
   const bool first = ch < p.c1;
   const int ld = first ? p.c1 : p.c2;
@@ -169,8 +170,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(GnK p) {
         unpack8(in[u], v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float t = v[j] * a[j] + d[j];
-          y[j] = p.act ? __fdividef(t, 1.0f + __expf(-t)) : t;
+          const float t = fmaf(v[j], a[j], d[j]);
+          y[j] = p.act ? swish_half(t) : t;
         }
         *reinterpret_cast<bf16x8*>(dst + (size_t)(pix + u * dpix) * C) = pack8(y);
       }

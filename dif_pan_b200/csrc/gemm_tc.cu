@@ -11,6 +11,7 @@
 // (tcgen05.ld -> bias / FiLM / CSM modulation / residual / SiLU / GroupNorm statistics -> bf16 NHWC store).
 #include "common.cuh"
 #include "ddif_internal.h"
+#include "epilogue.cuh"
 
 namespace ddif {
 
@@ -53,28 +54,6 @@ struct alignas(64) GemmKParams {
 
 static constexpr int kEpiWarps = 16;                      // 4 TMEM lane quarters x 4 column groups
 static constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warps 2..17 epilogue
-
-__device__ __forceinline__ void ldg256(const void* p, uint32_t* r) {
-  asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void stg256(void* p, const uint32_t* r) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
-               "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-__device__ __forceinline__ void unpack16(const uint32_t* r, float* f) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r[i]));
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // Persistent, warp-specialised: each CTA owns one N tile (blockIdx.y) and walks M tiles blockIdx.x, +gridDim.x, ...
 // Three pipelines: smem full/empty ring (TMA <-> MMA) running ACROSS tiles, TMEM full/empty (MMA <-> epilogue, two
@@ -132,81 +111,110 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // NOTE: this is ONE thread; its instruction count per K-iteration bounds the whole kernel, so the loop keeps
+    // running (stage, phase) counters instead of dividing, and walks dy/dx incrementally.
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(p.a_rows * p.span);
-      uint32_t it = 0;
+      const uint32_t tx_ab = a_bytes + (uint32_t)b_slot_bytes;
+      const uint32_t nstages = (uint32_t)p.stages;
+      uint32_t stage = 0, phase = 0;
+      uint8_t* a_dst = smem_a;
       bool first = true;
+      int img_grp = (int)blockIdx.x / tiles_per_img;
+      int t_in = (int)blockIdx.x - img_grp * tiles_per_img;
+      const int step_grp = (int)gridDim.x / tiles_per_img, step_in = (int)gridDim.x - step_grp * tiles_per_img;
       for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x, first = false) {
-        const int img_grp = m_tile / tiles_per_img;
-        const int t_in = m_tile - img_grp * tiles_per_img;
-        const int ty0 = (t_in / p.tiles_x) * p.th;
-        const int tx0 = (t_in % p.tiles_x) * p.tw;
+        const int trow = t_in / p.tiles_x;
+        const int ty0 = trow * p.th;
+        const int tx0 = (t_in - trow * p.tiles_x) * p.tw;
         const int n0 = img_grp * p.tn;
         const bool load_b = !p.resident_b || first;
+        const uint32_t tx_bytes = load_b ? tx_ab : a_bytes;
         int j = 0;
         for (int s = 0; s < p.nseg; ++s) {
-          for (int tap = 0; tap < p.taps[s]; ++tap) {
-            const int dy = (p.taps[s] == 9) ? tap / 3 : 0;
-            const int dx = (p.taps[s] == 9) ? tap % 3 : 0;
-            const int cw = tx0 * p.stride + dx - p.pad[s];
-            const int ch = ty0 * p.stride + dy - p.pad[s];
+          const int ntaps = p.taps[s], nkc = p.kchunks[s];
+          const int cw0 = tx0 * p.stride - p.pad[s], ch0 = ty0 * p.stride - p.pad[s];
+          int dy = 0, dx = 0;
+          for (int tap = 0; tap < ntaps; ++tap) {
             const int bz = p.b_per_sample[s] ? n0 : tap;
-            for (int kc = 0; kc < p.kchunks[s]; ++kc, ++it, ++j) {
-              const uint32_t stage = it % (uint32_t)p.stages;
-              const uint32_t phase = (it / (uint32_t)p.stages) & 1u;
+            for (int kc = 0; kc < nkc; ++kc, ++j) {
               mbar_wait(&empty_bar[stage], phase ^ 1u);
-              mbar_expect_tx(&full_bar[stage], a_bytes + (load_b ? (uint32_t)b_slot_bytes : 0u));
-              tma_load_4d(&p.tmA[s], &full_bar[stage], smem_a + (size_t)stage * a_stage_bytes, kc * p.bk, cw, ch, n0);
+              mbar_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_4d(&p.tmA[s], &full_bar[stage], a_dst, kc * p.bk, cw0 + dx, ch0 + dy, n0);
               if (load_b) {
                 const int slot = p.resident_b ? j : (int)stage;
                 tma_load_3d(&p.tmB[s], &full_bar[stage], smem_b + (size_t)slot * b_slot_bytes, kc * p.bk, n_tile * p.bn, bz);
               }
+              a_dst += a_stage_bytes;
+              if (++stage == nstages) {
+                stage = 0;
+                phase ^= 1u;
+                a_dst = smem_a;
+              }
+            }
+            if (++dx == 3) {
+              dx = 0;
+              ++dy;
             }
           }
+        }
+        t_in += step_in;
+        img_grp += step_grp;
+        if (t_in >= tiles_per_img) {
+          t_in -= tiles_per_img;
+          ++img_grp;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp, elected lane issues; see common.cuh) =====================
+    {
       const uint32_t sbo = 8u * (uint32_t)p.span;
       const int ksteps = p.bk / 16;
-      uint32_t it = 0, tcount = 0;
+      const uint32_t nstages = (uint32_t)p.stages;
+      const uint64_t desc_a0 = make_smem_desc(smem_u32(smem_a), sbo, p.layout_type);
+      const uint64_t desc_b0 = make_smem_desc(smem_u32(smem_b), sbo, p.layout_type);
+      const uint32_t a_step = (uint32_t)a_stage_bytes >> 4, b_step = (uint32_t)b_slot_bytes >> 4;
+      const bool resident = p.resident_b != 0;
+      uint32_t stage = 0, phase = 0, tcount = 0;
       for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1u, acc_phase = (tcount >> 1) & 1u;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.bn;
-        for (int j = 0; j < total_iters; ++j, ++it) {
-          const uint32_t stage = it % (uint32_t)p.stages;
-          const uint32_t phase = (it / (uint32_t)p.stages) & 1u;
+        uint32_t b_res = 0;
+        for (int j = 0; j < total_iters; ++j) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const int slot = p.resident_b ? j : (int)stage;
-          const uint64_t da = make_smem_desc(smem_u32(smem_a + (size_t)stage * a_stage_bytes), sbo, p.layout_type);
-          const uint64_t db = make_smem_desc(smem_u32(smem_b + (size_t)slot * b_slot_bytes), sbo, p.layout_type);
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (j | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+          const uint64_t da = desc_a0 + (uint64_t)(stage * a_step);
+          const uint64_t db = desc_b0 + (uint64_t)(resident ? b_res : stage * b_step);
+          const uint32_t accum = j != 0 ? 1u : 0u;
+          if (ksteps == 4) umma_bf16_ss_steps<4>(tmem_d, da, db, p.idesc, accum);
+          else if (ksteps == 2) umma_bf16_ss_steps<2>(tmem_d, da, db, p.idesc, accum);
+          else umma_bf16_ss_steps<1>(tmem_d, da, db, p.idesc, accum);
+          umma_commit_elect(&empty_bar[stage]);
+          b_res += b_step;
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        umma_commit_elect(&tmem_full_bar[acc]);
       }
     }
   } else {
     // ===================== epilogue (warps 2..17) =====================
-    // warp -> (TMEM lane quarter q = warp % 4, column group cg): thread = one output pixel x (bn / ngroups) channels.
-    // Global operands of the first 16-column chunk (residual / CSM scale+shift) are fetched BEFORE waiting for the
-    // accumulator, so their latency hides behind the MMAs of the tile.
+    // warp -> (TMEM lane quarter q = warp % 4, column group cg); see epilogue.cuh.
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
-    const int nchunks = p.bn >> 4;  // 16-column chunks of the accumulator; group cg owns chunks cg, cg+4, cg+8, ...
     const int row = q * 32 + lane;
     const int px_per_img = p.tw * p.th;
     const int tn_i = row / px_per_img;
     const int r_in = row - tn_i * px_per_img;
     const int ry = r_in / p.tw, rx = r_in % p.tw;
-    const bool wide_io = (p.out_ld % 16 == 0) && (p.res_ld % 16 == 0) && (p.n_valid % 16 == 0);
-    const bool active = (cg < nchunks) && (q * 32 < p.a_rows);
+    const bool active = (cg < (p.bn >> 4)) && (q * 32 < p.a_rows);
+    EpiParams e{p.bias, p.film, p.film_ld, p.mod, p.residual, p.res_ld, p.act, p.out, p.out_ld, p.out_nchw, p.stats,
+                p.n_valid, p.batch, p.out_h, p.out_w};
     uint32_t tcount = 0;
     for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x, ++tcount) {
       const int img_grp = m_tile / tiles_per_img;
@@ -217,140 +225,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
       const int b = n0 + tn_i;
       const bool row_ok = active && (row < p.a_rows) && (b < p.batch) && (y < p.out_h) && (x < p.out_w);
       const size_t pix = ((size_t)b * p.out_h + y) * p.out_w + x;
-      const int c_first = cg * 16;
-      uint32_t pre_res[8], pre_sc[8], pre_sh[8];
-      {
-        const int ng = n_tile * p.bn + c_first;
-        const bool full16 = wide_io && row_ok && (p.n_valid - ng >= 16);
-        if (full16 && p.residual) ldg256(p.residual + pix * (size_t)p.res_ld + ng, pre_res);
-        if (full16 && p.mod) {
-          const bf16* m = p.mod + pix * (size_t)(2 * p.n_valid) + ng;
-          ldg256(m, pre_sc);
-          ldg256(m + p.n_valid, pre_sh);
-        }
-      }
+      EpiPrefetch pf;
+      epilogue_prefetch<4>(e, pf, n_tile, p.bn, cg, row_ok, pix);
       const uint32_t acc = tcount & 1u, acc_phase = (tcount >> 1) & 1u;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      float s1 = 0.f, s2 = 0.f;
-      for (int cc = cg; cc < nchunks || cc == cg; cc += 4) {
-        const int c0 = cc * 16;
-        uint32_t r[16];
-        if (active) {
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.bn + (uint32_t)c0, r);
-          tmem_ld_wait();
-        }
-        if (cc + 4 >= nchunks) {
-          // this warp's TMEM reads of the accumulator are done: hand it back to the MMA warp before the math/stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-        }
-        const int ng = n_tile * p.bn + c0;  // global output channel of r[0]
-        if (row_ok && ng < p.n_valid) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          const int nrem = p.n_valid - ng;  // >= 1
-          const bool full16 = wide_io && nrem >= 16;
-          if (p.bias) {
-            if (nrem >= 16) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + ng + j));
-                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-              }
-            } else {
-              for (int j = 0; j < nrem; ++j) v[j] += __ldg(p.bias + ng + j);
-            }
-          }
-          if (p.film) {
-            const float* f = p.film + (size_t)b * p.film_ld + ng;
-            if (nrem >= 16 && (p.film_ld % 4 == 0)) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(f + j));
-                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-              }
-            } else {
-              for (int j = 0; j < 16 && j < nrem; ++j) v[j] += __ldg(f + j);
-            }
-          }
-          if (p.mod) {
-            const bf16* m = p.mod + pix * (size_t)(2 * p.n_valid) + ng;
-            if (full16) {
-              if (cc != cg) {
-                ldg256(m, pre_sc);
-                ldg256(m + p.n_valid, pre_sh);
-              }
-              float sc[16], sh[16];
-              unpack16(pre_sc, sc);
-              unpack16(pre_sh, sh);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = v[j] * (1.0f + sc[j]) + sh[j];
-            } else {
-              for (int j = 0; j < 16 && j < nrem; ++j)
-                v[j] = v[j] * (1.0f + __bfloat162float(m[j])) + __bfloat162float(m[p.n_valid + j]);
-            }
-          }
-          if (p.residual) {
-            const bf16* rs = p.residual + pix * (size_t)p.res_ld + ng;
-            if (full16) {
-              if (cc != cg) ldg256(rs, pre_res);
-              float rr[16];
-              unpack16(pre_res, rr);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] += rr[j];
-            } else {
-              for (int j = 0; j < 16 && j < nrem; ++j) v[j] += __bfloat162float(rs[j]);
-            }
-          }
-          if (p.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
-          }
-          if (p.stats) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < nrem) {
-                s1 += v[j];
-                s2 += v[j] * v[j];
-              }
-          }
-          if (p.out) {
-            bf16* o = p.out + pix * (size_t)p.out_ld + ng;
-            if (full16) {
-              uint32_t w[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                w[j] = *reinterpret_cast<const uint32_t*>(&t);
-              }
-              stg256(o, w);
-            } else if (nrem >= 16) {
-              *reinterpret_cast<bf16x8*>(o) = pack8(v);
-              *reinterpret_cast<bf16x8*>(o + 8) = pack8(v + 8);
-            } else {
-              for (int j = 0; j < nrem; ++j) o[j] = __float2bfloat16(v[j]);
-            }
-          }
-          if (p.out_nchw) {
-            const size_t hw = (size_t)p.out_h * p.out_w;
-            float* o = p.out_nchw + ((size_t)b * p.n_valid + ng) * hw + (size_t)y * p.out_w + x;
-            for (int j = 0; j < 16 && j < nrem; ++j) o[(size_t)j * hw] = v[j];
-          }
-        }
-      }
-      if (p.stats && active) {
-        // all rows of one warp belong to one sample (px_per_img is 64 or 128)
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        const int bw = n0 + (q * 32) / px_per_img;
-        if (lane == 0 && bw < p.batch) {
-          atomicAdd(p.stats + 2 * (size_t)bw, (double)s1);
-          atomicAdd(p.stats + 2 * (size_t)bw + 1, (double)s2);
-        }
-      }
+      epilogue_tile<4>(e, pf, tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.bn, &tmem_empty_bar[acc], p.bn, n_tile, cg, lane,
+                       active, row_ok, b, y, x, pix, n0 + (q * 32) / px_per_img);
     }
     tc_fence_before();
   }
@@ -368,6 +249,18 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+PFN_encodeTiled ddif_get_encode();
+int ddif_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      sms = n;
+    else
+      sms = 148;
+  }
+  return sms;
+}
 static PFN_encodeTiled get_encode() {
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
@@ -379,11 +272,17 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+PFN_encodeTiled ddif_get_encode() { return get_encode(); }
+
 static CUtensorMapSwizzle swizzle_for_span(int span) {
   return span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
 int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
+  const bool wants_fused = g.gn_stats != nullptr || g.a_up != 0;
+  if (wants_fused && !conv3_applicable(g)) return DDIF_ERR_SHAPE;  // the prologue exists only in the fused 3x3 kernel
+  if (wants_fused || (conv3_applicable(g) && !g.force_tma)) return conv3_prepare(g, L);
+  L.variant = 0;
   GemmKParams& p = *reinterpret_cast<GemmKParams*>(L.kparams);
   static_assert(sizeof(GemmKParams) <= sizeof(L.kparams), "kparams buffer too small");
   memset(&p, 0, sizeof(p));
@@ -458,14 +357,7 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   p.stages = stages;
   p.num_m_tiles = p.tiles_x * p.tiles_y * (int)ceil_div(B, tn);
   L.smem_bytes = stages * a_stage + p.b_slots * b_slot + (2 * stages + 6) * 8 + 1024;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      sms = n;
-    else
-      sms = 148;
-  }
+  const int sms = ddif_sm_count();
   L.grid_y = (int)(g.n_pad / bn);
   const int gx = (sms + L.grid_y - 1) / L.grid_y;  // persistent: ~one CTA per SM in total
   L.grid_x = p.num_m_tiles < gx ? p.num_m_tiles : gx;
@@ -514,6 +406,7 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
 }
 
 int gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
+  if (L.variant == 1) return conv3_launch(L, stream);
   const GemmKParams& p = *reinterpret_cast<const GemmKParams*>(L.kparams);
   conv_igemm_tc_kernel<<<dim3(L.grid_x, L.grid_y), kGemmThreads, L.smem_bytes, stream>>>(p);
   DDIF_LAUNCH_CHECK();

@@ -248,7 +248,9 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], net: "UNetSR3") -> Dict[str, to
         P["_film_offsets"][p] = off
         off += w.shape[0]
         film_w.append(w)
-        film_b.append(b)
+        # block1's conv bias is folded into the FiLM vector (both are per-(sample,)channel additive terms): one add less
+        # per output element in the conv epilogue
+        film_b.append(b + sd[p + ".block1.block.3.bias"])
         for blk in ("block1", "block2"):
             P[f"{p}.{blk}.gamma"] = f32(sd[f"{p}.{blk}.block.0.weight"])
             P[f"{p}.{blk}.beta"] = f32(sd[f"{p}.{blk}.block.0.bias"])
@@ -367,9 +369,12 @@ class Schedule:
         return Act(buf, B, H, W, C, st)
 
     def _gemm(self, pb, label, srcs, weights, n_valid, out: Optional[Act], *, taps, stride=1, bias=None, film=None,
-              film_ld=0, mod=None, residual: Optional[Act] = None, act=0, out_nchw=None, per_sample=(0, 0), w_s=None, out_hw=None):
+              film_ld=0, mod=None, residual: Optional[Act] = None, act=0, out_nchw=None, per_sample=(0, 0), w_s=None, out_hw=None,
+              gn=None, a_up=0):
+        """gn = (gamma_addr, beta_addr, act): fuse GroupNorm(+Swish) of the (single) source into the conv's loader, using the
+        source's own statistics; a_up = 1: read the source through a nearest x2 up-sampling."""
         a0 = srcs[0]
-        oh, ow = out_hw if out_hw else (a0.H // stride, a0.W // stride)
+        oh, ow = out_hw if out_hw else ((a0.H << a_up) // stride, (a0.W << a_up) // stride)
         n_pad = _ceil(n_valid, 16)
         nseg = len(srcs)
         k_total = sum(s.C * taps[i] for i, s in enumerate(srcs))
@@ -383,7 +388,11 @@ class Schedule:
             n_pad=n_pad, n_valid=n_valid, bias=bias, film=film, film_ld=film_ld, mod=mod,
             residual=residual.buf if residual else None, res_ld=residual.C if residual else 0, act=act,
             out=out.buf if out else None, out_ld=out.C if out else 0, out_nchw=out_nchw,
-            stats=out.stats if (out is not None and out.stats is not None) else None)
+            stats=out.stats if (out is not None and out.stats is not None) else None,
+            gn_stats=a0.stats if gn else None, gn_gamma=gn[0] if gn else None, gn_beta=gn[1] if gn else None, gn_eps=1e-5,
+            gn_act=gn[2] if gn else 0, a_up=a_up, force_tma=0)
+        if gn:
+            assert a0.stats is not None, label
         m = a0.B * oh * ow
         nbytes = sum(s.B * s.H * s.W * s.C * 2 for s in srcs) + m * n_valid * (2 if out else 4)
         if residual:
@@ -402,17 +411,30 @@ class Schedule:
                dw_w=dw_w, out_dw=out_dw.buf if out_dw else None, batch=src.B, h=src.H, w=src.W, act=act, eps=1e-5)
         return out, out_dw
 
+    @staticmethod
+    def _fusable(x: Act) -> bool:
+        """The fused GN+Swish+conv3x3 kernel tiles the image in 8x16 pixel boxes (csrc/conv3x3_tc.cu)."""
+        return x.W >= 16 and x.H >= 8 and x.C <= 256
+
+    def _gn_conv3(self, label, x: Act, gamma, beta, w, n_valid, out, **kw):
+        """Block = GN -> Swish -> Conv3x3 (sr3_dwt.py:288-300): one fused kernel where the tile shape allows, else
+        gn_apply + the generic TMA conv."""
+        pb = self.fwd
+        if self._fusable(x):
+            return self._gemm(pb, label + ".gn+conv", [x], [w], n_valid, out, taps=[9], gn=(gamma, beta, 1), **kw)
+        n, _ = self._gn(pb, label + ".gn", x, gamma, beta, 1, name=label + ".n")
+        return self._gemm(pb, label + ".conv", [n], [w], n_valid, out, taps=[9], **kw)
+
     def _res_block(self, x: Act, p: str) -> Act:
         A, pb = self.addr, self.fwd
         d = x.C
-        n1, _ = self._gn(pb, p + ".block1.gn", x, A[p + ".block1.gamma"], A[p + ".block1.beta"], 1, name=p + ".n1")
         h1 = self._act(pb, p + ".h1", x.B, x.H, x.W, d, stats=True)
         film_off = self.film_offsets[p]
-        self._gemm(pb, p + ".block1.conv", [n1], [A[p + ".block1.w"]], d, h1, taps=[9], bias=A[p + ".block1.b"],
-                   film=(self.film_buf, film_off * 4), film_ld=self.nfilm)
-        n2, _ = self._gn(pb, p + ".block2.gn", h1, A[p + ".block2.gamma"], A[p + ".block2.beta"], 1, name=p + ".n2")
+        self._gn_conv3(p + ".block1", x, A[p + ".block1.gamma"], A[p + ".block1.beta"], A[p + ".block1.w"], d, h1,
+                       film=(self.film_buf, film_off * 4), film_ld=self.nfilm)  # conv bias lives in the FiLM vector
         out = self._act(pb, p + ".out", x.B, x.H, x.W, d, stats=True)
-        self._gemm(pb, p + ".block2.conv", [n2], [A[p + ".block2.w"]], d, out, taps=[9], bias=A[p + ".block2.b"], residual=x)
+        self._gn_conv3(p + ".block2", h1, A[p + ".block2.gamma"], A[p + ".block2.beta"], A[p + ".block2.w"], d, out,
+                       bias=A[p + ".block2.b"], residual=x)
         return out
 
     def _attention(self, x: Act, p: str) -> Act:
@@ -537,11 +559,14 @@ class Schedule:
             kind = getattr(m, "kind", None)
             p = f"ups.{i}"
             if kind == "up":
-                up = self._act(pb, p + ".up", B, x.H * 2, x.W * 2, x.C)
-                pb.add("ddif_upsample2x_t", label=p + ".nearest", traffic=B * x.H * x.W * x.C * 10, **{"in": x.buf}, out=up.buf, batch=B,
-                       h=x.H, w=x.W, c=x.C)
-                y = self._act(pb, p, B, up.H, up.W, x.C, stats=True)
-                self._gemm(pb, p + ".conv", [up], [A[p + ".w"]], x.C, y, taps=[9], bias=A[p + ".b"])
+                y = self._act(pb, p, B, x.H * 2, x.W * 2, x.C, stats=True)
+                if x.W * 2 >= 16 and x.C <= 256:  # nearest x2 folded into the conv's loader
+                    self._gemm(pb, p + ".up+conv", [x], [A[p + ".w"]], x.C, y, taps=[9], bias=A[p + ".b"], a_up=1)
+                else:
+                    up = self._act(pb, p + ".up", B, x.H * 2, x.W * 2, x.C)
+                    pb.add("ddif_upsample2x_t", label=p + ".nearest", traffic=B * x.H * x.W * x.C * 10, **{"in": x.buf}, out=up.buf, batch=B,
+                           h=x.H, w=x.W, c=x.C)
+                    self._gemm(pb, p + ".conv", [up], [A[p + ".w"]], x.C, y, taps=[9], bias=A[p + ".b"])
                 x = y
                 self.taps[p] = (x, len(pb.ops))
                 continue
@@ -570,8 +595,8 @@ class Schedule:
             if m.with_attn:
                 x = self._attention(x, p + ".attn")
             self.taps[p] = (x, len(pb.ops))
-        n, _ = self._gn(pb, "final.gn", x, A["final.gamma"], A["final.beta"], 1, name="final.n")
-        self._gemm(pb, "final.conv", [n], [A["final.w"]], net.out_channel, None, taps=[9], bias=A["final.b"], out_nchw=self.io["out"])
+        self._gn_conv3("final", x, A["final.gamma"], A["final.beta"], A["final.w"], net.out_channel, None, bias=A["final.b"],
+                       out_nchw=self.io["out"])
         self.stats_buf.nbytes = max(self.n_stats * B * 16, 16)
         pb.ops[0].fields["bytes"] = self.stats_buf.nbytes
 

@@ -58,6 +58,8 @@ enum ddif_op_kind {
 /* ---- DDIF_OP_GEMM ------------------------------------------------------------------------------------------
  * out[b,y,x,n] = epilogue( sum_seg sum_tap sum_c  a_seg[b, y*stride+dy-pad, x*stride+dx-pad, c] * w_seg[z, n, c] )
  * z = tap (shared weights) or b (per-sample weights, 1x1 only).  Zero padding comes from TMA out-of-bounds fill.
+ * Two kernels implement it: conv3x3_fused_tc_kernel (3x3, stride 1, one segment: halo tile loaded once, optional fused
+ * GroupNorm+Swish prologue) and conv_igemm_tc_kernel (everything else: 1x1, stride 2, two segments, per-sample weights).
  * epilogue: v = acc + bias[n] + film[b*film_ld + n];  v = v*(1+mod[..,n]) + mod[..,n_valid+n];  v += residual;
  *           v = silu(v) if act;  stats[b] += (sum v, sum v^2);  store bf16 NHWC and/or fp32 NCHW.              */
 typedef struct {
@@ -72,6 +74,11 @@ typedef struct {
   void* out;            int64_t out_ld;
   float* out_nchw;
   double* stats;
+  /* Optional fused prologue on segment 0 (3x3 stride-1 convs only): a = act(GroupNorm_1group(a)) with the per-sample
+   * (sum, sumsq) statistics of the input tensor; a_up = 1 reads the input through a nearest x2 up-sampling
+   * (sr3_dwt.py:269).  force_tma = 1 selects the generic TMA kernel even where the fused 3x3 kernel applies. */
+  const double* gn_stats; const float* gn_gamma; const float* gn_beta; double gn_eps;
+  int64_t gn_act, a_up, force_tma;
 } ddif_gemm_t;
 
 typedef struct { const float* x; const float* self_cond; void* out; int64_t batch, c, h, w, c_pad; } ddif_in_convert_t;
@@ -174,6 +181,10 @@ int ddif_plan_graph_launch(ddif_plan_t* plan, ddif_stream_t stream);
 int ddif_plan_profile(ddif_plan_t* plan, ddif_stream_t stream, float* ms, int* kinds, int capacity);
 /* Number of kernel launches the plan issues per run. */
 int ddif_plan_launches(const ddif_plan_t* plan);
+
+/* Debug: device buffer of 3*64*4 int64 receiving clock64() at the pipeline hand-offs of CTA 0 of the fused 3x3 kernel
+ * (role-major: loader, MMA issuer, epilogue; 64 tiles; 4 stamps).  NULL disables.  Not for production use. */
+int ddif_debug_set_timestamps(void* device_ptr);
 
 /* Named convenience wrappers (same structs), the symbols a reference-side binding would call directly. */
 int ddif_haar_dwt2_f32(const ddif_haar_t* p, ddif_stream_t s);

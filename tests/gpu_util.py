@@ -35,11 +35,12 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 
 def gemm(srcs, weights, n_valid, *, taps, stride=1, bias=None, film=None, mod=None, residual=None, act=0,
-         per_sample=None, want_nchw=False, want_stats=False, out_hw=None):
-    """Run DDIF_OP_GEMM on NHWC bf16 tensors; returns (out_nhwc_bf16 | out_nchw_f32, stats | None)."""
+         per_sample=None, want_nchw=False, want_stats=False, out_hw=None, gn=None, a_up=0, force_tma=0):
+    """Run DDIF_OP_GEMM on NHWC bf16 tensors; returns (out_nhwc_bf16 | out_nchw_f32, stats | None).
+    gn = (stats[B,2] f64, gamma, beta, act) fuses GroupNorm(+Swish) of the source into the 3x3 kernel."""
     a0 = srcs[0]
     B, H, W, _ = a0.shape
-    oh, ow = out_hw if out_hw else (H // stride, W // stride)
+    oh, ow = out_hw if out_hw else ((H << a_up) // stride, (W << a_up) // stride)
     nseg = len(srcs)
     n_pad = (n_valid + 15) // 16 * 16
     out = torch.zeros(B, oh, ow, n_valid if n_valid % 8 == 0 else n_pad, dtype=torch.bfloat16, device=DEV) if not want_nchw else None
@@ -57,6 +58,8 @@ def gemm(srcs, weights, n_valid, *, taps, stride=1, bias=None, film=None, mod=No
         film_ld=film.shape[1] if film is not None else 0, mod=mod.data_ptr() if mod is not None else None,
         residual=residual.data_ptr() if residual is not None else None, res_ld=residual.shape[3] if residual is not None else 0,
         act=act, out=out.data_ptr() if out is not None else None, out_ld=out.shape[3] if out is not None else 0,
-        out_nchw=out_nchw.data_ptr() if out_nchw is not None else None, stats=stats.data_ptr() if stats is not None else None)
+        out_nchw=out_nchw.data_ptr() if out_nchw is not None else None, stats=stats.data_ptr() if stats is not None else None,
+        gn_stats=gn[0].data_ptr() if gn else None, gn_gamma=gn[1].data_ptr() if gn else None, gn_beta=gn[2].data_ptr() if gn else None,
+        gn_eps=1e-5, gn_act=gn[3] if gn else 0, a_up=a_up, force_tma=force_tma)
     torch.cuda.synchronize()
     return (out_nchw if want_nchw else out), stats

@@ -57,6 +57,63 @@ def test_conv_matches_torch(name, B, H, W, Cin, Cout, k, stride):
     _close(to_nchw_f32(out), ref, name)
 
 
+FUSED = [
+    # name,          B,  H,  W, Cin, Cout
+    ("f32_32",       3, 64, 64,  32,  32),   # span 64, resident weights, many tiles per CTA
+    ("f64_64",       2, 32, 32,  64,  64),   # span 128, resident weights
+    ("f64_128",      2, 32, 32,  64, 128),   # streamed weights
+    ("f128_64",      2, 16, 16, 128,  64),   # two K slabs, streamed weights
+    ("f96_64",       1, 32, 32,  96,  64),   # three K slabs of 32
+    ("f16_32",       2, 64, 64,  16,  32),   # span 32
+    ("f_ragged",     2, 24, 40,  32,  48),   # partial tiles in x and y
+    ("f256_128",     1, 16, 16, 256, 128),
+]
+
+
+@pytest.mark.parametrize("name,B,H,W,Cin,Cout", FUSED, ids=[c[0] for c in FUSED])
+def test_fused_gn_swish_conv3x3(name, B, H, W, Cin, Cout):
+    """GroupNorm(1 group)+Swish fused into the 3x3 conv loader vs torch, and the plain fused kernel vs the TMA kernel."""
+    x = _rand(B, Cin, H, W, seed=21, scale=1.5) + 0.4
+    w = _rand(Cout, Cin, 3, 3, seed=22, scale=1.0 / math.sqrt(Cin * 9))
+    bias = _rand(Cout, seed=23)
+    gamma, beta = 1 + 0.1 * _rand(Cin, seed=24), 0.1 * _rand(Cin, seed=25)
+    xa, wp = nhwc_bf16(x), pack_w(w)
+    xf = to_nchw_f32(xa)
+    stats = torch.stack([xf.double().sum(dim=(1, 2, 3)), (xf.double() ** 2).sum(dim=(1, 2, 3))], dim=1).contiguous()
+    out, _ = gemm([xa], [wp], Cout, taps=[9], bias=bias, gn=(stats, gamma, beta, 1))
+    h = F.group_norm(xf, 1, gamma, beta, eps=1e-5)
+    h = (h * torch.sigmoid(h)).to(torch.bfloat16).float()  # the kernel feeds the MMA bf16 operands
+    ref = F.conv2d(h, w.to(torch.bfloat16).float(), bias, padding=1)
+    got = to_nchw_f32(out)
+    assert rel_err(got, ref) < 6e-3, rel_err(got, ref)
+    # a bf16 flip of the normalised operand moves single outputs by ~2^-8 |h| |w|: bound the tail loosely
+    assert float((got - ref).abs().max()) < 0.06 * float(ref.abs().max())
+    plain, _ = gemm([xa], [wp], Cout, taps=[9], bias=bias)
+    tma, _ = gemm([xa], [wp], Cout, taps=[9], bias=bias, force_tma=1)
+    _close(to_nchw_f32(plain), F.conv2d(xf, w.to(torch.bfloat16).float(), bias, padding=1), name + " plain")
+    _close(to_nchw_f32(plain), to_nchw_f32(tma), name + " fused-vs-tma")
+
+
+def test_fused_upsample_conv_and_epilogue():
+    B, H, W, C = 2, 16, 16, 64
+    x = _rand(B, C, H, W, seed=31)
+    w, bias = _rand(C, C, 3, 3, seed=32, scale=0.05), _rand(C, seed=33)
+    xa, wp = nhwc_bf16(x), pack_w(w)
+    out, stats = gemm([xa], [wp], C, taps=[9], bias=bias, a_up=1, want_stats=True)
+    ref = F.conv2d(F.interpolate(to_nchw_f32(xa), scale_factor=2, mode="nearest"), w.to(torch.bfloat16).float(), bias, padding=1)
+    _close(to_nchw_f32(out), ref, "upsample fold")
+    s_ref = torch.stack([ref.double().sum(dim=(1, 2, 3)), (ref.double() ** 2).sum(dim=(1, 2, 3))], dim=1)
+    assert torch.allclose(stats, s_ref, rtol=2e-3, atol=0.5)
+    # residual + FiLM + fp32 NCHW store with N = 8 (the final conv)
+    res = nhwc_bf16(_rand(B, C, H, W, seed=34))
+    film = _rand(B, C, seed=35)
+    out, _ = gemm([xa], [wp], C, taps=[9], bias=bias, film=film, residual=res)
+    ref = F.conv2d(to_nchw_f32(xa), w.to(torch.bfloat16).float(), bias, padding=1) + film[:, :, None, None] + to_nchw_f32(res)
+    _close(to_nchw_f32(out), ref, "fused epilogue")
+    out8, _ = gemm([xa], [pack_w(w[:8])], 8, taps=[9], bias=bias[:8], want_nchw=True)
+    assert rel_err(out8, F.conv2d(to_nchw_f32(xa), w[:8].to(torch.bfloat16).float(), bias[:8], padding=1)) < 1e-4
+
+
 def test_direct_conv_checker_agrees():
     B, H, W, Cin, Cout = 2, 16, 16, 32, 48
     x, w, bias = _rand(B, Cin, H, W, seed=4), _rand(Cout, Cin, 3, 3, seed=5, scale=0.06), _rand(Cout, seed=6)

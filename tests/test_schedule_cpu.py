@@ -72,7 +72,12 @@ def test_schedule_structure(dataset, B, H, W):
     assert kinds.count("ddif_gemm_t") == 12 * 3 + 16 * 6 + 4 + 8 * 2 + 1 + 3 + 3 + 1
     assert kinds.count("ddif_attn_t") == 8
     assert kinds.count("ddif_softmax_h_t") == 16
-    assert kinds.count("ddif_gn_apply_t") == 30 * 2 + 8 + 16 + 1  # resblocks, attn norms, FWM prenorm, final
+    # GroupNorm+Swish of the 3x3 convs is fused into the conv loader except at the 8-pixel-wide level (9 resblocks);
+    # stand-alone launches left: 8 attention norms + 16 FWM prenorm(+dw) + 9 x 2
+    assert kinds.count("ddif_gn_apply_t") == 8 + 16 + 9 * 2
+    assert kinds.count("ddif_upsample2x_t") == 0  # nearest x2 folded into the following conv
+    fused = [op for op in s.fwd.ops if op.struct == "ddif_gemm_t" and op.fields.get("gn_stats") is not None]
+    assert len(fused) == 21 * 2 + 1
     assert len(s.mod) == 12 and len(s.weff) == 16
     flops = sum(op.flops for op in s.fwd.ops) + sum(op.flops for op in s.cnd.ops)
     assert flops > 0

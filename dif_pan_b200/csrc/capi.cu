@@ -231,7 +231,10 @@ int ddif_plan_profile(ddif_plan_t* plan, ddif_stream_t stream, float* ms, int* k
   return rc;
 }
 
-int ddif_debug_set_timestamps(void* device_ptr) { return ddif::conv3_set_debug_ts((long long*)device_ptr); }
+int ddif_debug_set_timestamps(void* device_ptr) {
+  const int rc = ddif::conv3_set_debug_ts((long long*)device_ptr);
+  return rc ? rc : ddif::conv3_halo_set_debug_ts((long long*)device_ptr);
+}
 
 int ddif_haar_dwt2_f32(const ddif_haar_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_HAAR_DWT2, p, s); }
 int ddif_haar_idwt2_f32(const ddif_haar_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_HAAR_IDWT2, p, s); }

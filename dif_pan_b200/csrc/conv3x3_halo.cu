@@ -1,0 +1,644 @@
+// 3x3 (stride 1, pad 1) convolution with an optional fused GroupNorm(1 group)+Swish prologue: ONE halo tile in shared
+// memory feeds all nine taps.  tcgen05 / TMEM / TMA, persistent, warp-specialised.
+//
+// Replaces `Block` = GN -> Swish -> Conv3x3 (/root/reference/models/sr3_dwt.py:288-300), the FWM ffn 3x3 convs
+// (:529-531) and downs[0] (:86).
+//
+// Output tile = 8 (x) x 16 (y) pixels = the 128 rows of one UMMA; its halo = 10 x 18 pixels.  One TMA 4D box
+// (C_slab x 10 x 18 x 1, hardware swizzle, out-of-bounds = zero padding) brings the halo into a stage of a 3-4 deep
+// ring: halo pixel (hy, hx) is row r = hy*10 + hx of `span` = C_slab*2 bytes.  Tap (dy, dx) of the implicit GEMM is the
+// SAME stage read through a descriptor that starts (dy*10 + dx) rows further and strides SBO = 10 rows between the
+// 8-row groups (8 pixels of one tile line): the UMMA swizzle is a function of the absolute shared-memory address
+// (tools/microbench/umma_offset.cu, profiles/r01_microbench_umma_offset.txt: every start row / SBO reads back exactly),
+// so no shifted copies are needed and each activation byte crosses L2->SMEM once (1.4x halo overhead instead of 9x).
+//
+// With the GN prologue, 8 transform warps normalise the landed stage IN PLACE (LDS.128 -> fma + tanh.approx -> STS.128;
+// padding pixels stay zero, as the reference pads the normalised tensor) and hand it to the MMA warp through a second
+// mbarrier; without it the TMA barrier feeds the MMA warp directly.  Weights of all taps stay resident in shared
+// memory; one elected thread issues the MMAs into two TMEM accumulators; 8 epilogue warps run epilogue.cuh.
+//
+// Measured floors (profiles/r01_microbench_*.txt): one M128xNxK16 MMA = max(44.8, N/2) cycles, so a 32->32 tile
+// (18 MMAs) needs >= 810 cycles; the TMA halo feed needs 420 (C=32) / 750 (C=64) cycles per tile.
+#include "common.cuh"
+#include "ddif_internal.h"
+#include "epilogue.cuh"
+
+namespace ddif {
+
+static constexpr int kHxfThreads = 256;                    // transform warps 0..7
+static constexpr int kHEpiWarps = 8;                       // warps 10..17
+static constexpr int kHThreads = kHxfThreads + 64 + 32 * kHEpiWarps;
+static constexpr int kHW = 10, kHH = 18, kHPx = kHW * kHH;  // halo of an 8 x 16 tile
+static constexpr int kHMaxStages = 4;
+static constexpr int kHMaxStat = 1024;
+
+struct alignas(64) HaloKParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int cin, kslab, nslab, span;
+  int batch, out_h, out_w;
+  int tiles_x, tiles_y, num_tiles;
+  int bn;
+  int stages;
+  uint32_t stage_bytes, b_slot_bytes;
+  uint32_t idesc, layout_type, tmem_cols;
+  const double* gn_stats;
+  const float* gn_gamma;
+  const float* gn_beta;
+  float gn_eps;
+  int gn_act;
+  double gn_count;
+  EpiParams epi;
+};
+
+// Debug hook (ddif_debug_set_timestamps): CTA 0 records clock64() at the pipeline hand-offs of its first 64 tiles:
+// ts[(role*64 + tile)*4 + k], role 0 = TMA producer, 1 = MMA issuer, 2 = epilogue warp 10 lane 0, 3 = transform thread 0.
+__device__ long long* g_halo_ts = nullptr;
+__device__ __forceinline__ void h_ts(int role, int tile, int k) {
+  if (g_halo_ts && blockIdx.x == 0 && tile < 64) g_halo_ts[(role * 64 + tile) * 4 + k] = clock64();
+}
+
+__device__ __forceinline__ void h_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 h_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void h_sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Tile walk of one persistent CTA (blockIdx.x, +gridDim.x, ...) without divisions in the loop.
+struct HaloIter {
+  int b, ty, tx, slab, remaining;
+  int sb, sy, sx, tiles_x, tiles_y, nslab;
+  __device__ __forceinline__ void init(const HaloKParams& p) {
+    const int tpi = p.tiles_x * p.tiles_y;
+    tiles_x = p.tiles_x; tiles_y = p.tiles_y; nslab = p.nslab;
+    const int m0 = (int)blockIdx.x, g = (int)gridDim.x;
+    b = m0 / tpi;
+    int r = m0 - b * tpi;
+    ty = r / tiles_x; tx = r - ty * tiles_x;
+    sb = g / tpi;
+    r = g - sb * tpi;
+    sy = r / tiles_x; sx = r - sy * tiles_x;
+    slab = 0;
+    remaining = ((p.num_tiles - m0 + g - 1) / g) * nslab;
+  }
+  __device__ __forceinline__ void next() {
+    --remaining;
+    if (++slab < nslab) return;
+    slab = 0;
+    tx += sx; ty += sy; b += sb;
+    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    if (ty >= tiles_y) { ty -= tiles_y; ++b; }
+  }
+};
+
+// ---- transform warps: GroupNorm affine (+Swish) of a landed stage, in place -------------------------------------------
+template <int NCK>
+__device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32_t a_base, uint64_t* a_tma, uint64_t* a_ready,
+                                                    const float* s_gamma, const float* s_beta, const float2* s_stat, int lt) {
+  constexpr int LPT = (kHPx * NCK + kHxfThreads - 1) / kHxfThreads;
+  constexpr int RPP = kHxfThreads / NCK;  // halo rows per pass
+  const int c = lt % NCK;
+  const int r0 = lt / NCK;
+  uint32_t soff[LPT];
+  int hy[LPT], hx[LPT];
+#pragma unroll
+  for (int k = 0; k < LPT; ++k) {
+    const int r = r0 + k * RPP;
+    const uint32_t sw = NCK == 8 ? ((uint32_t)r & 7u) : (NCK == 4 ? (((uint32_t)r >> 1) & 3u) : (((uint32_t)r >> 2) & 1u));
+    soff[k] = (uint32_t)r * (uint32_t)(NCK * 16) + (((uint32_t)c ^ sw) << 4);
+    hy[k] = r < kHPx ? r / kHW : -100000;
+    hx[k] = r % kHW;
+  }
+  const float hs = p.gn_act ? 0.5f : 1.0f;  // swish(t) = h*tanh(h) + h with h = t/2: the affine is pre-halved
+  const uint32_t nst = (uint32_t)p.stages;
+  HaloIter it;
+  it.init(p);
+  uint32_t stage = 0, phase = 0;
+  int cur_b = -1, cur_slab = -1, tcount = 0;
+  float a[8], d[8];
+  for (; it.remaining > 0; it.next()) {
+    if (it.b != cur_b || it.slab != cur_slab) {
+      cur_b = it.b; cur_slab = it.slab;
+      float mean, rstd;
+      if (it.b < kHMaxStat) {
+        const float2 mr = s_stat[it.b];
+        mean = mr.x; rstd = mr.y;
+      } else {
+        const double s = p.gn_stats[2 * it.b], ss = p.gn_stats[2 * it.b + 1];
+        const double m = s / p.gn_count;
+        double var = ss / p.gn_count - m * m;
+        if (var < 0) var = 0;
+        mean = (float)m;
+        rstd = rsqrtf((float)var + p.gn_eps);
+      }
+      const int ch0 = it.slab * p.kslab + c * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] = hs * rstd * s_gamma[ch0 + j];
+        d[j] = hs * s_beta[ch0 + j] - mean * a[j];
+      }
+    }
+    const int y0 = it.ty * 16 - 1, x0 = it.tx * 8 - 1;
+    const uint32_t sbase = a_base + stage * p.stage_bytes;
+    if (lt == 0) h_ts(3, tcount, 0);
+    mbar_wait(&a_tma[stage], phase);
+    if (lt == 0) h_ts(3, tcount, 1);
+    uint4 v[LPT];
+    bool ok[LPT];
+#pragma unroll
+    for (int k = 0; k < LPT; ++k) {
+      ok[k] = (unsigned)(y0 + hy[k]) < (unsigned)p.out_h && (unsigned)(x0 + hx[k]) < (unsigned)p.out_w;
+      if (ok[k]) v[k] = h_lds128(sbase + soff[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < LPT; ++k) {
+      if (ok[k]) {
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(&v[k]), f);
+        if (p.gn_act) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) f[q] = swish_half(fmaf(f[q], a[q], d[q]));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) f[q] = fmaf(f[q], a[q], d[q]);
+        }
+        const bf16x8 pk = pack8(f);
+        h_sts128(sbase + soff[k], *reinterpret_cast<const uint4*>(&pk));
+      }
+    }
+    if (lt == 0) h_ts(3, tcount, 2);
+    h_fence_proxy_async();
+    mbar_arrive(&a_ready[stage]);
+    if (lt == 0) h_ts(3, tcount, 3);
+    ++tcount;
+    if (++stage == nst) { stage = 0; phase ^= 1u; }
+  }
+}
+
+// ---- MMA warp --------------------------------------------------------------------------------------------------------
+template <int KSTEPS>
+__device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_base, uint32_t b_base, uint64_t* a_full, uint64_t* a_empty,
+                                              uint64_t* b_full, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int my_tiles) {
+  const uint32_t span = (uint32_t)p.span;
+  const uint64_t desc_a0 = make_smem_desc(a_base, (uint32_t)kHW * span, p.layout_type);  // SBO = one halo line (10 rows)
+  const uint64_t desc_b0 = make_smem_desc(b_base, 8u * span, p.layout_type);
+  const uint32_t stage16 = p.stage_bytes >> 4, b16 = p.b_slot_bytes >> 4;
+  uint32_t tap_off[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((uint32_t)((tap / 3) * kHW + (tap % 3)) * span) >> 4;
+  const uint32_t nst = (uint32_t)p.stages;
+  uint32_t stage = 0, phase = 0;
+  mbar_wait(b_full, 0u);
+  tc_fence_after();
+  for (int t = 0; t < my_tiles; ++t) {
+    const uint32_t acc = (uint32_t)t & 1u;
+    if ((threadIdx.x & 31) == 0) h_ts(1, t, 0);
+    mbar_wait(&tmem_empty[acc], (((uint32_t)t >> 1) & 1u) ^ 1u);
+    tc_fence_after();
+    if ((threadIdx.x & 31) == 0) h_ts(1, t, 1);
+    const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.bn;
+    uint64_t db = desc_b0;
+    for (int slab = 0; slab < p.nslab; ++slab) {
+      mbar_wait(&a_full[stage], phase);
+      tc_fence_after();
+      if ((threadIdx.x & 31) == 0) h_ts(1, t, 2);
+      const uint64_t da = desc_a0 + (uint64_t)(stage * stage16);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        umma_bf16_ss_steps<KSTEPS>(tmem_d, da + tap_off[tap], db, p.idesc, (slab | tap) != 0 ? 1u : 0u);
+        db += b16;
+      }
+      umma_commit_elect(&a_empty[stage]);
+      if (++stage == nst) { stage = 0; phase ^= 1u; }
+    }
+    umma_commit_elect(&tmem_full[acc]);
+    if ((threadIdx.x & 31) == 0) h_ts(1, t, 3);
+  }
+}
+
+// ---- epilogue --------------------------------------------------------------------------------------------------------
+// Two groups of 4 warps; group g owns TMEM accumulator g (tiles t = g, g+2, ...), so a warp has two tile periods for one
+// tile and the per-tile fixed cost (coordinates, barrier, statistics reduction) is paid once per 32 rows x ALL columns.
+// Compile-time flags keep the instruction stream short: the generic run-time epilogue (epilogue.cuh) spent ~2000
+// cycles per 128 x 32 tile on constant loads and branches (profiles/r01_halo_v1_*).
+enum : int { kEpiRes = 1, kEpiAct = 2, kEpiStats = 4, kEpiNchw = 8 };
+
+template <int F>
+__device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int warp,
+                                                   int lane, int my_tiles) {
+  constexpr bool kRes = (F & kEpiRes) != 0, kAct = (F & kEpiAct) != 0, kStats = (F & kEpiStats) != 0, kNchw = (F & kEpiNchw) != 0;
+  const int q = warp & 3;
+  const int grp = (warp - 10) >> 2;
+  const int row = q * 32 + lane;
+  const int ry = row >> 3, rx = row & 7;
+  const int tpi = p.tiles_x * p.tiles_y;
+  const int nch = p.bn >> 4;
+  const int n_valid = p.epi.n_valid;
+  const float* bias = p.epi.bias;
+  const float* film = p.epi.film;
+  const int film_ld = p.epi.film_ld;
+  const bf16* resid = p.epi.residual;
+  const int res_ld = p.epi.res_ld, out_ld = p.epi.out_ld;
+  bf16* outp = p.epi.out;
+  float* out_nchw = p.epi.out_nchw;
+  double* stats = p.epi.stats;
+  const int out_h = p.out_h, out_w = p.out_w, tiles_x = p.tiles_x;
+  const size_t hw = (size_t)out_h * out_w;
+  const uint32_t tm_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * (uint32_t)p.bn;
+  uint64_t* full = &tmem_full[grp];
+  uint64_t* empty = &tmem_empty[grp];
+  uint32_t it = 0;
+  for (int t = grp; t < my_tiles; t += 2, ++it) {
+    const int m_tile = (int)blockIdx.x + t * (int)gridDim.x;
+    const int b = m_tile / tpi;
+    const int r = m_tile - b * tpi;
+    const int trow = r / tiles_x;
+    const int y = trow * 16 + ry, x = (r - trow * tiles_x) * 8 + rx;
+    const bool row_ok = (y < out_h) && (x < out_w);
+    const size_t pix = ((size_t)b * out_h + y) * out_w + x;
+    const float* film_b = film ? film + (size_t)b * film_ld : nullptr;
+    uint32_t rs0[8], rs1[8];
+    if (kRes) {  // first two 16-channel chunks of the residual travel while the MMAs finish
+      if (row_ok) {
+        ldg256(resid + pix * (size_t)res_ld, rs0);
+        if (nch > 1) ldg256(resid + pix * (size_t)res_ld + 16, rs1);
+      }
+    }
+    if (warp == 10 && lane == 0) h_ts(2, t, 0);
+    mbar_wait(full, it & 1u);
+    tc_fence_after();
+    if (warp == 10 && lane == 0) h_ts(2, t, 1);
+    float s1 = 0.f, s2 = 0.f;
+    auto process = [&](const uint32_t (&acc)[16], const uint32_t (&rs)[8], int cc) {
+      const int ng = cc * 16;
+      const int nrem = n_valid - ng;
+      if (!row_ok || nrem <= 0) return;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+      if (nrem >= 16) {
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 tq = __ldg(reinterpret_cast<const float4*>(bias + ng + j));
+            v[j] += tq.x; v[j + 1] += tq.y; v[j + 2] += tq.z; v[j + 3] += tq.w;
+          }
+        }
+        if (film_b) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 tq = __ldg(reinterpret_cast<const float4*>(film_b + ng + j));
+            v[j] += tq.x; v[j + 1] += tq.y; v[j + 2] += tq.z; v[j + 3] += tq.w;
+          }
+        }
+        if (kRes) {
+          float rr[16];
+          unpack16(rs, rr);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += rr[j];
+        }
+        if (kAct) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = swish_half(0.5f * v[j]);
+        }
+        if (kStats) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            s1 += v[j];
+            s2 = fmaf(v[j], v[j], s2);
+          }
+        }
+        if (kNchw) {
+          float* o = out_nchw + ((size_t)b * n_valid + ng) * hw + (size_t)y * out_w + x;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[(size_t)j * hw] = v[j];
+        } else {
+          uint32_t w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const __nv_bfloat162 tq = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            w[j] = *reinterpret_cast<const uint32_t*>(&tq);
+          }
+          stg256(outp + pix * (size_t)out_ld + ng, w);
+        }
+      } else {  // ragged last chunk (n_valid % 16 != 0): scalar path
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j < nrem) {
+            float t2 = v[j];
+            if (bias) t2 += __ldg(bias + ng + j);
+            if (film_b) t2 += __ldg(film_b + ng + j);
+            if (kRes) t2 += __bfloat162float(resid[pix * (size_t)res_ld + ng + j]);
+            if (kAct) t2 = swish_half(0.5f * t2);
+            if (kStats) { s1 += t2; s2 = fmaf(t2, t2, s2); }
+            if (kNchw) out_nchw[((size_t)b * n_valid + ng + j) * hw + (size_t)y * out_w + x] = t2;
+            else outp[pix * (size_t)out_ld + ng + j] = __float2bfloat16(t2);
+          }
+        }
+      }
+    };
+    for (int cc = 0; cc < nch; cc += 2) {
+      uint32_t a0[16], a1[16];
+      const bool two = cc + 1 < nch;
+      if (kRes && cc > 0 && row_ok) {
+        ldg256(resid + pix * (size_t)res_ld + cc * 16, rs0);
+        if (two) ldg256(resid + pix * (size_t)res_ld + cc * 16 + 16, rs1);
+      }
+      tmem_ld16(tm_lane + (uint32_t)(cc * 16), a0);
+      if (two) tmem_ld16(tm_lane + (uint32_t)(cc * 16 + 16), a1);
+      tmem_ld_wait();
+      if (cc + 2 >= nch) {  // last TMEM read of this tile: hand the accumulator back before the math and the stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty);
+      }
+      process(a0, rs0, cc);
+      if (two) process(a1, rs1, cc + 1);
+    }
+    if (kStats) {
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        atomicAdd(stats + 2 * (size_t)b, (double)s1);
+        atomicAdd(stats + 2 * (size_t)b + 1, (double)s2);
+      }
+    }
+    if (warp == 10 && lane == 0) h_ts(2, t, 2);
+  }
+}
+
+template <int F>
+__global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __grid_constant__ HaloKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.stages * p.stage_bytes;
+  float* s_gamma = reinterpret_cast<float*>(smem_b + (size_t)(9 * p.nslab) * p.b_slot_bytes);
+  float* s_beta = s_gamma + p.cin;
+  float2* s_stat = reinterpret_cast<float2*>(s_beta + p.cin);
+  const int n_stat = p.gn_stats ? (p.batch < kHMaxStat ? p.batch : kHMaxStat) : 0;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + n_stat);
+  uint64_t* a_tma = bars;                       // [stages] TMA landed
+  uint64_t* a_ready = bars + kHMaxStages;       // [stages] transformed (count 256)
+  uint64_t* a_empty = bars + 2 * kHMaxStages;   // [stages] MMAs done
+  uint64_t* tmem_full = bars + 3 * kHMaxStages; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint64_t* b_full = tmem_empty + 2;            // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool gn = p.gn_stats != nullptr;
+
+  if (gn) {
+    for (int i = threadIdx.x; i < p.cin; i += blockDim.x) {
+      s_gamma[i] = p.gn_gamma[i];
+      s_beta[i] = p.gn_beta[i];
+    }
+    for (int i = threadIdx.x; i < n_stat; i += blockDim.x) {  // per-sample (mean, rstd), fp64 once per CTA
+      const double s = p.gn_stats[2 * i], ss = p.gn_stats[2 * i + 1];
+      const double m = s / p.gn_count;
+      double var = ss / p.gn_count - m * m;
+      if (var < 0) var = 0;
+      s_stat[i] = make_float2((float)m, rsqrtf((float)var + p.gn_eps));
+    }
+  }
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(&a_tma[i], 1);
+        mbar_init(&a_ready[i], kHxfThreads);
+        mbar_init(&a_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full[i], 1);
+        mbar_init(&tmem_empty[i], kHEpiWarps / 2);
+      }
+      mbar_init(b_full, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ===================== transform warps (only with the GroupNorm prologue) =====================
+    if (gn) {
+      const uint32_t a_base = smem_u32(smem_a);
+      if (p.kslab == 64) halo_transform_loop<8>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x);
+      else if (p.kslab == 32) halo_transform_loop<4>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x);
+      else halo_transform_loop<2>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x);
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer (converged warp, elected lane issues) =====================
+    uint64_t* a_full = gn ? a_ready : a_tma;
+    if (p.kslab == 64) halo_mma_loop<4>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles);
+    else if (p.kslab == 32) halo_mma_loop<2>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles);
+    else halo_mma_loop<1>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles);
+  } else if (warp == 9) {
+    // ===================== TMA producer: resident weights once, then the halo ring =====================
+    if (lane == 0) {
+      mbar_expect_tx(b_full, (uint32_t)(9 * p.nslab) * p.b_slot_bytes);
+      for (int slab = 0; slab < p.nslab; ++slab)
+        for (int tap = 0; tap < 9; ++tap)
+          tma_load_3d(&p.tmB, b_full, smem_b + (size_t)(slab * 9 + tap) * p.b_slot_bytes, slab * p.kslab, 0, tap);
+      const uint32_t tx = (uint32_t)(kHPx * p.span);
+      const uint32_t nst = (uint32_t)p.stages;
+      HaloIter it;
+      it.init(p);
+      uint32_t stage = 0, phase = 0;
+      int u = 0;
+      for (; it.remaining > 0; it.next(), ++u) {
+        h_ts(0, u, 0);
+        mbar_wait(&a_empty[stage], phase ^ 1u);
+        h_ts(0, u, 1);
+        mbar_expect_tx(&a_tma[stage], tx);
+        tma_load_4d(&p.tmA, &a_tma[stage], smem_a + (size_t)stage * p.stage_bytes, it.slab * p.kslab, it.tx * 8 - 1, it.ty * 16 - 1, it.b);
+        if (++stage == nst) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 10..17): two groups of 4 warps, one TMEM accumulator each =====================
+    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+int conv3_halo_set_debug_ts(long long* ptr) {
+  DDIF_CUDA_CHECK(cudaMemcpyToSymbol(g_halo_ts, &ptr, sizeof(ptr)));
+  return DDIF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled ddif_get_encode();
+int ddif_sm_count();
+
+typedef void (*HaloKernel)(const HaloKParams);
+static int halo_flags(const ddif_gemm_t& g) {
+  return (g.residual ? kEpiRes : 0) | (g.act ? kEpiAct : 0) | (g.stats ? kEpiStats : 0) | (g.out_nchw ? kEpiNchw : 0);
+}
+static HaloKernel halo_kernel(int f) {
+  switch (f) {
+    case 0: return conv3x3_halo_tc_kernel<0>;
+    case 1: return conv3x3_halo_tc_kernel<1>;
+    case 2: return conv3x3_halo_tc_kernel<2>;
+    case 3: return conv3x3_halo_tc_kernel<3>;
+    case 4: return conv3x3_halo_tc_kernel<4>;
+    case 5: return conv3x3_halo_tc_kernel<5>;
+    case 6: return conv3x3_halo_tc_kernel<6>;
+    case 7: return conv3x3_halo_tc_kernel<7>;
+    case 8: return conv3x3_halo_tc_kernel<8>;
+    default: return nullptr;
+  }
+}
+static cudaError_t halo_set_attrs() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  for (int f = 0; f <= 8; ++f) {
+    cudaError_t e = cudaFuncSetAttribute(halo_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+  }
+  done = true;
+  return cudaSuccess;
+}
+
+struct HaloGeom {
+  int kslab, nslab, span, stages, stage_bytes, b_slot, n_stat, misc, smem;
+};
+
+static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
+  if (g.nseg != 1 || g.taps[0] != 9 || g.stride != 1 || g.w_per_sample[0] || g.a_up != 0) return false;
+  if (g.out_w < 8 || g.out_h < 8) return false;
+  if (g.a_c[0] % 16 != 0 || g.a_c[0] > 512) return false;
+  if (g.n_pad % 16 != 0 || g.n_pad > 256 || g.n_pad < 16) return false;
+  if (g.a_ld[0] % 8 != 0 || g.w_k[0] % 8 != 0 || g.w_k[0] < g.a_c[0]) return false;
+  if (g.mod || halo_kernel(halo_flags(g)) == nullptr) return false;  // CSM modulation / fp32 store + residual: generic kernel
+  if (g.out && g.out_nchw) return false;
+  if (g.out && g.out_ld % 16 != 0) return false;                       // 32-byte stores
+  if (g.residual && g.res_ld % 16 != 0) return false;
+  if (g.film && g.film_ld % 4 != 0) return false;
+  if (!g.out && !g.out_nchw) return false;
+  const int cin = (int)g.a_c[0];
+  h.kslab = cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16);
+  h.nslab = cin / h.kslab;
+  h.span = h.kslab * 2;
+  h.stage_bytes = (kHPx * h.span + 1023) & ~1023;
+  h.b_slot = (int)g.n_pad * h.span;
+  h.n_stat = g.gn_stats ? (int)(g.batch < kHMaxStat ? g.batch : kHMaxStat) : 0;
+  h.misc = 2 * cin * 4 + h.n_stat * 8 + (3 * kHMaxStages + 8) * 8 + 64 + 1024;
+  const int budget = 227 * 1024 - h.misc - 9 * h.nslab * h.b_slot;
+  int st = budget / h.stage_bytes;
+  if (st > kHMaxStages) st = kHMaxStages;
+  if (st < 2) return false;
+  h.stages = st;
+  h.smem = st * h.stage_bytes + 9 * h.nslab * h.b_slot + h.misc;
+  return true;
+}
+
+bool conv3_halo_applicable(const ddif_gemm_t& g) {
+  HaloGeom h;
+  return halo_geometry(g, h);
+}
+
+int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
+  HaloKParams& p = *reinterpret_cast<HaloKParams*>(L.kparams);
+  static_assert(sizeof(HaloKParams) <= sizeof(L.kparams), "kparams buffer too small");
+  memset(&p, 0, sizeof(p));
+  PFN_encodeTiled enc = ddif_get_encode();
+  if (!enc) return DDIF_ERR_DRIVER;
+  DDIF_CUDA_CHECK(halo_set_attrs());
+  HaloGeom h;
+  if (!halo_geometry(g, h)) return DDIF_ERR_SHAPE;
+  if (g.n_valid > g.n_pad || g.n_valid < 1) return DDIF_ERR_SHAPE;
+  const int cin = (int)g.a_c[0];
+  p.cin = cin; p.kslab = h.kslab; p.nslab = h.nslab; p.span = h.span;
+  p.batch = (int)g.batch; p.out_h = (int)g.out_h; p.out_w = (int)g.out_w;
+  if ((int)g.a_h[0] != p.out_h || (int)g.a_w[0] != p.out_w) return DDIF_ERR_SHAPE;
+  p.tiles_x = (int)ceil_div(p.out_w, 8);
+  p.tiles_y = (int)ceil_div(p.out_h, 16);
+  p.num_tiles = p.tiles_x * p.tiles_y * p.batch;
+  p.bn = (int)g.n_pad;
+  p.stages = h.stages;
+  p.stage_bytes = (uint32_t)h.stage_bytes;
+  p.b_slot_bytes = (uint32_t)h.b_slot;
+  p.layout_type = p.span == 128 ? 2u : p.span == 64 ? 4u : 6u;
+  uint32_t cols = 32;
+  while ((int)cols < 2 * p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  L.smem_bytes = h.smem;
+  L.grid_y = 1;
+  const int sms = ddif_sm_count();
+  L.grid_x = p.num_tiles < sms ? p.num_tiles : sms;
+  L.variant = 2;
+  L.flags = halo_flags(g);
+  const CUtensorMapSwizzle sw = p.span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : p.span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)g.a_w[0], (cuuint64_t)g.a_h[0], (cuuint64_t)g.batch};
+    cuuint64_t strides[3] = {(cuuint64_t)g.a_ld[0] * 2, (cuuint64_t)g.a_w[0] * g.a_ld[0] * 2, (cuuint64_t)g.a_h[0] * g.a_w[0] * g.a_ld[0] * 2};
+    cuuint32_t box[4] = {(cuuint32_t)p.kslab, (cuuint32_t)kHW, (cuuint32_t)kHH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g.a[0]), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)g.w_k[0], (cuuint64_t)g.n_pad, (cuuint64_t)g.w_s[0]};
+    cuuint64_t strides[2] = {(cuuint64_t)g.w_k[0] * 2, (cuuint64_t)g.n_pad * g.w_k[0] * 2};
+    cuuint32_t box[3] = {(cuuint32_t)p.kslab, (cuuint32_t)p.bn, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(g.w[0]), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
+  }
+  p.gn_stats = g.gn_stats;
+  p.gn_gamma = g.gn_gamma;
+  p.gn_beta = g.gn_beta;
+  p.gn_eps = (float)g.gn_eps;
+  p.gn_act = (int)g.gn_act;
+  p.gn_count = (double)cin * p.out_h * p.out_w;
+  if (p.gn_stats && (!p.gn_gamma || !p.gn_beta)) return DDIF_ERR_ARG;
+  EpiParams& e = p.epi;
+  e.bias = g.bias; e.film = g.film; e.film_ld = (int)g.film_ld; e.mod = (const bf16*)g.mod; e.residual = (const bf16*)g.residual;
+  e.res_ld = (int)g.res_ld; e.act = (int)g.act; e.out = (bf16*)g.out; e.out_ld = (int)g.out_ld; e.out_nchw = g.out_nchw; e.stats = g.stats;
+  e.n_valid = (int)g.n_valid; e.batch = p.batch; e.out_h = p.out_h; e.out_w = p.out_w;
+  if (e.out && (e.out_ld % 8 != 0)) return DDIF_ERR_SHAPE;
+  if (e.mod && (e.n_valid % 8 != 0)) return DDIF_ERR_SHAPE;
+  if (e.residual && (e.res_ld % 8 != 0)) return DDIF_ERR_SHAPE;
+  return DDIF_OK;
+}
+
+int conv3_halo_launch(const GemmLaunch& L, cudaStream_t stream) {
+  const HaloKParams& p = *reinterpret_cast<const HaloKParams*>(L.kparams);
+  HaloKernel k = halo_kernel(L.flags);
+  if (!k) return DDIF_ERR_STATE;
+  k<<<dim3(L.grid_x, 1), kHThreads, L.smem_bytes, stream>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+}  // namespace ddif

@@ -12,7 +12,9 @@ namespace ddif {
 struct alignas(64) GemmLaunch {
   unsigned char kparams[1024];
   int grid_x, grid_y, smem_bytes;
-  int variant;  // 0: conv_igemm_tc_kernel (TMA activations), 1: conv3x3_fused_tc_kernel (LDG halo tile + fused GN)
+  int flags;    // variant 2: compile-time epilogue specialisation (kEpi* bits)
+  int variant;  // 0: conv_igemm_tc_kernel (TMA tap boxes), 1: conv3x3_fused_tc_kernel (LDG halo, 3 shifted copies; nearest-x2 loader),
+                // 2: conv3x3_halo_tc_kernel (one TMA halo tile feeds all nine taps; in-place GN+Swish)
 };
 
 int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L);
@@ -21,6 +23,10 @@ bool conv3_applicable(const ddif_gemm_t& g);
 int conv3_prepare(const ddif_gemm_t& g, GemmLaunch& L);
 int conv3_launch(const GemmLaunch& L, cudaStream_t stream);
 int conv3_set_debug_ts(long long* ptr);
+bool conv3_halo_applicable(const ddif_gemm_t& g);
+int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L);
+int conv3_halo_launch(const GemmLaunch& L, cudaStream_t stream);
+int conv3_halo_set_debug_ts(long long* ptr);
 
 // elementwise.cu
 int launch_in_convert(const ddif_in_convert_t& p, cudaStream_t s);

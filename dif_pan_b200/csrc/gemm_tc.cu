@@ -9,6 +9,8 @@
 // K-major stage; one elected thread issues tcgen05.mma (M128 x N x K16) into a TMEM accumulator; tcgen05.commit
 // frees the stage.  Warp roles: warp0 = TMA producer, warp1 = TMEM alloc + MMA issue, warps2-5 = epilogue
 // (tcgen05.ld -> bias / FiLM / CSM modulation / residual / SiLU / GroupNorm statistics -> bf16 NHWC store).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ddif_internal.h"
 #include "epilogue.cuh"
@@ -281,6 +283,10 @@ static CUtensorMapSwizzle swizzle_for_span(int span) {
 int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   const bool wants_fused = g.gn_stats != nullptr || g.a_up != 0;
   if (wants_fused && !conv3_applicable(g)) return DDIF_ERR_SHAPE;  // the prologue exists only in the fused 3x3 kernel
+  if (!g.force_tma && conv3_halo_applicable(g)) {
+    static const bool no_halo = getenv("DDIF_NO_HALO") != nullptr;  // A/B switch for profiling only
+    if (!no_halo) return conv3_halo_prepare(g, L);
+  }
   if (wants_fused || (conv3_applicable(g) && !g.force_tma)) return conv3_prepare(g, L);
   L.variant = 0;
   GemmKParams& p = *reinterpret_cast<GemmKParams*>(L.kparams);
@@ -407,6 +413,7 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
 
 int gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   if (L.variant == 1) return conv3_launch(L, stream);
+  if (L.variant == 2) return conv3_halo_launch(L, stream);
   const GemmKParams& p = *reinterpret_cast<const GemmKParams*>(L.kparams);
   conv_igemm_tc_kernel<<<dim3(L.grid_x, L.grid_y), kGemmThreads, L.smem_bytes, stream>>>(p);
   DDIF_LAUNCH_CHECK();

@@ -182,8 +182,9 @@ int ddif_plan_profile(ddif_plan_t* plan, ddif_stream_t stream, float* ms, int* k
 /* Number of kernel launches the plan issues per run. */
 int ddif_plan_launches(const ddif_plan_t* plan);
 
-/* Debug: device buffer of 3*64*4 int64 receiving clock64() at the pipeline hand-offs of CTA 0 of the fused 3x3 kernel
- * (role-major: loader, MMA issuer, epilogue; 64 tiles; 4 stamps).  NULL disables.  Not for production use. */
+/* Debug: device buffer of 4*64*4 int64 receiving clock64() at the pipeline hand-offs of CTA 0 of the 3x3 conv kernels
+ * (role-major: loader / TMA producer, MMA issuer, epilogue, GN transform; 64 tiles; 4 stamps).  NULL disables.
+ * Not for production use. */
 int ddif_debug_set_timestamps(void* device_ptr);
 
 /* Named convenience wrappers (same structs), the symbols a reference-side binding would call directly. */

@@ -25,16 +25,19 @@
 
 namespace ddif {
 
-static constexpr int kHxfThreads = 256;                    // transform warps 0..7
-static constexpr int kHEpiWarps = 8;                       // warps 10..17
-static constexpr int kHThreads = kHxfThreads + 64 + 32 * kHEpiWarps;
+static constexpr int kHxfThreads = 256;                    // transform warps 0..7: two groups of 128, alternating stages
+static constexpr int kHxfGroup = kHxfThreads / 2;
+static constexpr int kHEpiWarps = 8;                       // warps 10..17: two groups of 4, one TMEM accumulator each
+static constexpr int kHThreads = kHxfThreads + 64 + 32 * kHEpiWarps + 32;  // + MMA warps 8, 9 + TMA producer warp 18
 static constexpr int kHW = 10, kHH = 18, kHPx = kHW * kHH;  // halo of an 8 x 16 tile
-static constexpr int kHMaxStages = 4;
+static constexpr int kHMaxStages = 8;
 static constexpr int kHMaxStat = 1024;
 
 struct alignas(64) HaloKParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmR;   // residual tile box (L2 prefetch only)
+  int has_res_map;
   int cin, kslab, nslab, span;
   int batch, out_h, out_w;
   int tiles_x, tiles_y, num_tiles;
@@ -54,8 +57,9 @@ struct alignas(64) HaloKParams {
 // Debug hook (ddif_debug_set_timestamps): CTA 0 records clock64() at the pipeline hand-offs of its first 64 tiles:
 // ts[(role*64 + tile)*4 + k], role 0 = TMA producer, 1 = MMA issuer, 2 = epilogue warp 10 lane 0, 3 = transform thread 0.
 __device__ long long* g_halo_ts = nullptr;
-__device__ __forceinline__ void h_ts(int role, int tile, int k) {
-  if (g_halo_ts && blockIdx.x == 0 && tile < 64) g_halo_ts[(role * 64 + tile) * 4 + k] = clock64();
+// `ts` is read from g_halo_ts ONCE per thread (a probe is then a clock read + one fire-and-forget store).
+__device__ __forceinline__ void h_ts(long long* ts, int role, int tile, int k) {
+  if (ts && tile < 64) ts[(role * 64 + tile) * 4 + k] = clock64();
 }
 
 __device__ __forceinline__ void h_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -96,31 +100,44 @@ struct HaloIter {
 };
 
 // ---- transform warps: GroupNorm affine (+Swish) of a landed stage, in place -------------------------------------------
+// Group g (warps 4g..4g+3) takes the units (tile x slab) u = g, g+2, ...: each group has two unit periods per stage, so
+// the wait -> LDS -> math -> STS -> fence -> arrive latency chain of one stage overlaps the other group's.
 template <int NCK>
 __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32_t a_base, uint64_t* a_tma, uint64_t* a_ready,
-                                                    const float* s_gamma, const float* s_beta, const float2* s_stat, int lt) {
-  constexpr int LPT = (kHPx * NCK + kHxfThreads - 1) / kHxfThreads;
-  constexpr int RPP = kHxfThreads / NCK;  // halo rows per pass
+                                                    const float* s_gamma, const float* s_beta, const float2* s_stat, int tid, long long* dts) {
+  constexpr int RPP = kHxfGroup / NCK;                 // halo rows per pass of one group
+  constexpr int NPASS = (kHPx + RPP - 1) / RPP;        // 12 / 6 / 3 chunks per thread
+  constexpr int BATCH = NPASS % 6 == 0 ? 6 : 3;
+  static_assert(NPASS % BATCH == 0, "pass batching");
+  const int grp = tid / kHxfGroup, lt = tid % kHxfGroup;
   const int c = lt % NCK;
   const int r0 = lt / NCK;
-  uint32_t soff[LPT];
-  int hy[LPT], hx[LPT];
-#pragma unroll
-  for (int k = 0; k < LPT; ++k) {
-    const int r = r0 + k * RPP;
-    const uint32_t sw = NCK == 8 ? ((uint32_t)r & 7u) : (NCK == 4 ? (((uint32_t)r >> 1) & 3u) : (((uint32_t)r >> 2) & 1u));
-    soff[k] = (uint32_t)r * (uint32_t)(NCK * 16) + (((uint32_t)c ^ sw) << 4);
-    hy[k] = r < kHPx ? r / kHW : -100000;
-    hx[k] = r % kHW;
-  }
   const float hs = p.gn_act ? 0.5f : 1.0f;  // swish(t) = h*tanh(h) + h with h = t/2: the affine is pre-halved
   const uint32_t nst = (uint32_t)p.stages;
+  // per-thread tables (tile independent): swizzled smem offset and halo (line, column) of each of the thread's chunks
+  uint32_t soff[NPASS];
+  int hyx[NPASS];  // hy << 8 | hx; rows past the halo get hy = 255 (never in bounds)
+#pragma unroll
+  for (int k = 0; k < NPASS; ++k) {
+    const int r = r0 + k * RPP;
+    const int hy = r / kHW, hx = r - hy * kHW;
+    const uint32_t sw = NCK == 8 ? ((uint32_t)r & 7u) : (NCK == 4 ? (((uint32_t)r >> 1) & 3u) : (((uint32_t)r >> 2) & 1u));
+    soff[k] = (uint32_t)r * (uint32_t)(NCK * 16) + (((uint32_t)c ^ sw) << 4);
+    hyx[k] = r < kHPx ? ((hy << 8) | hx) : (255 << 8);
+  }
+  const bool act = p.gn_act != 0;
+  const unsigned H = (unsigned)p.out_h, W = (unsigned)p.out_w;
   HaloIter it;
   it.init(p);
   uint32_t stage = 0, phase = 0;
-  int cur_b = -1, cur_slab = -1, tcount = 0;
-  float a[8], d[8];
-  for (; it.remaining > 0; it.next()) {
+  auto advance = [&]() {
+    it.next();
+    if (++stage == nst) { stage = 0; phase ^= 1u; }
+  };
+  if (grp == 1 && it.remaining > 0) advance();
+  int cur_b = -1, cur_slab = -1, tcount = grp;
+  f32x2 a2[4], d2[4];
+  while (it.remaining > 0) {
     if (it.b != cur_b || it.slab != cur_slab) {
       cur_b = it.b; cur_slab = it.slab;
       float mean, rstd;
@@ -128,61 +145,70 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
         const float2 mr = s_stat[it.b];
         mean = mr.x; rstd = mr.y;
       } else {
-        const double s = p.gn_stats[2 * it.b], ss = p.gn_stats[2 * it.b + 1];
-        const double m = s / p.gn_count;
+        const double sm = p.gn_stats[2 * it.b], ss = p.gn_stats[2 * it.b + 1];
+        const double m = sm / p.gn_count;
         double var = ss / p.gn_count - m * m;
         if (var < 0) var = 0;
         mean = (float)m;
         rstd = rsqrtf((float)var + p.gn_eps);
       }
       const int ch0 = it.slab * p.kslab + c * 8;
+      const float sc = hs * rstd;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a[j] = hs * rstd * s_gamma[ch0 + j];
-        d[j] = hs * s_beta[ch0 + j] - mean * a[j];
+      for (int j = 0; j < 4; ++j) {
+        const float a0 = sc * s_gamma[ch0 + 2 * j], a1 = sc * s_gamma[ch0 + 2 * j + 1];
+        a2[j] = pk2(a0, a1);
+        d2[j] = pk2(fmaf(-mean, a0, hs * s_beta[ch0 + 2 * j]), fmaf(-mean, a1, hs * s_beta[ch0 + 2 * j + 1]));
       }
     }
     const int y0 = it.ty * 16 - 1, x0 = it.tx * 8 - 1;
     const uint32_t sbase = a_base + stage * p.stage_bytes;
-    if (lt == 0) h_ts(3, tcount, 0);
+    if (tid == 0) h_ts(dts, 3, tcount, 0);
     mbar_wait(&a_tma[stage], phase);
-    if (lt == 0) h_ts(3, tcount, 1);
-    uint4 v[LPT];
-    bool ok[LPT];
+    if (tid == 0) h_ts(dts, 3, tcount, 1);
 #pragma unroll
-    for (int k = 0; k < LPT; ++k) {
-      ok[k] = (unsigned)(y0 + hy[k]) < (unsigned)p.out_h && (unsigned)(x0 + hx[k]) < (unsigned)p.out_w;
-      if (ok[k]) v[k] = h_lds128(sbase + soff[k]);
-    }
+    for (int k0 = 0; k0 < NPASS; k0 += BATCH) {
+      uint4 v[BATCH];
+      bool ok[BATCH];
 #pragma unroll
-    for (int k = 0; k < LPT; ++k) {
-      if (ok[k]) {
-        float f[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(&v[k]), f);
-        if (p.gn_act) {
+      for (int k = 0; k < BATCH; ++k) {
+        ok[k] = (unsigned)(y0 + (hyx[k0 + k] >> 8)) < H && (unsigned)(x0 + (hyx[k0 + k] & 255)) < W;
+        if (ok[k]) v[k] = h_lds128(sbase + soff[k0 + k]);
+      }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) f[q] = swish_half(fmaf(f[q], a[q], d[q]));
-        } else {
+      for (int k = 0; k < BATCH; ++k) {
+        if (ok[k]) {
+          const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+          uint32_t o[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) f[q] = fmaf(f[q], a[q], d[q]);
+          for (int q = 0; q < 4; ++q) {
+            f32x2 t = fma2(bf2_to_f2(w[q]), a2[q], d2[q]);
+            if (act) t = swish_half2(t);
+            o[q] = f2_to_bf2(t);
+          }
+          h_sts128(sbase + soff[k0 + k], make_uint4(o[0], o[1], o[2], o[3]));
         }
-        const bf16x8 pk = pack8(f);
-        h_sts128(sbase + soff[k], *reinterpret_cast<const uint4*>(&pk));
       }
     }
-    if (lt == 0) h_ts(3, tcount, 2);
+    if (tid == 0) h_ts(dts, 3, tcount, 2);
     h_fence_proxy_async();
     mbar_arrive(&a_ready[stage]);
-    if (lt == 0) h_ts(3, tcount, 3);
-    ++tcount;
-    if (++stage == nst) { stage = 0; phase ^= 1u; }
+    if (tid == 0) h_ts(dts, 3, tcount, 3);
+    tcount += 2;
+    advance();
+    if (it.remaining > 0) advance();
   }
 }
 
-// ---- MMA warp --------------------------------------------------------------------------------------------------------
+// ---- MMA warps -------------------------------------------------------------------------------------------------------
+// Two issuing warps: warp w takes tiles t = w, w+2, ... into TMEM accumulator w.  A tcgen05.mma issue blocks for its
+// ~45-cycle slot (profiles/r01_microbench_umma_rate.txt), so a single issuer adds its barrier waits (~600 cycles per
+// tile) to the tensor pipe's critical path; with two, one warp waits for its next stage / accumulator while the other's
+// MMAs execute.
 template <int KSTEPS>
 __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_base, uint32_t b_base, uint64_t* a_full, uint64_t* a_empty,
-                                              uint64_t* b_full, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int my_tiles) {
+                                              uint64_t* b_full, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int my_tiles,
+                                              int w, long long* dts) {
   const uint32_t span = (uint32_t)p.span;
   const uint64_t desc_a0 = make_smem_desc(a_base, (uint32_t)kHW * span, p.layout_type);  // SBO = one halo line (10 rows)
   const uint64_t desc_b0 = make_smem_desc(b_base, 8u * span, p.layout_type);
@@ -192,20 +218,25 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
   for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((uint32_t)((tap / 3) * kHW + (tap % 3)) * span) >> 4;
   const uint32_t nst = (uint32_t)p.stages;
   uint32_t stage = 0, phase = 0;
+  auto advance = [&]() {
+    if (++stage == nst) { stage = 0; phase ^= 1u; }
+  };
+  if (w == 1)
+    for (int slab = 0; slab < p.nslab; ++slab) advance();
   mbar_wait(b_full, 0u);
   tc_fence_after();
-  for (int t = 0; t < my_tiles; ++t) {
-    const uint32_t acc = (uint32_t)t & 1u;
-    if ((threadIdx.x & 31) == 0) h_ts(1, t, 0);
-    mbar_wait(&tmem_empty[acc], (((uint32_t)t >> 1) & 1u) ^ 1u);
+  const uint32_t tmem_d = tmem_base + (uint32_t)w * (uint32_t)p.bn;
+  uint32_t itn = 0;
+  for (int t = w; t < my_tiles; t += 2, ++itn) {
+    if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 0);
+    mbar_wait(&tmem_empty[w], (itn & 1u) ^ 1u);
     tc_fence_after();
-    if ((threadIdx.x & 31) == 0) h_ts(1, t, 1);
-    const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.bn;
+    if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 1);
     uint64_t db = desc_b0;
     for (int slab = 0; slab < p.nslab; ++slab) {
       mbar_wait(&a_full[stage], phase);
       tc_fence_after();
-      if ((threadIdx.x & 31) == 0) h_ts(1, t, 2);
+      if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 2);
       const uint64_t da = desc_a0 + (uint64_t)(stage * stage16);
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
@@ -213,10 +244,11 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
         db += b16;
       }
       umma_commit_elect(&a_empty[stage]);
-      if (++stage == nst) { stage = 0; phase ^= 1u; }
+      advance();
     }
-    umma_commit_elect(&tmem_full[acc]);
-    if ((threadIdx.x & 31) == 0) h_ts(1, t, 3);
+    umma_commit_elect(&tmem_full[w]);
+    if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 3);
+    for (int slab = 0; slab < p.nslab; ++slab) advance();  // the other warp's tile
   }
 }
 
@@ -229,13 +261,12 @@ enum : int { kEpiRes = 1, kEpiAct = 2, kEpiStats = 4, kEpiNchw = 8 };
 
 template <int F>
 __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int warp,
-                                                   int lane, int my_tiles) {
+                                                   int lane, int my_tiles, long long* dts, float* s_add) {
   constexpr bool kRes = (F & kEpiRes) != 0, kAct = (F & kEpiAct) != 0, kStats = (F & kEpiStats) != 0, kNchw = (F & kEpiNchw) != 0;
   const int q = warp & 3;
   const int grp = (warp - 10) >> 2;
   const int row = q * 32 + lane;
   const int ry = row >> 3, rx = row & 7;
-  const int tpi = p.tiles_x * p.tiles_y;
   const int nch = p.bn >> 4;
   const int n_valid = p.epi.n_valid;
   const float* bias = p.epi.bias;
@@ -246,111 +277,143 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
   bf16* outp = p.epi.out;
   float* out_nchw = p.epi.out_nchw;
   double* stats = p.epi.stats;
-  const int out_h = p.out_h, out_w = p.out_w, tiles_x = p.tiles_x;
+  const int out_h = p.out_h, out_w = p.out_w, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
   const size_t hw = (size_t)out_h * out_w;
   const uint32_t tm_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * (uint32_t)p.bn;
   uint64_t* full = &tmem_full[grp];
   uint64_t* empty = &tmem_empty[grp];
+  // per-warp additive vector (bias, or FiLM row of the tile's sample [+ bias]) in shared memory: with ~200 KB of dynamic
+  // smem the L1 is a few KB, so per-tile __ldg of these vectors paid an L2 round trip per 16-channel chunk
+  float* addv = s_add + (warp - 10) * 256;
+  const bool has_add = bias != nullptr || film != nullptr;
+  const int nadd = (p.bn + 31) >> 5;  // values per lane
+  if (!film && bias) {
+    for (int k = 0; k < nadd; ++k) {
+      const int ch = lane + 32 * k;
+      addv[ch] = ch < n_valid ? bias[ch] : 0.f;
+    }
+    __syncwarp();
+  }
+  // divide-free walk over this group's tiles: start blockIdx.x + grp*gridDim.x, stride 2*gridDim.x
+  int b, ty, tx, sb, sy, sx;
+  {
+    const int tpi = tiles_x * tiles_y;
+    const int m0 = (int)blockIdx.x + grp * (int)gridDim.x, g2 = 2 * (int)gridDim.x;
+    b = m0 / tpi;
+    int r = m0 - b * tpi;
+    ty = r / tiles_x; tx = r - ty * tiles_x;
+    sb = g2 / tpi;
+    r = g2 - sb * tpi;
+    sy = r / tiles_x; sx = r - sy * tiles_x;
+  }
   uint32_t it = 0;
   for (int t = grp; t < my_tiles; t += 2, ++it) {
-    const int m_tile = (int)blockIdx.x + t * (int)gridDim.x;
-    const int b = m_tile / tpi;
-    const int r = m_tile - b * tpi;
-    const int trow = r / tiles_x;
-    const int y = trow * 16 + ry, x = (r - trow * tiles_x) * 8 + rx;
+    const int y = ty * 16 + ry, x = tx * 8 + rx;
     const bool row_ok = (y < out_h) && (x < out_w);
     const size_t pix = ((size_t)b * out_h + y) * out_w + x;
-    const float* film_b = film ? film + (size_t)b * film_ld : nullptr;
+    const bf16* res_px = kRes ? resid + pix * (size_t)res_ld : nullptr;
+    float fa[8];
+    if (film) {  // this tile's FiLM row travels while the MMAs finish
+      const float* film_b = film + (size_t)b * film_ld;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int ch = lane + 32 * k;
+        if (k < nadd) fa[k] = ch < n_valid ? __ldg(film_b + ch) + (bias ? __ldg(bias + ch) : 0.f) : 0.f;
+      }
+    }
     uint32_t rs0[8], rs1[8];
     if (kRes) {  // first two 16-channel chunks of the residual travel while the MMAs finish
       if (row_ok) {
-        ldg256(resid + pix * (size_t)res_ld, rs0);
-        if (nch > 1) ldg256(resid + pix * (size_t)res_ld + 16, rs1);
+        ldg256(res_px, rs0);
+        if (nch > 1) ldg256(res_px + 16, rs1);
       }
     }
-    if (warp == 10 && lane == 0) h_ts(2, t, 0);
     mbar_wait(full, it & 1u);
     tc_fence_after();
-    if (warp == 10 && lane == 0) h_ts(2, t, 1);
-    float s1 = 0.f, s2 = 0.f;
+    if (warp == 10 && lane == 0) h_ts(dts, 2, t, 0);
+    if (film) {
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < nadd) addv[lane + 32 * k] = fa[k];
+      __syncwarp();
+    }
+    f32x2 s1 = pk2(0.f, 0.f), s2 = pk2(0.f, 0.f);
     auto process = [&](const uint32_t (&acc)[16], const uint32_t (&rs)[8], int cc) {
       const int ng = cc * 16;
       const int nrem = n_valid - ng;
       if (!row_ok || nrem <= 0) return;
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
       if (nrem >= 16) {
-        if (bias) {
+        f32x2 v[8];
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 tq = __ldg(reinterpret_cast<const float4*>(bias + ng + j));
-            v[j] += tq.x; v[j + 1] += tq.y; v[j + 2] += tq.z; v[j + 3] += tq.w;
-          }
-        }
-        if (film_b) {
+        for (int j = 0; j < 8; ++j) v[j] = pk2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+        if (has_add) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 tq = __ldg(reinterpret_cast<const float4*>(film_b + ng + j));
-            v[j] += tq.x; v[j + 1] += tq.y; v[j + 2] += tq.z; v[j + 3] += tq.w;
+          for (int j = 0; j < 4; ++j) {
+            const float4 tq = *reinterpret_cast<const float4*>(addv + ng + 4 * j);
+            v[2 * j] = add2(v[2 * j], pk2(tq.x, tq.y));
+            v[2 * j + 1] = add2(v[2 * j + 1], pk2(tq.z, tq.w));
           }
         }
         if (kRes) {
-          float rr[16];
-          unpack16(rs, rr);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += rr[j];
+          for (int j = 0; j < 8; ++j) v[j] = add2(v[j], bf2_to_f2(rs[j]));
         }
         if (kAct) {
+          const f32x2 half2 = pk2(0.5f, 0.5f);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = swish_half(0.5f * v[j]);
+          for (int j = 0; j < 8; ++j) v[j] = swish_half2(mul2(v[j], half2));
         }
         if (kStats) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            s1 += v[j];
-            s2 = fmaf(v[j], v[j], s2);
+          for (int j = 0; j < 8; ++j) {
+            s1 = add2(s1, v[j]);
+            s2 = fma2(v[j], v[j], s2);
           }
         }
         if (kNchw) {
           float* o = out_nchw + ((size_t)b * n_valid + ng) * hw + (size_t)y * out_w + x;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[(size_t)j * hw] = v[j];
+          for (int j = 0; j < 8; ++j) {
+            float lo, hi;
+            upk2(v[j], lo, hi);
+            o[(size_t)(2 * j) * hw] = lo;
+            o[(size_t)(2 * j + 1) * hw] = hi;
+          }
         } else {
           uint32_t w[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const __nv_bfloat162 tq = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            w[j] = *reinterpret_cast<const uint32_t*>(&tq);
-          }
+          for (int j = 0; j < 8; ++j) w[j] = f2_to_bf2(v[j]);
           stg256(outp + pix * (size_t)out_ld + ng, w);
         }
       } else {  // ragged last chunk (n_valid % 16 != 0): scalar path
+        float ss1 = 0.f, ss2 = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (j < nrem) {
-            float t2 = v[j];
-            if (bias) t2 += __ldg(bias + ng + j);
-            if (film_b) t2 += __ldg(film_b + ng + j);
-            if (kRes) t2 += __bfloat162float(resid[pix * (size_t)res_ld + ng + j]);
+            float t2 = __uint_as_float(acc[j]);
+            if (has_add) t2 += addv[ng + j];
+            if (kRes) t2 += __bfloat162float(res_px[ng + j]);
             if (kAct) t2 = swish_half(0.5f * t2);
-            if (kStats) { s1 += t2; s2 = fmaf(t2, t2, s2); }
+            if (kStats) { ss1 += t2; ss2 = fmaf(t2, t2, ss2); }
             if (kNchw) out_nchw[((size_t)b * n_valid + ng + j) * hw + (size_t)y * out_w + x] = t2;
             else outp[pix * (size_t)out_ld + ng + j] = __float2bfloat16(t2);
           }
         }
+        if (kStats) { s1 = add2(s1, pk2(ss1, 0.f)); s2 = add2(s2, pk2(ss2, 0.f)); }
       }
     };
     for (int cc = 0; cc < nch; cc += 2) {
       uint32_t a0[16], a1[16];
       const bool two = cc + 1 < nch;
       if (kRes && cc > 0 && row_ok) {
-        ldg256(resid + pix * (size_t)res_ld + cc * 16, rs0);
-        if (two) ldg256(resid + pix * (size_t)res_ld + cc * 16 + 16, rs1);
+        ldg256(res_px + cc * 16, rs0);
+        if (two) ldg256(res_px + cc * 16 + 16, rs1);
       }
       tmem_ld16(tm_lane + (uint32_t)(cc * 16), a0);
       if (two) tmem_ld16(tm_lane + (uint32_t)(cc * 16 + 16), a1);
       tmem_ld_wait();
+      if (warp == 10 && lane == 0 && cc == 0) h_ts(dts, 2, t, 1);
       if (cc + 2 >= nch) {  // last TMEM read of this tile: hand the accumulator back before the math and the stores
         tc_fence_before();
         __syncwarp();
@@ -359,15 +422,21 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
       process(a0, rs0, cc);
       if (two) process(a1, rs1, cc + 1);
     }
+    if (warp == 10 && lane == 0) h_ts(dts, 2, t, 2);
     if (kStats) {
-      s1 = warp_sum(s1);
-      s2 = warp_sum(s2);
+      float l1, h1, l2, h2;
+      upk2(s1, l1, h1);
+      upk2(s2, l2, h2);
+      const float t1 = warp_sum(l1 + h1), t2 = warp_sum(l2 + h2);
       if (lane == 0) {
-        atomicAdd(stats + 2 * (size_t)b, (double)s1);
-        atomicAdd(stats + 2 * (size_t)b + 1, (double)s2);
+        atomicAdd(stats + 2 * (size_t)b, (double)t1);
+        atomicAdd(stats + 2 * (size_t)b + 1, (double)t2);
       }
     }
-    if (warp == 10 && lane == 0) h_ts(2, t, 2);
+    if (warp == 10 && lane == 0) h_ts(dts, 2, t, 3);
+    tx += sx; ty += sy; b += sb;
+    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    if (ty >= tiles_y) { ty -= tiles_y; ++b; }
   }
 }
 
@@ -383,7 +452,8 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   float* s_beta = s_gamma + p.cin;
   float2* s_stat = reinterpret_cast<float2*>(s_beta + p.cin);
   const int n_stat = p.gn_stats ? (p.batch < kHMaxStat ? p.batch : kHMaxStat) : 0;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + n_stat);
+  float* s_add = reinterpret_cast<float*>(s_stat + ((n_stat + 1) & ~1));  // [8 epilogue warps][256], 16-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_add + kHEpiWarps * 256);
   uint64_t* a_tma = bars;                       // [stages] TMA landed
   uint64_t* a_ready = bars + kHMaxStages;       // [stages] transformed (count 256)
   uint64_t* a_empty = bars + 2 * kHMaxStages;   // [stages] MMAs done
@@ -396,6 +466,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   const int lane = threadIdx.x & 31;
   const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool gn = p.gn_stats != nullptr;
+  long long* const dts = blockIdx.x == 0 ? g_halo_ts : nullptr;
 
   if (gn) {
     for (int i = threadIdx.x; i < p.cin; i += blockDim.x) {
@@ -410,7 +481,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
       s_stat[i] = make_float2((float)m, rsqrtf((float)var + p.gn_eps));
     }
   }
-  if (warp == 9 && lane == 0) {
+  if (warp == 18 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
   }
@@ -418,7 +489,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
     if (lane == 0) {
       for (int i = 0; i < p.stages; ++i) {
         mbar_init(&a_tma[i], 1);
-        mbar_init(&a_ready[i], kHxfThreads);
+        mbar_init(&a_ready[i], kHxfGroup);
         mbar_init(&a_empty[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
@@ -441,17 +512,18 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
     // ===================== transform warps (only with the GroupNorm prologue) =====================
     if (gn) {
       const uint32_t a_base = smem_u32(smem_a);
-      if (p.kslab == 64) halo_transform_loop<8>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x);
-      else if (p.kslab == 32) halo_transform_loop<4>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x);
-      else halo_transform_loop<2>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x);
+      if (p.kslab == 64) halo_transform_loop<8>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x, dts);
+      else if (p.kslab == 32) halo_transform_loop<4>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x, dts);
+      else halo_transform_loop<2>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x, dts);
     }
-  } else if (warp == 8) {
-    // ===================== MMA issuer (converged warp, elected lane issues) =====================
+  } else if (warp == 8 || warp == 9) {
+    // ===================== MMA issuers (converged warps, elected lane issues) =====================
     uint64_t* a_full = gn ? a_ready : a_tma;
-    if (p.kslab == 64) halo_mma_loop<4>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles);
-    else if (p.kslab == 32) halo_mma_loop<2>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles);
-    else halo_mma_loop<1>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles);
-  } else if (warp == 9) {
+    const int w = warp - 8;
+    if (p.kslab == 64) halo_mma_loop<4>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
+    else if (p.kslab == 32) halo_mma_loop<2>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
+    else halo_mma_loop<1>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
+  } else if (warp == 18) {
     // ===================== TMA producer: resident weights once, then the halo ring =====================
     if (lane == 0) {
       mbar_expect_tx(b_full, (uint32_t)(9 * p.nslab) * p.b_slot_bytes);
@@ -465,17 +537,18 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
       uint32_t stage = 0, phase = 0;
       int u = 0;
       for (; it.remaining > 0; it.next(), ++u) {
-        h_ts(0, u, 0);
+        h_ts(dts, 0, u, 0);
         mbar_wait(&a_empty[stage], phase ^ 1u);
-        h_ts(0, u, 1);
+        h_ts(dts, 0, u, 1);
         mbar_expect_tx(&a_tma[stage], tx);
         tma_load_4d(&p.tmA, &a_tma[stage], smem_a + (size_t)stage * p.stage_bytes, it.slab * p.kslab, it.tx * 8 - 1, it.ty * 16 - 1, it.b);
+        if (p.has_res_map && it.slab == 0) tma_prefetch_l2_4d(&p.tmR, 0, it.tx * 8, it.ty * 16, it.b);  // residual tile -> L2, `stages` tiles ahead
         if (++stage == nst) { stage = 0; phase ^= 1u; }
       }
     }
-  } else {
+  } else if (warp >= 10 && warp < 18) {
     // ===================== epilogue (warps 10..17): two groups of 4 warps, one TMEM accumulator each =====================
-    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles);
+    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, dts, s_add);
     tc_fence_before();
   }
   __syncthreads();
@@ -549,7 +622,7 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
   h.stage_bytes = (kHPx * h.span + 1023) & ~1023;
   h.b_slot = (int)g.n_pad * h.span;
   h.n_stat = g.gn_stats ? (int)(g.batch < kHMaxStat ? g.batch : kHMaxStat) : 0;
-  h.misc = 2 * cin * 4 + h.n_stat * 8 + (3 * kHMaxStages + 8) * 8 + 64 + 1024;
+  h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + (3 * kHMaxStages + 8) * 8 + 64 + 1024;
   const int budget = 227 * 1024 - h.misc - 9 * h.nslab * h.b_slot;
   int st = budget / h.stage_bytes;
   if (st > kHMaxStages) st = kHMaxStages;
@@ -614,6 +687,16 @@ int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
     CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(g.w[0]), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
+  }
+  if (g.residual) {
+    cuuint64_t dims[4] = {(cuuint64_t)g.n_valid, (cuuint64_t)g.out_w, (cuuint64_t)g.out_h, (cuuint64_t)g.batch};
+    cuuint64_t strides[3] = {(cuuint64_t)g.res_ld * 2, (cuuint64_t)g.out_w * g.res_ld * 2, (cuuint64_t)g.out_h * g.out_w * g.res_ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)(g.n_valid / 8 * 8), 8, 16, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (box[0] >= 8 && box[0] <= 256 &&
+        enc(&p.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g.residual), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+      p.has_res_map = 1;
   }
   p.gn_stats = g.gn_stats;
   p.gn_gamma = g.gn_gamma;

@@ -35,7 +35,7 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 
 def gemm(srcs, weights, n_valid, *, taps, stride=1, bias=None, film=None, mod=None, residual=None, act=0,
-         per_sample=None, want_nchw=False, want_stats=False, out_hw=None, gn=None, a_up=0, force_tma=0):
+         per_sample=None, want_nchw=False, want_stats=False, out_hw=None, gn=None, a_up=0, force_tma=0, reuse=None, sync=True):
     """Run DDIF_OP_GEMM on NHWC bf16 tensors; returns (out_nhwc_bf16 | out_nchw_f32, stats | None).
     gn = (stats[B,2] f64, gamma, beta, act) fuses GroupNorm(+Swish) of the source into the 3x3 kernel."""
     a0 = srcs[0]
@@ -43,9 +43,12 @@ def gemm(srcs, weights, n_valid, *, taps, stride=1, bias=None, film=None, mod=No
     oh, ow = out_hw if out_hw else ((H << a_up) // stride, (W << a_up) // stride)
     nseg = len(srcs)
     n_pad = (n_valid + 15) // 16 * 16
-    out = torch.zeros(B, oh, ow, n_valid if n_valid % 8 == 0 else n_pad, dtype=torch.bfloat16, device=DEV) if not want_nchw else None
-    out_nchw = torch.zeros(B, n_valid, oh, ow, dtype=torch.float32, device=DEV) if want_nchw else None
-    stats = torch.zeros(B, 2, dtype=torch.float64, device=DEV) if want_stats else None
+    if reuse is not None:  # (out | out_nchw, stats) of an earlier call: no allocation, for timing loops
+        out, out_nchw, stats = (None, reuse[0], reuse[1]) if want_nchw else (reuse[0], None, reuse[1])
+    else:
+        out = torch.zeros(B, oh, ow, n_valid if n_valid % 8 == 0 else n_pad, dtype=torch.bfloat16, device=DEV) if not want_nchw else None
+        out_nchw = torch.zeros(B, n_valid, oh, ow, dtype=torch.float32, device=DEV) if want_nchw else None
+        stats = torch.zeros(B, 2, dtype=torch.float64, device=DEV) if want_stats else None
     ps = list(per_sample) if per_sample else [0] * nseg
     pad2 = lambda lst, fill: list(lst) + [fill] * (2 - nseg)
     _lib.launch(
@@ -61,5 +64,6 @@ def gemm(srcs, weights, n_valid, *, taps, stride=1, bias=None, film=None, mod=No
         out_nchw=out_nchw.data_ptr() if out_nchw is not None else None, stats=stats.data_ptr() if stats is not None else None,
         gn_stats=gn[0].data_ptr() if gn else None, gn_gamma=gn[1].data_ptr() if gn else None, gn_beta=gn[2].data_ptr() if gn else None,
         gn_eps=1e-5, gn_act=gn[3] if gn else 0, a_up=a_up, force_tma=force_tma)
-    torch.cuda.synchronize()
+    if sync:
+        torch.cuda.synchronize()
     return (out_nchw if want_nchw else out), stats

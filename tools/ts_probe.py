@@ -25,9 +25,9 @@ t=ts.cpu().view(4,64,4)
 t0=int(t[t>0].min())
 r=lambda v: (int(v)-t0) if v>0 else -1
 print(f"B={B} {H}x{W} {Cin}->{Cout} gn={gnflag} res={resflag}")
-print("tile | producer: pre-wait issue | xform: pre-wait landed stored arrived | mma: pre-empty got-empty got-a_full committed | epi: pre-wait got-full done")
+print("tile | producer: pre-wait issue | xform: pre-wait landed stored arrived | mma: pre-empty got-empty got-a_full committed | epi: got-full tmem-loaded processed done")
 for i in range(14):
-    print(i, '|', [r(v) for v in t[0,i][:2]], '|', [r(v) for v in t[3,i]], '|', [r(v) for v in t[1,i]], '|', [r(v) for v in t[2,i][:3]])
+    print(i, '|', [r(v) for v in t[0,i][:2]], '|', [r(v) for v in t[3,i]], '|', [r(v) for v in t[1,i]], '|', [r(v) for v in t[2,i]])
 n=min(40, int((t[1,:,3]>0).sum()))
 d=[int(t[1,i+1,3]-t[1,i,3]) for i in range(4,n-1)]
 print('cycles per tile (mma commit to commit), tiles 4..', n, ':', sum(d)/max(len(d),1))

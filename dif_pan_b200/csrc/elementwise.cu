@@ -204,11 +204,130 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(GnK p) {
     }
   }
 }
+// ---- GroupNorm(1 group) + depthwise 3x3, shared-memory tiled   (FWM prenorm_x + q[0], sr3_dwt.py:507-512,541) -----
+// One CTA = one (16 x 8)-pixel tile x one 32-channel group: the (18 x 10) halo is read ONCE (16-byte loads), normalised
+// in fp32 into shared memory (zero outside the image: the depthwise conv pads the NORMALISED tensor), the centre pixels
+// are written out as x_hat, then every thread produces two (pixel, 8-channel) outputs of the depthwise conv from
+// shared memory.  HBM traffic = 2 B read + 4 B written per element instead of nine re-normalised neighbour reads
+// (profiles/r01_step_B256_v1: 840 GB/s for the per-pixel version).  Row pitch 144 B keeps every LDS.128 / STS.128
+// phase on distinct banks.
+static constexpr int kDwTW = 16, kDwTH = 8, kDwHW = kDwTW + 2, kDwHH = kDwTH + 2, kDwHalo = kDwHW * kDwHH;
+static constexpr int kDwCh = 32, kDwPitch = 144, kDwThreads = 256;
+
+__global__ void __launch_bounds__(kDwThreads) gn_dw_tile_kernel(GnK p) {
+  __shared__ __align__(16) uint8_t s_tile[kDwHalo * kDwPitch];
+  __shared__ __align__(16) float s_w[9][kDwCh];
+  __shared__ __align__(16) float s_a[kDwCh], s_d[kDwCh];
+  const int C = p.c1 + p.c2;
+  const int ngrp = C / kDwCh;
+  const int cg = blockIdx.x % ngrp;
+  const int tile = blockIdx.x / ngrp;
+  const int tiles_x = (p.W + kDwTW - 1) / kDwTW;
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int b = blockIdx.y;
+  const int ch0 = cg * kDwCh;
+  const int HW = p.H * p.W;
+  const int t = threadIdx.x;
+  if (t < kDwCh) {
+    double s = p.st1[2 * b], ss = p.st1[2 * b + 1];
+    double n = (double)p.c1 * HW;
+    if (p.c2) {
+      s += p.st2[2 * b];
+      ss += p.st2[2 * b + 1];
+      n += (double)p.c2 * HW;
+    }
+    const double mean_d = s / n;
+    double var_d = ss / n - mean_d * mean_d;
+    if (var_d < 0) var_d = 0;
+    const float mean = (float)mean_d;
+    const float rstd = rsqrtf((float)var_d + p.eps);
+    const float a = rstd * __ldg(p.gamma + ch0 + t);
+    s_a[t] = a;
+    s_d[t] = __ldg(p.beta + ch0 + t) - mean * a;
+  }
+  for (int i = t; i < 9 * kDwCh; i += kDwThreads) s_w[i / kDwCh][i % kDwCh] = __ldg(p.dw_w + (size_t)(i / kDwCh) * C + ch0 + (i % kDwCh));
+  __syncthreads();
+  // phase 1: halo -> normalise -> smem (fp32) and x_hat (bf16, centre pixels)
+  const int y0 = ty * kDwTH - 1, x0 = tx * kDwTW - 1;
+  const int c = t & 3;            // 8-channel chunk inside the 32-channel group
+  const int chc = ch0 + c * 8;    // its first channel in the concatenated tensor
+  const bool first = chc < p.c1;
+  const int ld = first ? p.c1 : p.c2;
+  const bf16* src = (first ? p.src1 + chc : p.src2 + (chc - p.c1)) + (size_t)b * HW * ld;
+  float a[8], d[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a[j] = s_a[c * 8 + j];
+    d[j] = s_d[c * 8 + j];
+  }
+  bf16x8 in[3];
+  bool ok[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int px = (t >> 2) + k * (kDwThreads / 4);
+    const int hy = px / kDwHW, hx = px - hy * kDwHW;
+    const int gy = y0 + hy, gx = x0 + hx;
+    ok[k] = px < kDwHalo && (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W;
+    if (ok[k]) in[k] = *reinterpret_cast<const bf16x8*>(src + (size_t)(gy * p.W + gx) * ld);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int px = (t >> 2) + k * (kDwThreads / 4);
+    if (px < kDwHalo) {
+      float y[8];
+      if (ok[k]) {
+        float v[8];
+        unpack8(in[k], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = fmaf(v[j], a[j], d[j]);
+        const int hy = px / kDwHW, hx = px - hy * kDwHW;
+        if (hy >= 1 && hy <= kDwTH && hx >= 1 && hx <= kDwTW)
+          *reinterpret_cast<bf16x8*>(p.out + ((size_t)b * HW + (size_t)(y0 + hy) * p.W + (x0 + hx)) * C + chc) = pack8(y);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = 0.f;
+      }
+      float4* dst = reinterpret_cast<float4*>(s_tile + px * kDwPitch + c * 32);
+      dst[0] = make_float4(y[0], y[1], y[2], y[3]);
+      dst[1] = make_float4(y[4], y[5], y[6], y[7]);
+    }
+  }
+  __syncthreads();
+  // phase 2: depthwise 3x3 from smem; thread -> pixels (t>>2) and (t>>2)+64 of the 128-pixel tile, chunk c
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int pt = (t >> 2) + k * 64;
+    const int py = pt / kDwTW, pxx = pt - py * kDwTW;
+    const int gy = ty * kDwTH + py, gx = tx * kDwTW + pxx;
+    if (gy >= p.H || gx >= p.W) continue;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float4* z = reinterpret_cast<const float4*>(s_tile + ((py + tap / 3) * kDwHW + pxx + tap % 3) * kDwPitch + c * 32);
+      const float4* w = reinterpret_cast<const float4*>(&s_w[tap][c * 8]);
+      const float4 z0 = z[0], z1 = z[1], w0 = w[0], w1 = w[1];
+      acc[0] += w0.x * z0.x; acc[1] += w0.y * z0.y; acc[2] += w0.z * z0.z; acc[3] += w0.w * z0.w;
+      acc[4] += w1.x * z1.x; acc[5] += w1.y * z1.y; acc[6] += w1.z * z1.z; acc[7] += w1.w * z1.w;
+    }
+    *reinterpret_cast<bf16x8*>(p.out_dw + ((size_t)b * HW + (size_t)gy * p.W + gx) * C + chc) = pack8(acc);
+  }
+}
+
 int launch_gn_apply(const ddif_gn_apply_t& p, cudaStream_t s) {
   if (p.c1 % 8 != 0 || p.c2 % 8 != 0 || p.c1 <= 0) return DDIF_ERR_SHAPE;
   if (p.c2 && (!p.src2 || !p.stats2)) return DDIF_ERR_ARG;
   if (p.dw_w && !p.out_dw) return DDIF_ERR_ARG;
   const int nchunk = (int)((p.c1 + p.c2) / 8);
+  if (p.dw_w && (p.c1 + p.c2) % kDwCh == 0 && !p.act && p.batch <= 65535) {
+    GnK k{(const bf16*)p.src1, (const bf16*)p.src2, (int)p.c1, (int)p.c2, p.stats1, p.stats2, p.gamma, p.beta,
+          (bf16*)p.out, p.dw_w, (bf16*)p.out_dw, (int)p.h, (int)p.w, (int)p.act, (float)p.eps};
+    const int64_t tiles = ceil_div(p.w, kDwTW) * ceil_div(p.h, kDwTH);
+    gn_dw_tile_kernel<<<dim3((unsigned)(tiles * ((p.c1 + p.c2) / kDwCh)), (unsigned)p.batch), kDwThreads, 0, s>>>(k);
+    DDIF_LAUNCH_CHECK();
+    return DDIF_OK;
+  }
   if (kGnThreads % nchunk != 0) return DDIF_ERR_SHAPE;  // channel counts are multiples of 8 dividing 1536
   GnK k{(const bf16*)p.src1, (const bf16*)p.src2, (int)p.c1, (int)p.c2, p.stats1, p.stats2, p.gamma, p.beta,
         (bf16*)p.out, p.dw_w, (bf16*)p.out_dw, (int)p.h, (int)p.w, (int)p.act, (float)p.eps};

@@ -72,6 +72,29 @@ def test_gn_apply(act, two):
     assert rel_err(to_nchw_f32(out_dw), ref_dw) < 5e-3
 
 
+@pytest.mark.parametrize("H,W,c1,c2", [(24, 40, 64, 32), (8, 8, 128, 128), (64, 64, 32, 32), (10, 18, 64, 0)])
+def test_gn_dw_tiled(H, W, c1, c2):
+    """smem-tiled GroupNorm + depthwise 3x3 (csrc/elementwise.cu gn_dw_tile_kernel): partial tiles, two sources."""
+    B = 2
+    a = nhwc_bf16(_rand(B, c1, H, W, seed=14, scale=2.0) + 0.7)
+    b = nhwc_bf16(_rand(B, c2, H, W, seed=15) - 0.3) if c2 else None
+    C = c1 + c2
+    gamma, beta = 1 + 0.1 * _rand(C, seed=16), 0.1 * _rand(C, seed=17)
+    dw = _rand(C, 1, 3, 3, seed=18, scale=0.3)
+    dw9 = dw.reshape(C, 9).t().contiguous()
+    out = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=DEV)
+    out_dw = torch.zeros_like(out)
+    sa, sb = _stats_of(a), (_stats_of(b) if c2 else None)
+    _lib.launch("ddif_gn_apply_t", stream(), src1=a.data_ptr(), c1=c1, src2=b.data_ptr() if c2 else None, c2=c2, stats1=sa.data_ptr(),
+                stats2=sb.data_ptr() if c2 else None, gamma=gamma.data_ptr(), beta=beta.data_ptr(), out=out.data_ptr(),
+                dw_w=dw9.data_ptr(), out_dw=out_dw.data_ptr(), batch=B, h=H, w=W, act=0, eps=1e-5)
+    torch.cuda.synchronize()
+    xcat = torch.cat([to_nchw_f32(a)] + ([to_nchw_f32(b)] if c2 else []), 1)
+    ref = F.group_norm(xcat, 1, gamma, beta, eps=1e-5)
+    assert rel_err(to_nchw_f32(out), ref) < 4e-3
+    assert rel_err(to_nchw_f32(out_dw), F.conv2d(ref, dw, None, padding=1, groups=C)) < 5e-3
+
+
 def test_softmax_h_and_attention():
     B, H, W, C = 2, 16, 8, 64
     q = nhwc_bf16(_rand(B, C, H, W, seed=9, scale=2.0))

@@ -34,11 +34,12 @@ static constexpr int kHMaxStages = 8;
 static constexpr int kHMaxStat = 1024;
 
 struct alignas(64) HaloKParams {
-  CUtensorMap tmA;
-  CUtensorMap tmB;
-  CUtensorMap tmR;   // residual tile box (L2 prefetch only)
+  CUtensorMap tmA[2];  // activations of K segment 0 / 1 (virtual channel concat: torch.cat((x, skip), 1), sr3_dwt.py:212)
+  CUtensorMap tmB[2];  // weights of segment 0 / 1
+  CUtensorMap tmR;     // residual tile box (L2 prefetch only)
   int has_res_map;
   int cin, kslab, nslab, span;
+  int nslab0;          // slabs that come from segment 0
   int batch, out_h, out_w;
   int tiles_x, tiles_y, num_tiles;
   int bn;
@@ -46,6 +47,7 @@ struct alignas(64) HaloKParams {
   uint32_t stage_bytes, b_slot_bytes;
   uint32_t idesc, layout_type, tmem_cols;
   const double* gn_stats;
+  const double* gn_stats2;  // statistics of segment 1 (the GroupNorm runs over the concatenated tensor)
   const float* gn_gamma;
   const float* gn_beta;
   float gn_eps;
@@ -72,22 +74,38 @@ __device__ __forceinline__ void h_sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// Tile walk of one persistent CTA (blockIdx.x, +gridDim.x, ...) without divisions in the loop.
+// (mean, rstd) of sample b over the (concatenated) input, from the fp64 (sum, sumsq) pairs of its one or two sources.
+__device__ __forceinline__ float2 halo_mean_rstd(const HaloKParams& p, int b) {
+  double s = p.gn_stats[2 * b], ss = p.gn_stats[2 * b + 1];
+  if (p.gn_stats2) {
+    s += p.gn_stats2[2 * b];
+    ss += p.gn_stats2[2 * b + 1];
+  }
+  const double m = s / p.gn_count;
+  double var = ss / p.gn_count - m * m;
+  if (var < 0) var = 0;
+  return make_float2((float)m, rsqrtf((float)var + p.gn_eps));
+}
+
+// Divide-free walk over tiles m = start, start + stride, ... (< num_tiles) with their K slabs.
+// PIPELINE OWNERSHIP RULE: the CTA runs two half-pipelines r = 0, 1 (tiles of its walk with even / odd position): stage
+// ring r, transform group r, MMA warp r, TMEM accumulator r and epilogue group r.  Every mbarrier is therefore waited on
+// by the same thread(s) for each of its phases, in order -- a parity wait issued two phases ahead of the barrier would
+// return immediately on the stale phase (the bug a shared ring with alternating consumers has).
 struct HaloIter {
   int b, ty, tx, slab, remaining;
   int sb, sy, sx, tiles_x, tiles_y, nslab;
-  __device__ __forceinline__ void init(const HaloKParams& p) {
+  __device__ __forceinline__ void init(const HaloKParams& p, int start, int stride) {
     const int tpi = p.tiles_x * p.tiles_y;
     tiles_x = p.tiles_x; tiles_y = p.tiles_y; nslab = p.nslab;
-    const int m0 = (int)blockIdx.x, g = (int)gridDim.x;
-    b = m0 / tpi;
-    int r = m0 - b * tpi;
+    b = start / tpi;
+    int r = start - b * tpi;
     ty = r / tiles_x; tx = r - ty * tiles_x;
-    sb = g / tpi;
-    r = g - sb * tpi;
+    sb = stride / tpi;
+    r = stride - sb * tpi;
     sy = r / tiles_x; sx = r - sy * tiles_x;
     slab = 0;
-    remaining = ((p.num_tiles - m0 + g - 1) / g) * nslab;
+    remaining = start < p.num_tiles ? ((p.num_tiles - start + stride - 1) / stride) * nslab : 0;
   }
   __device__ __forceinline__ void next() {
     --remaining;
@@ -100,8 +118,8 @@ struct HaloIter {
 };
 
 // ---- transform warps: GroupNorm affine (+Swish) of a landed stage, in place -------------------------------------------
-// Group g (warps 4g..4g+3) takes the units (tile x slab) u = g, g+2, ...: each group has two unit periods per stage, so
-// the wait -> LDS -> math -> STS -> fence -> arrive latency chain of one stage overlaps the other group's.
+// Group g (warps 4g..4g+3) serves half-pipeline g: its wait -> LDS -> math -> STS -> fence -> arrive latency chain on one
+// stage overlaps the other group's.
 template <int NCK>
 __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32_t a_base, uint64_t* a_tma, uint64_t* a_ready,
                                                     const float* s_gamma, const float* s_beta, const float2* s_stat, int tid, long long* dts) {
@@ -113,7 +131,7 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
   const int c = lt % NCK;
   const int r0 = lt / NCK;
   const float hs = p.gn_act ? 0.5f : 1.0f;  // swish(t) = h*tanh(h) + h with h = t/2: the affine is pre-halved
-  const uint32_t nst = (uint32_t)p.stages;
+  const uint32_t nst = (uint32_t)p.stages >> 1;  // stages of this group's ring
   // per-thread tables (tile independent): swizzled smem offset and halo (line, column) of each of the thread's chunks
   uint32_t soff[NPASS];
   int hyx[NPASS];  // hy << 8 | hx; rows past the halo get hy = 255 (never in bounds)
@@ -128,16 +146,13 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
   const bool act = p.gn_act != 0;
   const unsigned H = (unsigned)p.out_h, W = (unsigned)p.out_w;
   HaloIter it;
-  it.init(p);
+  it.init(p, (int)blockIdx.x + grp * (int)gridDim.x, 2 * (int)gridDim.x);
+  a_tma += grp * nst; a_ready += grp * nst;
+  a_base += (uint32_t)grp * nst * p.stage_bytes;
   uint32_t stage = 0, phase = 0;
-  auto advance = [&]() {
-    it.next();
-    if (++stage == nst) { stage = 0; phase ^= 1u; }
-  };
-  if (grp == 1 && it.remaining > 0) advance();
-  int cur_b = -1, cur_slab = -1, tcount = grp;
+  int cur_b = -1, cur_slab = -1, tcount = 0;
   f32x2 a2[4], d2[4];
-  while (it.remaining > 0) {
+  for (; it.remaining > 0; it.next()) {
     if (it.b != cur_b || it.slab != cur_slab) {
       cur_b = it.b; cur_slab = it.slab;
       float mean, rstd;
@@ -145,12 +160,8 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
         const float2 mr = s_stat[it.b];
         mean = mr.x; rstd = mr.y;
       } else {
-        const double sm = p.gn_stats[2 * it.b], ss = p.gn_stats[2 * it.b + 1];
-        const double m = sm / p.gn_count;
-        double var = ss / p.gn_count - m * m;
-        if (var < 0) var = 0;
-        mean = (float)m;
-        rstd = rsqrtf((float)var + p.gn_eps);
+        const float2 mr = halo_mean_rstd(p, it.b);
+        mean = mr.x; rstd = mr.y;
       }
       const int ch0 = it.slab * p.kslab + c * 8;
       const float sc = hs * rstd;
@@ -194,9 +205,8 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
     h_fence_proxy_async();
     mbar_arrive(&a_ready[stage]);
     if (tid == 0) h_ts(dts, 3, tcount, 3);
-    tcount += 2;
-    advance();
-    if (it.remaining > 0) advance();
+    ++tcount;
+    if (++stage == nst) { stage = 0; phase ^= 1u; }
   }
 }
 
@@ -210,19 +220,16 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
                                               uint64_t* b_full, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int my_tiles,
                                               int w, long long* dts) {
   const uint32_t span = (uint32_t)p.span;
-  const uint64_t desc_a0 = make_smem_desc(a_base, (uint32_t)kHW * span, p.layout_type);  // SBO = one halo line (10 rows)
   const uint64_t desc_b0 = make_smem_desc(b_base, 8u * span, p.layout_type);
   const uint32_t stage16 = p.stage_bytes >> 4, b16 = p.b_slot_bytes >> 4;
   uint32_t tap_off[9];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((uint32_t)((tap / 3) * kHW + (tap % 3)) * span) >> 4;
-  const uint32_t nst = (uint32_t)p.stages;
+  const uint32_t nst = (uint32_t)p.stages >> 1;  // stages of this warp's ring
+  a_full += (uint32_t)w * nst; a_empty += (uint32_t)w * nst;
+  a_base += (uint32_t)w * nst * p.stage_bytes;
+  const uint64_t desc_a0 = make_smem_desc(a_base, (uint32_t)kHW * span, p.layout_type);  // SBO = one halo line (10 rows)
   uint32_t stage = 0, phase = 0;
-  auto advance = [&]() {
-    if (++stage == nst) { stage = 0; phase ^= 1u; }
-  };
-  if (w == 1)
-    for (int slab = 0; slab < p.nslab; ++slab) advance();
   mbar_wait(b_full, 0u);
   tc_fence_after();
   const uint32_t tmem_d = tmem_base + (uint32_t)w * (uint32_t)p.bn;
@@ -244,11 +251,10 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
         db += b16;
       }
       umma_commit_elect(&a_empty[stage]);
-      advance();
+      if (++stage == nst) { stage = 0; phase ^= 1u; }
     }
     umma_commit_elect(&tmem_full[w]);
     if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 3);
-    for (int slab = 0; slab < p.nslab; ++slab) advance();  // the other warp's tile
   }
 }
 
@@ -268,13 +274,15 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
   const int row = q * 32 + lane;
   const int ry = row >> 3, rx = row & 7;
   const int nch = p.bn >> 4;
-  const int n_valid = p.epi.n_valid;
-  const float* bias = p.epi.bias;
-  const float* film = p.epi.film;
+  const int n0 = (int)blockIdx.y * p.bn;           // first output channel of this CTA's N tile
+  const int n_valid = p.epi.n_valid - n0;          // valid channels of the tile (may exceed bn: clipped by nch)
+  const int n_total = p.epi.n_valid;
+  const float* bias = p.epi.bias ? p.epi.bias + n0 : nullptr;
+  const float* film = p.epi.film ? p.epi.film + n0 : nullptr;
   const int film_ld = p.epi.film_ld;
-  const bf16* resid = p.epi.residual;
+  const bf16* resid = p.epi.residual ? p.epi.residual + n0 : nullptr;
   const int res_ld = p.epi.res_ld, out_ld = p.epi.out_ld;
-  bf16* outp = p.epi.out;
+  bf16* outp = p.epi.out ? p.epi.out + n0 : nullptr;
   float* out_nchw = p.epi.out_nchw;
   double* stats = p.epi.stats;
   const int out_h = p.out_h, out_w = p.out_w, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
@@ -372,7 +380,7 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
           }
         }
         if (kNchw) {
-          float* o = out_nchw + ((size_t)b * n_valid + ng) * hw + (size_t)y * out_w + x;
+          float* o = out_nchw + ((size_t)b * n_total + n0 + ng) * hw + (size_t)y * out_w + x;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float lo, hi;
@@ -396,7 +404,7 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
             if (kRes) t2 += __bfloat162float(res_px[ng + j]);
             if (kAct) t2 = swish_half(0.5f * t2);
             if (kStats) { ss1 += t2; ss2 = fmaf(t2, t2, ss2); }
-            if (kNchw) out_nchw[((size_t)b * n_valid + ng + j) * hw + (size_t)y * out_w + x] = t2;
+            if (kNchw) out_nchw[((size_t)b * n_total + n0 + ng + j) * hw + (size_t)y * out_w + x] = t2;
             else outp[pix * (size_t)out_ld + ng + j] = __float2bfloat16(t2);
           }
         }
@@ -466,24 +474,22 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   const int lane = threadIdx.x & 31;
   const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool gn = p.gn_stats != nullptr;
-  long long* const dts = blockIdx.x == 0 ? g_halo_ts : nullptr;
+  long long* const dts = (blockIdx.x == 0 && blockIdx.y == 0) ? g_halo_ts : nullptr;
 
   if (gn) {
     for (int i = threadIdx.x; i < p.cin; i += blockDim.x) {
       s_gamma[i] = p.gn_gamma[i];
       s_beta[i] = p.gn_beta[i];
     }
-    for (int i = threadIdx.x; i < n_stat; i += blockDim.x) {  // per-sample (mean, rstd), fp64 once per CTA
-      const double s = p.gn_stats[2 * i], ss = p.gn_stats[2 * i + 1];
-      const double m = s / p.gn_count;
-      double var = ss / p.gn_count - m * m;
-      if (var < 0) var = 0;
-      s_stat[i] = make_float2((float)m, rsqrtf((float)var + p.gn_eps));
-    }
+    for (int i = threadIdx.x; i < n_stat; i += blockDim.x) s_stat[i] = halo_mean_rstd(p, i);  // fp64 once per CTA
   }
   if (warp == 18 && lane == 0) {
-    tma_prefetch_desc(&p.tmA);
-    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB[0]);
+    if (p.nslab0 < p.nslab) {
+      tma_prefetch_desc(&p.tmA[1]);
+      tma_prefetch_desc(&p.tmB[1]);
+    }
   }
   if (warp == 8) {
     if (lane == 0) {
@@ -529,21 +535,27 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
       mbar_expect_tx(b_full, (uint32_t)(9 * p.nslab) * p.b_slot_bytes);
       for (int slab = 0; slab < p.nslab; ++slab)
         for (int tap = 0; tap < 9; ++tap)
-          tma_load_3d(&p.tmB, b_full, smem_b + (size_t)(slab * 9 + tap) * p.b_slot_bytes, slab * p.kslab, 0, tap);
+          tma_load_3d(&p.tmB[slab >= p.nslab0], b_full, smem_b + (size_t)(slab * 9 + tap) * p.b_slot_bytes,
+                      (slab >= p.nslab0 ? slab - p.nslab0 : slab) * p.kslab, (int)blockIdx.y * p.bn, tap);
       const uint32_t tx = (uint32_t)(kHPx * p.span);
-      const uint32_t nst = (uint32_t)p.stages;
+      const uint32_t nst = (uint32_t)p.stages >> 1;  // per ring
       HaloIter it;
-      it.init(p);
-      uint32_t stage = 0, phase = 0;
+      it.init(p, (int)blockIdx.x, (int)gridDim.x);
+      uint32_t rs[2] = {0u, 0u}, rp[2] = {0u, 0u};  // (stage, phase) of ring 0 / 1
+      uint32_t ring = 0;
       int u = 0;
       for (; it.remaining > 0; it.next(), ++u) {
+        const uint32_t stage = ring * nst + rs[ring];
         h_ts(dts, 0, u, 0);
-        mbar_wait(&a_empty[stage], phase ^ 1u);
+        mbar_wait(&a_empty[stage], rp[ring] ^ 1u);
         h_ts(dts, 0, u, 1);
         mbar_expect_tx(&a_tma[stage], tx);
-        tma_load_4d(&p.tmA, &a_tma[stage], smem_a + (size_t)stage * p.stage_bytes, it.slab * p.kslab, it.tx * 8 - 1, it.ty * 16 - 1, it.b);
-        if (p.has_res_map && it.slab == 0) tma_prefetch_l2_4d(&p.tmR, 0, it.tx * 8, it.ty * 16, it.b);  // residual tile -> L2, `stages` tiles ahead
-        if (++stage == nst) { stage = 0; phase ^= 1u; }
+        const int seg = it.slab >= p.nslab0;
+        tma_load_4d(&p.tmA[seg], &a_tma[stage], smem_a + (size_t)stage * p.stage_bytes, (seg ? it.slab - p.nslab0 : it.slab) * p.kslab, it.tx * 8 - 1,
+                    it.ty * 16 - 1, it.b);
+        if (p.has_res_map && it.slab == 0) tma_prefetch_l2_4d(&p.tmR, (int)blockIdx.y * p.bn, it.tx * 8, it.ty * 16, it.b);  // residual tile -> L2, `stages` tiles ahead
+        if (++rs[ring] == nst) { rs[ring] = 0; rp[ring] ^= 1u; }
+        if (it.slab == p.nslab - 1) ring ^= 1u;  // next tile -> other half-pipeline
       }
     }
   } else if (warp >= 10 && warp < 18) {
@@ -600,36 +612,56 @@ static cudaError_t halo_set_attrs() {
 }
 
 struct HaloGeom {
-  int kslab, nslab, span, stages, stage_bytes, b_slot, n_stat, misc, smem;
+  int cin, kslab, nslab, nslab0, span, stages, stage_bytes, b_slot, n_stat, misc, smem, split, bn;
 };
 
 static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
-  if (g.nseg != 1 || g.taps[0] != 9 || g.stride != 1 || g.w_per_sample[0] || g.a_up != 0) return false;
+  if (g.nseg < 1 || g.nseg > 2 || g.stride != 1 || g.a_up != 0) return false;
   if (g.out_w < 8 || g.out_h < 8) return false;
-  if (g.a_c[0] % 16 != 0 || g.a_c[0] > 512) return false;
   if (g.n_pad % 16 != 0 || g.n_pad > 256 || g.n_pad < 16) return false;
-  if (g.a_ld[0] % 8 != 0 || g.w_k[0] % 8 != 0 || g.w_k[0] < g.a_c[0]) return false;
+  int cin = 0, gcd = 64;
+  for (int s = 0; s < g.nseg; ++s) {
+    if (g.taps[s] != 9 || g.w_per_sample[s]) return false;
+    if (g.a_c[s] % 16 != 0 || g.a_c[s] <= 0) return false;
+    if (g.a_ld[s] % 8 != 0 || g.w_k[s] % 8 != 0 || g.w_k[s] < g.a_c[s]) return false;
+    if (g.a_h[s] != g.out_h || g.a_w[s] != g.out_w) return false;
+    while (g.a_c[s] % gcd != 0) gcd >>= 1;
+    cin += (int)g.a_c[s];
+  }
+  if (cin > 512) return false;
+  if (g.nseg == 2 && g.gn_stats && !g.gn_stats2) return false;
   if (g.mod || halo_kernel(halo_flags(g)) == nullptr) return false;  // CSM modulation / fp32 store + residual: generic kernel
   if (g.out && g.out_nchw) return false;
   if (g.out && g.out_ld % 16 != 0) return false;                       // 32-byte stores
   if (g.residual && g.res_ld % 16 != 0) return false;
   if (g.film && g.film_ld % 4 != 0) return false;
   if (!g.out && !g.out_nchw) return false;
-  const int cin = (int)g.a_c[0];
-  h.kslab = cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16);
-  h.nslab = cin / h.kslab;
-  h.span = h.kslab * 2;
-  h.stage_bytes = (kHPx * h.span + 1023) & ~1023;
-  h.b_slot = (int)g.n_pad * h.span;
+  h.cin = cin;
   h.n_stat = g.gn_stats ? (int)(g.batch < kHMaxStat ? g.batch : kHMaxStat) : 0;
   h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + (3 * kHMaxStages + 8) * 8 + 64 + 1024;
-  const int budget = 227 * 1024 - h.misc - 9 * h.nslab * h.b_slot;
-  int st = budget / h.stage_bytes;
-  if (st > kHMaxStages) st = kHMaxStages;
-  if (st < 2) return false;
-  h.stages = st;
-  h.smem = st * h.stage_bytes + 9 * h.nslab * h.b_slot + h.misc;
-  return true;
+  // Resident weights of one CTA (9 taps x all K slabs x bn rows) must leave room for two rings of >= 2 halo stages:
+  // split N over blockIdx.y (1, 2, 4 CTAs per tile) and, before splitting further, halve the K slab (smaller stages).
+  for (int pass = 0; pass < 2; ++pass) {  // pass 0: >= 4 stages; pass 1: accept 2
+    for (int split = 1; split <= 4; split *= 2) {
+      if (g.n_pad % (16 * split) != 0) break;
+      if (split > 1 && g.out_nchw) break;
+      const int bn = (int)g.n_pad / split;
+      for (int kslab = gcd; kslab >= 16; kslab >>= 1) {
+        const int span = kslab * 2;
+        const int stage_bytes = (kHPx * span + 1023) & ~1023;
+        const int b_total = 9 * cin * bn * 2;  // independent of the slab size
+        int st = ((227 * 1024 - h.misc - b_total) / stage_bytes) & ~1;
+        if (st > kHMaxStages) st = kHMaxStages;
+        if (st >= (pass == 0 ? 4 : 2)) {
+          h.kslab = kslab; h.nslab = cin / kslab; h.nslab0 = (int)g.a_c[0] / kslab; h.span = span;
+          h.stage_bytes = stage_bytes; h.split = split; h.bn = bn; h.b_slot = bn * span; h.stages = st;
+          h.smem = st * stage_bytes + b_total + h.misc;
+          return true;
+        }
+      }
+    }
+  }
+  return false;
 }
 
 bool conv3_halo_applicable(const ddif_gemm_t& g) {
@@ -647,14 +679,12 @@ int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   HaloGeom h;
   if (!halo_geometry(g, h)) return DDIF_ERR_SHAPE;
   if (g.n_valid > g.n_pad || g.n_valid < 1) return DDIF_ERR_SHAPE;
-  const int cin = (int)g.a_c[0];
-  p.cin = cin; p.kslab = h.kslab; p.nslab = h.nslab; p.span = h.span;
+  p.cin = h.cin; p.kslab = h.kslab; p.nslab = h.nslab; p.nslab0 = h.nslab0; p.span = h.span;
   p.batch = (int)g.batch; p.out_h = (int)g.out_h; p.out_w = (int)g.out_w;
-  if ((int)g.a_h[0] != p.out_h || (int)g.a_w[0] != p.out_w) return DDIF_ERR_SHAPE;
   p.tiles_x = (int)ceil_div(p.out_w, 8);
   p.tiles_y = (int)ceil_div(p.out_h, 16);
   p.num_tiles = p.tiles_x * p.tiles_y * p.batch;
-  p.bn = (int)g.n_pad;
+  p.bn = h.bn;
   p.stages = h.stages;
   p.stage_bytes = (uint32_t)h.stage_bytes;
   p.b_slot_bytes = (uint32_t)h.b_slot;
@@ -664,54 +694,56 @@ int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   p.tmem_cols = cols;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   L.smem_bytes = h.smem;
-  L.grid_y = 1;
+  L.grid_y = h.split;
   const int sms = ddif_sm_count();
-  L.grid_x = p.num_tiles < sms ? p.num_tiles : sms;
+  const int gx = sms / h.split > 0 ? sms / h.split : 1;
+  L.grid_x = p.num_tiles < gx ? p.num_tiles : gx;
   L.variant = 2;
   L.flags = halo_flags(g);
   const CUtensorMapSwizzle sw = p.span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : p.span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)g.a_w[0], (cuuint64_t)g.a_h[0], (cuuint64_t)g.batch};
-    cuuint64_t strides[3] = {(cuuint64_t)g.a_ld[0] * 2, (cuuint64_t)g.a_w[0] * g.a_ld[0] * 2, (cuuint64_t)g.a_h[0] * g.a_w[0] * g.a_ld[0] * 2};
-    cuuint32_t box[4] = {(cuuint32_t)p.kslab, (cuuint32_t)kHW, (cuuint32_t)kHH, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g.a[0]), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
-  }
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)g.w_k[0], (cuuint64_t)g.n_pad, (cuuint64_t)g.w_s[0]};
-    cuuint64_t strides[2] = {(cuuint64_t)g.w_k[0] * 2, (cuuint64_t)g.n_pad * g.w_k[0] * 2};
-    cuuint32_t box[3] = {(cuuint32_t)p.kslab, (cuuint32_t)p.bn, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(g.w[0]), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
+  for (int s = 0; s < g.nseg; ++s) {
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)g.a_c[s], (cuuint64_t)g.a_w[s], (cuuint64_t)g.a_h[s], (cuuint64_t)g.batch};
+      cuuint64_t strides[3] = {(cuuint64_t)g.a_ld[s] * 2, (cuuint64_t)g.a_w[s] * g.a_ld[s] * 2, (cuuint64_t)g.a_h[s] * g.a_w[s] * g.a_ld[s] * 2};
+      cuuint32_t box[4] = {(cuuint32_t)p.kslab, (cuuint32_t)kHW, (cuuint32_t)kHH, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = enc(&p.tmA[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g.a[s]), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
+    }
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)g.w_k[s], (cuuint64_t)g.n_pad, (cuuint64_t)g.w_s[s]};
+      cuuint64_t strides[2] = {(cuuint64_t)g.w_k[s] * 2, (cuuint64_t)g.n_pad * g.w_k[s] * 2};
+      cuuint32_t box[3] = {(cuuint32_t)p.kslab, (cuuint32_t)p.bn, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      CUresult r = enc(&p.tmB[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(g.w[s]), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
+    }
   }
   if (g.residual) {
+    const int nb = (int)(g.n_valid < p.bn ? g.n_valid : p.bn) / 8 * 8;
     cuuint64_t dims[4] = {(cuuint64_t)g.n_valid, (cuuint64_t)g.out_w, (cuuint64_t)g.out_h, (cuuint64_t)g.batch};
     cuuint64_t strides[3] = {(cuuint64_t)g.res_ld * 2, (cuuint64_t)g.out_w * g.res_ld * 2, (cuuint64_t)g.out_h * g.out_w * g.res_ld * 2};
-    cuuint32_t box[4] = {(cuuint32_t)(g.n_valid / 8 * 8), 8, 16, 1};
+    cuuint32_t box[4] = {(cuuint32_t)nb, 8, 16, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    if (box[0] >= 8 && box[0] <= 256 &&
+    if (nb >= 8 && nb <= 256 &&
         enc(&p.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g.residual), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
       p.has_res_map = 1;
   }
   p.gn_stats = g.gn_stats;
+  p.gn_stats2 = g.nseg == 2 ? g.gn_stats2 : nullptr;
   p.gn_gamma = g.gn_gamma;
   p.gn_beta = g.gn_beta;
   p.gn_eps = (float)g.gn_eps;
   p.gn_act = (int)g.gn_act;
-  p.gn_count = (double)cin * p.out_h * p.out_w;
+  p.gn_count = (double)h.cin * p.out_h * p.out_w;
   if (p.gn_stats && (!p.gn_gamma || !p.gn_beta)) return DDIF_ERR_ARG;
   EpiParams& e = p.epi;
   e.bias = g.bias; e.film = g.film; e.film_ld = (int)g.film_ld; e.mod = (const bf16*)g.mod; e.residual = (const bf16*)g.residual;
   e.res_ld = (int)g.res_ld; e.act = (int)g.act; e.out = (bf16*)g.out; e.out_ld = (int)g.out_ld; e.out_nchw = g.out_nchw; e.stats = g.stats;
   e.n_valid = (int)g.n_valid; e.batch = p.batch; e.out_h = p.out_h; e.out_w = p.out_w;
-  if (e.out && (e.out_ld % 8 != 0)) return DDIF_ERR_SHAPE;
-  if (e.mod && (e.n_valid % 8 != 0)) return DDIF_ERR_SHAPE;
-  if (e.residual && (e.res_ld % 8 != 0)) return DDIF_ERR_SHAPE;
   return DDIF_OK;
 }
 
@@ -719,7 +751,7 @@ int conv3_halo_launch(const GemmLaunch& L, cudaStream_t stream) {
   const HaloKParams& p = *reinterpret_cast<const HaloKParams*>(L.kparams);
   HaloKernel k = halo_kernel(L.flags);
   if (!k) return DDIF_ERR_STATE;
-  k<<<dim3(L.grid_x, 1), kHThreads, L.smem_bytes, stream>>>(p);
+  k<<<dim3(L.grid_x, L.grid_y), kHThreads, L.smem_bytes, stream>>>(p);
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }

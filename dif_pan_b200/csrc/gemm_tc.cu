@@ -282,11 +282,11 @@ static CUtensorMapSwizzle swizzle_for_span(int span) {
 
 int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   const bool wants_fused = g.gn_stats != nullptr || g.a_up != 0;
-  if (wants_fused && !conv3_applicable(g)) return DDIF_ERR_SHAPE;  // the prologue exists only in the fused 3x3 kernel
   if (!g.force_tma && conv3_halo_applicable(g)) {
     static const bool no_halo = getenv("DDIF_NO_HALO") != nullptr;  // A/B switch for profiling only
-    if (!no_halo) return conv3_halo_prepare(g, L);
+    if (!no_halo || g.nseg == 2) return conv3_halo_prepare(g, L);
   }
+  if (wants_fused && !conv3_applicable(g)) return DDIF_ERR_SHAPE;  // the prologues exist only in the 3x3 kernels
   if (wants_fused || (conv3_applicable(g) && !g.force_tma)) return conv3_prepare(g, L);
   L.variant = 0;
   GemmKParams& p = *reinterpret_cast<GemmKParams*>(L.kparams);

@@ -17,6 +17,7 @@ Training-mode forward/backward is not implemented in this round (inference path 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -296,6 +297,9 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], net: "UNetSR3") -> Dict[str, to
                 P[q + ".gamma"], P[q + ".beta"] = f32(sd[q + ".prenorm_x.weight"]), f32(sd[q + ".prenorm_x.bias"])
                 P[q + ".q0"] = f32(sd[q + ".q.0.weight"].reshape(dim, 9).t())  # [9][dim]
                 P[q + ".q1.w"] = _pack_conv(sd[q + ".q.1.weight"])
+                # q = Conv1x1(DW3x3(.)) composed once in fp32 into one dense 3x3 (sr3_dwt.py:509-512): W[o,c,ky,kx] = W1[o,c] * Wdw[c,ky,kx]
+                P[q + ".qc.w"] = _pack_conv(torch.einsum("oc,ckl->ockl", sd[q + ".q.1.weight"].to(torch.float32)[:, :, 0, 0],
+                                                          sd[q + ".q.0.weight"].to(torch.float32)[:, 0]))
                 P[q + ".q1.b"] = f32(sd[q + ".q.1.bias"])
                 cd = sd[q + ".kv.0.weight"].shape[0]
                 P[q + ".kv0"] = f32(sd[q + ".kv.0.weight"].reshape(cd, 9))
@@ -350,6 +354,7 @@ class Schedule:
         self.weff: Dict[str, Buf] = {}
         self.film_offsets = None
         self.first_body_op = 0
+        self.use_qconv = os.environ.get("DDIF_NO_QCONV") is None  # A/B switch for profiling only
 
     @staticmethod
     def _levels(net) -> int:
@@ -370,7 +375,7 @@ class Schedule:
 
     def _gemm(self, pb, label, srcs, weights, n_valid, out: Optional[Act], *, taps, stride=1, bias=None, film=None,
               film_ld=0, mod=None, residual: Optional[Act] = None, act=0, out_nchw=None, per_sample=(0, 0), w_s=None, out_hw=None,
-              gn=None, a_up=0):
+              gn=None, a_up=0, w_k=None):
         """gn = (gamma_addr, beta_addr, act): fuse GroupNorm(+Swish) of the (single) source into the conv's loader, using the
         source's own statistics; a_up = 1: read the source through a nearest x2 up-sampling."""
         a0 = srcs[0]
@@ -383,16 +388,17 @@ class Schedule:
             a_c=[s.C for s in srcs] + [0] * (2 - nseg), a_h=[s.H for s in srcs] + [0] * (2 - nseg),
             a_w=[s.W for s in srcs] + [0] * (2 - nseg), w=list(weights) + [None] * (2 - nseg),
             w_s=[(w_s[i] if w_s else taps[i]) for i in range(nseg)] + [0] * (2 - nseg),
-            w_k=[s.C for s in srcs] + [0] * (2 - nseg), taps=list(taps) + [0] * (2 - nseg),
+            w_k=(list(w_k) if w_k else [s.C for s in srcs]) + [0] * (2 - nseg), taps=list(taps) + [0] * (2 - nseg),
             w_per_sample=list(per_sample)[:nseg] + [0] * (2 - nseg), nseg=nseg, stride=stride, batch=a0.B, out_h=oh, out_w=ow,
             n_pad=n_pad, n_valid=n_valid, bias=bias, film=film, film_ld=film_ld, mod=mod,
             residual=residual.buf if residual else None, res_ld=residual.C if residual else 0, act=act,
             out=out.buf if out else None, out_ld=out.C if out else 0, out_nchw=out_nchw,
             stats=out.stats if (out is not None and out.stats is not None) else None,
             gn_stats=a0.stats if gn else None, gn_gamma=gn[0] if gn else None, gn_beta=gn[1] if gn else None, gn_eps=1e-5,
-            gn_act=gn[2] if gn else 0, a_up=a_up, force_tma=0)
+            gn_act=gn[2] if gn else 0, a_up=a_up, force_tma=0,
+            gn_stats2=srcs[1].stats if (gn and nseg == 2) else None)
         if gn:
-            assert a0.stats is not None, label
+            assert all(s.stats is not None for s in srcs), label
         m = a0.B * oh * ow
         nbytes = sum(s.B * s.H * s.W * s.C * 2 for s in srcs) + m * n_valid * (2 if out else 4)
         if residual:
@@ -574,9 +580,16 @@ class Schedule:
             q = p + ".cond_inj"
             dim, o = m.dim, m.dim_out
             assert dim == x.C + skip.C, (p, dim, x.C, skip.C)
-            xh, xdw = self._gn(pb, q + ".prenorm+dw", x, A[q + ".gamma"], A[q + ".beta"], 0, src2=skip, dw_w=A[q + ".q0"], name=q + ".xh")
             qt = self._act(pb, q + ".q", B, x.H, x.W, dim)
-            self._gemm(pb, q + ".q1", [xdw], [A[q + ".q1.w"]], dim, qt, taps=[1], bias=A[q + ".q1.b"])
+            if x.H >= 16 and x.W >= 8 and dim <= 192 and self.use_qconv:
+                # prenorm_x -> DW3x3 -> Conv1x1 as ONE tensor-core 3x3 conv over the virtual concat (x, skip) with the
+                # GroupNorm fused into its loader; x_hat itself is only needed by attn_res below
+                xh, _ = self._gn(pb, q + ".prenorm", x, A[q + ".gamma"], A[q + ".beta"], 0, src2=skip, name=q + ".xh")
+                self._gemm(pb, q + ".qconv", [x, skip], [A[q + ".qc.w"], A[q + ".qc.w"] + 2 * x.C], dim, qt, taps=[9, 9], bias=A[q + ".q1.b"],
+                           gn=(A[q + ".gamma"], A[q + ".beta"], 0), w_k=[dim, dim])
+            else:
+                xh, xdw = self._gn(pb, q + ".prenorm+dw", x, A[q + ".gamma"], A[q + ".beta"], 0, src2=skip, dw_w=A[q + ".q0"], name=q + ".xh")
+                self._gemm(pb, q + ".q1", [xdw], [A[q + ".q1.w"]], dim, qt, taps=[1], bias=A[q + ".q1.b"])
             qs = self._act(pb, q + ".qs", B, x.H, x.W, dim)
             pb.add("ddif_softmax_h_t", label=q + ".softmax_h", traffic=B * x.H * x.W * dim * 6, **{"in": qt.buf}, out=qs.buf, batch=B,
                    h=x.H, w=x.W, c=dim, scale=1.0)

@@ -58,8 +58,9 @@ enum ddif_op_kind {
 /* ---- DDIF_OP_GEMM ------------------------------------------------------------------------------------------
  * out[b,y,x,n] = epilogue( sum_seg sum_tap sum_c  a_seg[b, y*stride+dy-pad, x*stride+dx-pad, c] * w_seg[z, n, c] )
  * z = tap (shared weights) or b (per-sample weights, 1x1 only).  Zero padding comes from TMA out-of-bounds fill.
- * Two kernels implement it: conv3x3_fused_tc_kernel (3x3, stride 1, one segment: halo tile loaded once, optional fused
- * GroupNorm+Swish prologue) and conv_igemm_tc_kernel (everything else: 1x1, stride 2, two segments, per-sample weights).
+ * Three kernels implement it: conv3x3_halo_tc_kernel (3x3, stride 1: ONE TMA halo tile feeds all nine taps, optional
+ * fused GroupNorm(+Swish) prologue, 1-2 concatenated sources, N split over CTAs), conv3x3_fused_tc_kernel (its
+ * nearest-x2 up-sampling variant) and conv_igemm_tc_kernel (everything else: 1x1, stride 2, per-sample weights).
  * epilogue: v = acc + bias[n] + film[b*film_ld + n];  v = v*(1+mod[..,n]) + mod[..,n_valid+n];  v += residual;
  *           v = silu(v) if act;  stats[b] += (sum v, sum v^2);  store bf16 NHWC and/or fp32 NCHW.              */
 typedef struct {
@@ -79,6 +80,10 @@ typedef struct {
    * (sr3_dwt.py:269).  force_tma = 1 selects the generic TMA kernel even where the fused 3x3 kernel applies. */
   const double* gn_stats; const float* gn_gamma; const float* gn_beta; double gn_eps;
   int64_t gn_act, a_up, force_tma;
+  /* 3x3 stride-1 convs may take TWO segments = channel concat of two tensors (torch.cat((x, skip), 1), sr3_dwt.py:212);
+   * the fused GroupNorm then runs over the concatenation: gn_stats2 = (sum, sumsq) of segment 1, gamma/beta in concat
+   * order.  Used for FWM q = Conv1x1(DW3x3(GN(cat))) with the two convs composed into one dense 3x3 (sr3_dwt.py:507-541). */
+  const double* gn_stats2;
 } ddif_gemm_t;
 
 typedef struct { const float* x; const float* self_cond; void* out; int64_t batch, c, h, w, c_pad; } ddif_in_convert_t;

@@ -63,7 +63,8 @@ def gemm(srcs, weights, n_valid, *, taps, stride=1, bias=None, film=None, mod=No
         act=act, out=out.data_ptr() if out is not None else None, out_ld=out.shape[3] if out is not None else 0,
         out_nchw=out_nchw.data_ptr() if out_nchw is not None else None, stats=stats.data_ptr() if stats is not None else None,
         gn_stats=gn[0].data_ptr() if gn else None, gn_gamma=gn[1].data_ptr() if gn else None, gn_beta=gn[2].data_ptr() if gn else None,
-        gn_eps=1e-5, gn_act=gn[3] if gn else 0, a_up=a_up, force_tma=force_tma)
+        gn_eps=1e-5, gn_act=gn[3] if gn else 0, a_up=a_up, force_tma=force_tma,
+        gn_stats2=gn[4].data_ptr() if (gn and len(gn) > 4 and gn[4] is not None) else None)
     if sync:
         torch.cuda.synchronize()
     return (out_nchw if want_nchw else out), stats

@@ -94,6 +94,49 @@ def test_fused_gn_swish_conv3x3(name, B, H, W, Cin, Cout):
     _close(to_nchw_f32(plain), to_nchw_f32(tma), name + " fused-vs-tma")
 
 
+CONCAT = [
+    # name,        B,  H,  W, c1, c2, Cout, act
+    ("cat64_32",   2, 32, 32, 64, 32,  96, 0),   # kslab 32, three slabs, N = 96 in one CTA
+    ("cat32_32",   3, 64, 64, 32, 32,  64, 0),
+    ("cat64_64",   2, 32, 32, 64, 64, 128, 0),   # kslab 64, N split over two CTAs
+    ("cat128_64",  2, 16, 16, 128, 64, 192, 1),  # three slabs of 64, N split
+    ("cat_ragged", 1, 24, 40, 32, 16,  48, 1),   # kslab 16, partial tiles
+    ("cat_many32", 40, 64, 64, 32, 32,  64, 0),  # every persistent CTA walks several (tile, slab) units
+    ("cat_many64", 48, 32, 32, 64, 64, 128, 1),  # ... with the N split and three stages
+    ("cat_many192", 80, 16, 16, 128, 64, 192, 0),
+]
+
+
+@pytest.mark.parametrize("name,B,H,W,c1,c2,Cout,act", CONCAT, ids=[c[0] for c in CONCAT])
+def test_concat_gn_conv3x3(name, B, H, W, c1, c2, Cout, act):
+    """Two K segments = channel concat of two tensors, GroupNorm over the concatenation fused into the loader
+    (FWM q = Conv1x1(DW3x3(GN(cat(x, skip)))) composed into one dense 3x3; sr3_dwt.py:212,507-541)."""
+    x1 = _rand(B, c1, H, W, seed=41, scale=1.5) + 0.4
+    x2 = _rand(B, c2, H, W, seed=42, scale=0.7) - 0.2
+    C = c1 + c2
+    w = _rand(Cout, C, 3, 3, seed=43, scale=1.0 / math.sqrt(C * 9))
+    bias = _rand(Cout, seed=44)
+    gamma, beta = 1 + 0.1 * _rand(C, seed=45), 0.1 * _rand(C, seed=46)
+    a1, a2 = nhwc_bf16(x1), nhwc_bf16(x2)
+    f1, f2 = to_nchw_f32(a1), to_nchw_f32(a2)
+    st = lambda f: torch.stack([f.double().sum(dim=(1, 2, 3)), (f.double() ** 2).sum(dim=(1, 2, 3))], dim=1).contiguous()
+    s1, s2 = st(f1), st(f2)
+    w1, w2 = pack_w(w[:, :c1].contiguous()), pack_w(w[:, c1:].contiguous())
+    out, stats = gemm([a1, a2], [w1, w2], Cout, taps=[9, 9], bias=bias, gn=(s1, gamma, beta, act, s2), want_stats=True)
+    h = F.group_norm(torch.cat([f1, f2], 1), 1, gamma, beta, eps=1e-5)
+    if act:
+        h = h * torch.sigmoid(h)
+    ref = F.conv2d(h.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, padding=1)
+    got = to_nchw_f32(out)
+    assert rel_err(got, ref) < 6e-3, rel_err(got, ref)
+    assert float((got - ref).abs().max()) < 0.06 * float(ref.abs().max())
+    s_ref = torch.stack([ref.double().sum(dim=(1, 2, 3)), (ref.double() ** 2).sum(dim=(1, 2, 3))], dim=1)
+    assert torch.allclose(stats, s_ref, rtol=5e-3, atol=1.0), (stats, s_ref)
+    # no GroupNorm: plain concat conv
+    plain, _ = gemm([a1, a2], [w1, w2], Cout, taps=[9, 9], bias=bias)
+    _close(to_nchw_f32(plain), F.conv2d(torch.cat([f1, f2], 1), w.to(torch.bfloat16).float(), bias, padding=1), name + " plain")
+
+
 def test_fused_upsample_conv_and_epilogue():
     B, H, W, C = 2, 16, 16, 64
     x = _rand(B, C, H, W, seed=31)

@@ -16,7 +16,8 @@ from dif_pan_b200 import synth  # noqa: E402
 
 def category(label, struct):
     if struct == "ddif_gemm_t":
-        for key in ("x_conv", "q1", "attn_out", "ffn0", "ffn23", "block1.conv", "block2.conv", "qkv", ".out", "final", "downs.0"):
+        for key in ("x_conv", "qconv", "q1", "attn_out", "ffn0", "ffn23", "gn+conv", "block1.conv", "block2.conv", "qkv", ".out", "final", "downs.0",
+                    "up+conv"):
             if key in label:
                 return "gemm:" + key
         return "gemm:resample"

@@ -46,6 +46,7 @@ struct alignas(64) HaloKParams {
   int stages;
   uint32_t stage_bytes, b_slot_bytes;
   uint32_t idesc, layout_type, tmem_cols;
+  int nacc;            // TMEM accumulators: 2 (one per half-pipeline) or 4 (two per half-pipeline: the MMA warp runs one tile ahead of its epilogue group)
   const double* gn_stats;
   const double* gn_stats2;  // statistics of segment 1 (the GroupNorm runs over the concatenated tensor)
   const float* gn_gamma;
@@ -177,6 +178,11 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
     if (tid == 0) h_ts(dts, 3, tcount, 0);
     mbar_wait(&a_tma[stage], phase);
     if (tid == 0) h_ts(dts, 3, tcount, 1);
+#ifndef DDIF_VAR_NO_XFORM
+    // Branch-free: every chunk is loaded and normalised unconditionally (rows past the halo / padding pixels compute on
+    // whatever is there) and only the STORE is predicated, so the BATCH chunks of a thread form independent dependency
+    // chains the scheduler can interleave (MUFU.TANH issues at 8 cycles per warp instruction per SM sub-partition:
+    // profiles/r01_microbench_sfu_rate.txt); per-chunk divergent regions serialised them.
 #pragma unroll
     for (int k0 = 0; k0 < NPASS; k0 += BATCH) {
       uint4 v[BATCH];
@@ -184,26 +190,29 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
 #pragma unroll
       for (int k = 0; k < BATCH; ++k) {
         ok[k] = (unsigned)(y0 + (hyx[k0 + k] >> 8)) < H && (unsigned)(x0 + (hyx[k0 + k] & 255)) < W;
-        if (ok[k]) v[k] = h_lds128(sbase + soff[k0 + k]);
+        v[k] = h_lds128(sbase + soff[k0 + k]);
       }
 #pragma unroll
       for (int k = 0; k < BATCH; ++k) {
-        if (ok[k]) {
-          const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-          uint32_t o[4];
+        const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        uint32_t o[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            f32x2 t = fma2(bf2_to_f2(w[q]), a2[q], d2[q]);
-            if (act) t = swish_half2(t);
-            o[q] = f2_to_bf2(t);
-          }
-          h_sts128(sbase + soff[k0 + k], make_uint4(o[0], o[1], o[2], o[3]));
+        for (int q = 0; q < 4; ++q) {
+          f32x2 t = fma2(bf2_to_f2(w[q]), a2[q], d2[q]);
+          if (act) t = swish_half2(t);
+          o[q] = f2_to_bf2(t);
         }
+        v[k] = make_uint4(o[0], o[1], o[2], o[3]);
       }
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k)
+        if (ok[k]) h_sts128(sbase + soff[k0 + k], v[k]);
     }
+#endif
     if (tid == 0) h_ts(dts, 3, tcount, 2);
     h_fence_proxy_async();
-    mbar_arrive(&a_ready[stage]);
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&a_ready[stage]);  // one arrive per warp (count kHxfGroup / 32)
     if (tid == 0) h_ts(dts, 3, tcount, 3);
     ++tcount;
     if (++stage == nst) { stage = 0; phase ^= 1u; }
@@ -232,11 +241,13 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
   uint32_t stage = 0, phase = 0;
   mbar_wait(b_full, 0u);
   tc_fence_after();
-  const uint32_t tmem_d = tmem_base + (uint32_t)w * (uint32_t)p.bn;
+  const bool four = p.nacc == 4;
   uint32_t itn = 0;
   for (int t = w; t < my_tiles; t += 2, ++itn) {
     if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 0);
-    mbar_wait(&tmem_empty[w], (itn & 1u) ^ 1u);
+    const uint32_t acc = (uint32_t)w + (four ? 2u * (itn & 1u) : 0u);
+    const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.bn;
+    mbar_wait(&tmem_empty[acc], ((four ? itn >> 1 : itn) & 1u) ^ 1u);
     tc_fence_after();
     if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 1);
     uint64_t db = desc_b0;
@@ -245,15 +256,17 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
       tc_fence_after();
       if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 2);
       const uint64_t da = desc_a0 + (uint64_t)(stage * stage16);
+#ifndef DDIF_VAR_NO_MMA
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         umma_bf16_ss_steps<KSTEPS>(tmem_d, da + tap_off[tap], db, p.idesc, (slab | tap) != 0 ? 1u : 0u);
         db += b16;
       }
+#endif
       umma_commit_elect(&a_empty[stage]);
       if (++stage == nst) { stage = 0; phase ^= 1u; }
     }
-    umma_commit_elect(&tmem_full[w]);
+    umma_commit_elect(&tmem_full[acc]);
     if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 3);
   }
 }
@@ -287,9 +300,8 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
   double* stats = p.epi.stats;
   const int out_h = p.out_h, out_w = p.out_w, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
   const size_t hw = (size_t)out_h * out_w;
-  const uint32_t tm_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * (uint32_t)p.bn;
-  uint64_t* full = &tmem_full[grp];
-  uint64_t* empty = &tmem_empty[grp];
+  const uint32_t tm_lane0 = tmem_base + ((uint32_t)(q * 32) << 16);
+  const bool four = p.nacc == 4;
   // per-warp additive vector (bias, or FiLM row of the tile's sample [+ bias]) in shared memory: with ~200 KB of dynamic
   // smem the L1 is a few KB, so per-tile __ldg of these vectors paid an L2 round trip per 16-channel chunk
   float* addv = s_add + (warp - 10) * 256;
@@ -336,7 +348,10 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
         if (nch > 1) ldg256(res_px + 16, rs1);
       }
     }
-    mbar_wait(full, it & 1u);
+    const uint32_t acc = (uint32_t)grp + (four ? 2u * (it & 1u) : 0u);
+    const uint32_t tm_lane = tm_lane0 + acc * (uint32_t)p.bn;
+    uint64_t* empty = &tmem_empty[acc];
+    mbar_wait(&tmem_full[acc], (four ? it >> 1 : it) & 1u);
     tc_fence_after();
     if (warp == 10 && lane == 0) h_ts(dts, 2, t, 0);
     if (film) {
@@ -427,8 +442,10 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
         __syncwarp();
         if (lane == 0) mbar_arrive(empty);
       }
+#ifndef DDIF_VAR_NO_EPI
       process(a0, rs0, cc);
       if (two) process(a1, rs1, cc + 1);
+#endif
     }
     if (warp == 10 && lane == 0) h_ts(dts, 2, t, 2);
     if (kStats) {
@@ -465,9 +482,9 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   uint64_t* a_tma = bars;                       // [stages] TMA landed
   uint64_t* a_ready = bars + kHMaxStages;       // [stages] transformed (count 256)
   uint64_t* a_empty = bars + 2 * kHMaxStages;   // [stages] MMAs done
-  uint64_t* tmem_full = bars + 3 * kHMaxStages; // [2]
-  uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint64_t* b_full = tmem_empty + 2;            // [1]
+  uint64_t* tmem_full = bars + 3 * kHMaxStages; // [4]
+  uint64_t* tmem_empty = tmem_full + 4;         // [4]
+  uint64_t* b_full = tmem_empty + 4;            // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -495,10 +512,10 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
     if (lane == 0) {
       for (int i = 0; i < p.stages; ++i) {
         mbar_init(&a_tma[i], 1);
-        mbar_init(&a_ready[i], kHxfGroup);
+        mbar_init(&a_ready[i], kHxfGroup / 32);
         mbar_init(&a_empty[i], 1);
       }
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < p.nacc; ++i) {
         mbar_init(&tmem_full[i], 1);
         mbar_init(&tmem_empty[i], kHEpiWarps / 2);
       }
@@ -549,11 +566,17 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
         h_ts(dts, 0, u, 0);
         mbar_wait(&a_empty[stage], rp[ring] ^ 1u);
         h_ts(dts, 0, u, 1);
+#ifdef DDIF_VAR_NO_TMA
+        mbar_arrive(&a_tma[stage]);
+#else
         mbar_expect_tx(&a_tma[stage], tx);
         const int seg = it.slab >= p.nslab0;
         tma_load_4d(&p.tmA[seg], &a_tma[stage], smem_a + (size_t)stage * p.stage_bytes, (seg ? it.slab - p.nslab0 : it.slab) * p.kslab, it.tx * 8 - 1,
                     it.ty * 16 - 1, it.b);
+#endif
+#ifndef DDIF_VAR_NO_RESPF
         if (p.has_res_map && it.slab == 0) tma_prefetch_l2_4d(&p.tmR, (int)blockIdx.y * p.bn, it.tx * 8, it.ty * 16, it.b);  // residual tile -> L2, `stages` tiles ahead
+#endif
         if (++rs[ring] == nst) { rs[ring] = 0; rp[ring] ^= 1u; }
         if (it.slab == p.nslab - 1) ring ^= 1u;  // next tile -> other half-pipeline
       }
@@ -638,7 +661,7 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
   if (!g.out && !g.out_nchw) return false;
   h.cin = cin;
   h.n_stat = g.gn_stats ? (int)(g.batch < kHMaxStat ? g.batch : kHMaxStat) : 0;
-  h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + (3 * kHMaxStages + 8) * 8 + 64 + 1024;
+  h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + (3 * kHMaxStages + 12) * 8 + 64 + 1024;
   // Resident weights of one CTA (9 taps x all K slabs x bn rows) must leave room for two rings of >= 2 halo stages:
   // split N over blockIdx.y (1, 2, 4 CTAs per tile) and, before splitting further, halve the K slab (smaller stages).
   for (int pass = 0; pass < 2; ++pass) {  // pass 0: >= 4 stages; pass 1: accept 2
@@ -689,8 +712,9 @@ int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   p.stage_bytes = (uint32_t)h.stage_bytes;
   p.b_slot_bytes = (uint32_t)h.b_slot;
   p.layout_type = p.span == 128 ? 2u : p.span == 64 ? 4u : 6u;
+  p.nacc = 4 * p.bn <= 512 ? 4 : 2;
   uint32_t cols = 32;
-  while ((int)cols < 2 * p.bn) cols <<= 1;
+  while ((int)cols < p.nacc * p.bn) cols <<= 1;
   p.tmem_cols = cols;
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   L.smem_bytes = h.smem;

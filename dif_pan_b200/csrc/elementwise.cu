@@ -379,8 +379,59 @@ __global__ void softmax_h_kernel(const bf16* __restrict__ in, bf16* __restrict__
     }
   }
 }
+// Register-resident variant for H <= 64: one thread owns one bf16x2 word (2 channels) of one image column, keeps its H
+// values packed in registers (H independent 4-byte loads in flight; a warp covers 128 contiguous bytes per row) and
+// makes ONE pass over HBM: 4 B/element instead of 6, one exp per element instead of three.
+template <int H>
+__global__ void __launch_bounds__(128) softmax_h_reg_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t items,
+                                                            int row_words, float scale) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / row_words;
+    const int r = (int)(i - b * row_words);
+    const uint32_t* src = in + (size_t)b * H * row_words + r;
+    uint32_t* dst = out + (size_t)b * H * row_words + r;
+    uint32_t w[H];
+#pragma unroll
+    for (int y = 0; y < H; ++y) w[y] = __ldg(src + (size_t)y * row_words);
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int y = 0; y < H; ++y) {
+      m0 = fmaxf(m0, __uint_as_float(w[y] << 16));
+      m1 = fmaxf(m1, __uint_as_float(w[y] & 0xffff0000u));
+    }
+    const float c0 = -m0 * kLog2e, c1 = -m1 * kLog2e;
+    float l0 = 0.f, l1 = 0.f;
+    float e0[H], e1[H];
+#pragma unroll
+    for (int y = 0; y < H; ++y) {
+      e0[y] = exp2f(fmaf(__uint_as_float(w[y] << 16), kLog2e, c0));
+      e1[y] = exp2f(fmaf(__uint_as_float(w[y] & 0xffff0000u), kLog2e, c1));
+      l0 += e0[y];
+      l1 += e1[y];
+    }
+    const float r0 = scale / l0, r1 = scale / l1;
+#pragma unroll
+    for (int y = 0; y < H; ++y) {
+      const __nv_bfloat162 t = __floats2bfloat162_rn(e0[y] * r0, e1[y] * r1);
+      dst[(size_t)y * row_words] = *reinterpret_cast<const uint32_t*>(&t);
+    }
+  }
+}
+template <int H>
+static int launch_softmax_h_reg(const ddif_softmax_h_t& p, cudaStream_t s) {
+  const int row_words = (int)(p.w * p.c / 2);
+  const int64_t items = p.batch * (int64_t)row_words;
+  softmax_h_reg_kernel<H><<<grid_for(items, 128, 148 * 24), 128, 0, s>>>((const uint32_t*)p.in, (uint32_t*)p.out, items, row_words, (float)p.scale);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
 int launch_softmax_h(const ddif_softmax_h_t& p, cudaStream_t s) {
   if (p.c % 8 != 0) return DDIF_ERR_SHAPE;
+  if (p.h == 64) return launch_softmax_h_reg<64>(p, s);
+  if (p.h == 32) return launch_softmax_h_reg<32>(p, s);
+  if (p.h == 16) return launch_softmax_h_reg<16>(p, s);
+  if (p.h == 8) return launch_softmax_h_reg<8>(p, s);
   softmax_h_kernel<<<grid_for(p.batch * p.w * (p.c / 8), 128), 128, 0, s>>>((const bf16*)p.in, (bf16*)p.out, (int)p.batch, (int)p.h,
                                                                               (int)p.w, (int)p.c, (float)p.scale);
   DDIF_LAUNCH_CHECK();

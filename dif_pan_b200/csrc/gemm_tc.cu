@@ -40,7 +40,8 @@ struct alignas(64) GemmKParams {
   int b_slots;             // resident_b ? total K iterations : stages
   uint32_t idesc;
   uint32_t layout_type;
-  uint32_t tmem_cols;      // 2 accumulators of bn columns, rounded to a power of two >= 32
+  uint32_t tmem_cols;      // `groups` accumulators of bn columns, rounded to a power of two >= 32
+  int groups;              // TMEM accumulators = epilogue warp groups working on different tiles (2 or 4)
   const float* bias;
   const float* film;
   int film_ld;
@@ -72,9 +73,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_slots * b_slot_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
-  uint64_t* tmem_full_bar = bars + 2 * p.stages;       // [2]
-  uint64_t* tmem_empty_bar = bars + 2 * p.stages + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+  uint64_t* tmem_full_bar = bars + 2 * p.stages;       // [4]
+  uint64_t* tmem_empty_bar = bars + 2 * p.stages + 4;  // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,9 +94,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
         mbar_init(&full_bar[i], 1);
         mbar_init(&empty_bar[i], 1);
       }
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < p.groups; ++i) {
         mbar_init(&tmem_full_bar[i], 1);
-        mbar_init(&tmem_empty_bar[i], kEpiWarps);  // one arrive per epilogue warp
+        mbar_init(&tmem_empty_bar[i], kEpiWarps / p.groups);  // one arrive per epilogue warp of the group
       }
       mbar_fence_init();
     }
@@ -178,9 +179,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
       const uint64_t desc_b0 = make_smem_desc(smem_u32(smem_b), sbo, p.layout_type);
       const uint32_t a_step = (uint32_t)a_stage_bytes >> 4, b_step = (uint32_t)b_slot_bytes >> 4;
       const bool resident = p.resident_b != 0;
-      uint32_t stage = 0, phase = 0, tcount = 0;
-      for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x, ++tcount) {
-        const uint32_t acc = tcount & 1u, acc_phase = (tcount >> 1) & 1u;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const uint32_t ngroups = (uint32_t)p.groups;
+      for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.bn;
@@ -202,13 +203,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
           }
         }
         umma_commit_elect(&tmem_full_bar[acc]);
+        if (++acc == ngroups) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
     }
   } else {
     // ===================== epilogue (warps 2..17) =====================
-    // warp -> (TMEM lane quarter q = warp % 4, column group cg); see epilogue.cuh.
+    // warp -> (TMEM lane quarter q = warp % 4, tile group grp, column group cg); see epilogue.cuh.  Group g owns TMEM
+    // accumulator g and the CTA's tiles g, g + groups, ...: while one group waits for its residual / modulation loads and
+    // stores a tile, the others work on the next tiles (a single group left the 1x1 convs latency-bound: ~4000 cycles per
+    // 128 x 32 tile, profiles/r01_step_profile_B256_s4.txt x_conv rows).
     const int q = warp & 3;
-    const int cg = (warp - 2) >> 2;
+    const int sub = (warp - 2) >> 2;
+    const int grp = p.groups == 4 ? sub : (sub & 1);
+    const int cg = p.groups == 4 ? 0 : (sub >> 1);
     const int row = q * 32 + lane;
     const int px_per_img = p.tw * p.th;
     const int tn_i = row / px_per_img;
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
     EpiParams e{p.bias, p.film, p.film_ld, p.mod, p.residual, p.res_ld, p.act, p.out, p.out_ld, p.out_nchw, p.stats,
                 p.n_valid, p.batch, p.out_h, p.out_w};
     uint32_t tcount = 0;
-    for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x, ++tcount) {
+    for (int m_tile = (int)blockIdx.x + grp * (int)gridDim.x; m_tile < p.num_m_tiles; m_tile += p.groups * (int)gridDim.x, ++tcount) {
       const int img_grp = m_tile / tiles_per_img;
       const int t_in = m_tile - img_grp * tiles_per_img;
       const int y = (t_in / p.tiles_x) * p.th + ry;
@@ -229,11 +239,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
       const size_t pix = ((size_t)b * p.out_h + y) * p.out_w + x;
       EpiPrefetch pf;
       epilogue_prefetch<4>(e, pf, n_tile, p.bn, cg, row_ok, pix);
-      const uint32_t acc = tcount & 1u, acc_phase = (tcount >> 1) & 1u;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      mbar_wait(&tmem_full_bar[grp], tcount & 1u);
       tc_fence_after();
-      epilogue_tile<4>(e, pf, tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.bn, &tmem_empty_bar[acc], p.bn, n_tile, cg, lane,
-                       active, row_ok, b, y, x, pix, n0 + (q * 32) / px_per_img);
+      const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)grp * (uint32_t)p.bn;
+      if (p.groups == 4)
+        epilogue_tile<1>(e, pf, tm, &tmem_empty_bar[grp], p.bn, n_tile, cg, lane, active, row_ok, b, y, x, pix, n0 + (q * 32) / px_per_img);
+      else
+        epilogue_tile<2>(e, pf, tm, &tmem_empty_bar[grp], p.bn, n_tile, cg, lane, active, row_ok, b, y, x, pix, n0 + (q * 32) / px_per_img);
     }
     tc_fence_before();
   }
@@ -338,8 +350,9 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   }
   p.bn = bn;
   p.n_valid = (int)g.n_valid;
+  p.groups = 4 * bn <= 512 ? 4 : 2;
   uint32_t cols = 32;
-  while ((int)cols < 2 * bn) cols <<= 1;  // two accumulators
+  while ((int)cols < p.groups * bn) cols <<= 1;
   p.tmem_cols = cols;
   // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at bit 17, M>>4 at bit 24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -362,7 +375,7 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   if (!p.resident_b) p.b_slots = stages;
   p.stages = stages;
   p.num_m_tiles = p.tiles_x * p.tiles_y * (int)ceil_div(B, tn);
-  L.smem_bytes = stages * a_stage + p.b_slots * b_slot + (2 * stages + 6) * 8 + 1024;
+  L.smem_bytes = stages * a_stage + p.b_slots * b_slot + (2 * stages + 10) * 8 + 1024;
   const int sms = ddif_sm_count();
   L.grid_y = (int)(g.n_pad / bn);
   const int gx = (sms + L.grid_y - 1) / L.grid_y;  // persistent: ~one CTA per SM in total

@@ -419,8 +419,9 @@ class Schedule:
 
     @staticmethod
     def _fusable(x: Act) -> bool:
-        """The fused GN+Swish+conv3x3 kernel tiles the image in 8x16 pixel boxes (csrc/conv3x3_tc.cu)."""
-        return x.W >= 16 and x.H >= 8 and x.C <= 256
+        """The halo kernel with the GN+Swish prologue tiles the image in 8 (x) x 16 (y) pixel boxes (csrc/conv3x3_halo.cu);
+        at the 8x8 level half of every tile is padding, still cheaper than a stand-alone normalisation launch."""
+        return x.W >= 8 and x.H >= 8 and x.C <= 256
 
     def _gn_conv3(self, label, x: Act, gamma, beta, w, n_valid, out, **kw):
         """Block = GN -> Swish -> Conv3x3 (sr3_dwt.py:288-300): one fused kernel where the tile shape allows, else

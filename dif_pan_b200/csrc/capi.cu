@@ -1,11 +1,18 @@
 // extern "C" surface of libddif_b200.so: immediate launches, the recorded op list ("plan") that replays one
 // UNet forward per call, CUDA-graph capture of a plan, and per-op event profiling.  See include/ddif_b200.h.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
 #include "ddif_internal.h"
 
 namespace ddif {
+
+bool ddif_pdl_enabled() {
+  static const bool on = getenv("DDIF_NO_PDL") == nullptr;
+  return on;
+}
 
 union OpParams {
   ddif_gemm_t gemm;

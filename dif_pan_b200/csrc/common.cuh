@@ -28,6 +28,23 @@ typedef __nv_bfloat16 bf16;
 
 namespace ddif {
 
+// Host: launch with the PDL attribute (DDIF_NO_PDL=1 in the environment turns it off for A/B measurements).
+bool ddif_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = ddif_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- bf16 <-> fp32 vector helpers (8 channels = 16 bytes) -------------------------------------------------
@@ -106,6 +123,21 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The ~210 kernels of one UNet forward run back to back on one stream / graph branch.  Launched with the
+// programmatic-stream-serialization attribute, kernel i+1 becomes resident as soon as kernel i's CTAs exit and runs its
+// prologue (barrier init, TMEM allocation, descriptor prefetch, resident WEIGHT loads -- nothing a previous kernel of
+// the step writes) while kernel i's tail drains; pdl_wait() then blocks until kernel i has completed and its memory is
+// visible.  RULE: every kernel launched through launch_pdl() calls pdl_wait() in ALL threads before its first access
+// to activations / statistics / the workspace and before exiting (completion of kernel i then implies completion of
+// kernels < i, which keeps workspace reuse and skip connections safe).  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+#ifndef DDIF_PDL_NO_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------

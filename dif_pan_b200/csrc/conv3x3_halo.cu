@@ -493,13 +493,6 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   const bool gn = p.gn_stats != nullptr;
   long long* const dts = (blockIdx.x == 0 && blockIdx.y == 0) ? g_halo_ts : nullptr;
 
-  if (gn) {
-    for (int i = threadIdx.x; i < p.cin; i += blockDim.x) {
-      s_gamma[i] = p.gn_gamma[i];
-      s_beta[i] = p.gn_beta[i];
-    }
-    for (int i = threadIdx.x; i < n_stat; i += blockDim.x) s_stat[i] = halo_mean_rstd(p, i);  // fp64 once per CTA
-  }
   if (warp == 18 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB[0]);
@@ -530,6 +523,23 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Resident weights: static data, requested BEFORE the dependency wait so that the load overlaps the previous kernel's tail.
+  if (warp == 18 && lane == 0) {
+    mbar_expect_tx(b_full, (uint32_t)(9 * p.nslab) * p.b_slot_bytes);
+    for (int slab = 0; slab < p.nslab; ++slab)
+      for (int tap = 0; tap < 9; ++tap)
+        tma_load_3d(&p.tmB[slab >= p.nslab0], b_full, smem_b + (size_t)(slab * 9 + tap) * p.b_slot_bytes,
+                    (slab >= p.nslab0 ? slab - p.nslab0 : slab) * p.kslab, (int)blockIdx.y * p.bn, tap);
+  }
+  pdl_wait();  // everything below reads what earlier kernels of the step wrote
+  if (gn) {
+    for (int i = threadIdx.x; i < p.cin; i += blockDim.x) {
+      s_gamma[i] = p.gn_gamma[i];
+      s_beta[i] = p.gn_beta[i];
+    }
+    for (int i = threadIdx.x; i < n_stat; i += blockDim.x) s_stat[i] = halo_mean_rstd(p, i);  // fp64 once per CTA
+    __syncthreads();
+  }
 
   if (warp < 8) {
     // ===================== transform warps (only with the GroupNorm prologue) =====================
@@ -547,13 +557,8 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
     else if (p.kslab == 32) halo_mma_loop<2>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
     else halo_mma_loop<1>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
   } else if (warp == 18) {
-    // ===================== TMA producer: resident weights once, then the halo ring =====================
+    // ===================== TMA producer: the halo ring (the resident weights were requested above) =====================
     if (lane == 0) {
-      mbar_expect_tx(b_full, (uint32_t)(9 * p.nslab) * p.b_slot_bytes);
-      for (int slab = 0; slab < p.nslab; ++slab)
-        for (int tap = 0; tap < 9; ++tap)
-          tma_load_3d(&p.tmB[slab >= p.nslab0], b_full, smem_b + (size_t)(slab * 9 + tap) * p.b_slot_bytes,
-                      (slab >= p.nslab0 ? slab - p.nslab0 : slab) * p.kslab, (int)blockIdx.y * p.bn, tap);
       const uint32_t tx = (uint32_t)(kHPx * p.span);
       const uint32_t nst = (uint32_t)p.stages >> 1;  // per ring
       HaloIter it;
@@ -580,6 +585,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
         if (++rs[ring] == nst) { rs[ring] = 0; rp[ring] ^= 1u; }
         if (it.slab == p.nslab - 1) ring ^= 1u;  // next tile -> other half-pipeline
       }
+      pdl_trigger();  // all loads of this CTA are in flight: the next kernel's CTAs may take over SMs as ours exit
     }
   } else if (warp >= 10 && warp < 18) {
     // ===================== epilogue (warps 10..17): two groups of 4 warps, one TMEM accumulator each =====================
@@ -775,8 +781,7 @@ int conv3_halo_launch(const GemmLaunch& L, cudaStream_t stream) {
   const HaloKParams& p = *reinterpret_cast<const HaloKParams*>(L.kparams);
   HaloKernel k = halo_kernel(L.flags);
   if (!k) return DDIF_ERR_STATE;
-  k<<<dim3(L.grid_x, L.grid_y), kHThreads, L.smem_bytes, stream>>>(p);
-  DDIF_LAUNCH_CHECK();
+  DDIF_CUDA_CHECK(launch_pdl(k, dim3(L.grid_x, L.grid_y), dim3(kHThreads), (size_t)L.smem_bytes, stream, p));
   return DDIF_OK;
 }
 

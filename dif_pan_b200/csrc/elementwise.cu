@@ -18,6 +18,7 @@ static inline int grid_for(int64_t items, int threads, int cap = 148 * 16) {
 // ---- NCHW fp32 (x, self_cond) -> NHWC bf16 [self_cond | x | 0-pad]   (sr3_dwt.py:172-174) -----------------
 __global__ void in_convert_kernel(const float* __restrict__ x, const float* __restrict__ sc, bf16* __restrict__ out,
                                   int B, int C, int HW, int c_pad) {
+  pdl_wait();
   const int64_t total = (int64_t)B * HW;
   const int nsrc = sc ? 2 : 1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -44,13 +45,14 @@ __global__ void in_convert_kernel(const float* __restrict__ x, const float* __re
 int launch_in_convert(const ddif_in_convert_t& p, cudaStream_t s) {
   if (p.c_pad % 8 != 0 || p.c_pad < (p.self_cond ? 2 : 1) * p.c) return DDIF_ERR_SHAPE;
   const int64_t hw = p.h * p.w;
-  in_convert_kernel<<<grid_for(p.batch * hw, 256), 256, 0, s>>>(p.x, p.self_cond, (bf16*)p.out, (int)p.batch, (int)p.c, (int)hw, (int)p.c_pad);
+  DDIF_CUDA_CHECK(launch_pdl(in_convert_kernel, dim3(grid_for(p.batch * hw, 256)), dim3(256), (size_t)(0), s, p.x, p.self_cond, (bf16*)p.out, (int)p.batch, (int)p.c, (int)hw, (int)p.c_pad));
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }
 
 // ---- time embedding + all FiLM vectors (sr3_dwt.py:57-64, 223-238, 245-257) ------------------------------
 __global__ void time_embed_kernel(ddif_time_embed_t p) {
+  pdl_wait();
   extern __shared__ float sm[];
   const int inner = (int)p.inner, hid = 4 * inner, count = inner / 2;
   float* enc = sm;
@@ -85,7 +87,7 @@ __global__ void time_embed_kernel(ddif_time_embed_t p) {
 }
 int launch_time_embed(const ddif_time_embed_t& p, cudaStream_t s) {
   if (p.inner % 2 != 0 || p.inner > 256) return DDIF_ERR_SHAPE;
-  time_embed_kernel<<<(int)p.batch, 256, (size_t)(6 * p.inner) * sizeof(float), s>>>(p);
+  DDIF_CUDA_CHECK(launch_pdl(time_embed_kernel, dim3((int)p.batch), dim3(256), (size_t)((size_t)(6 * p.inner) * sizeof(float)), s, p));
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }
@@ -115,6 +117,7 @@ static constexpr int kGnThreads = 192;  // divisible by every chunk count the UN
 
 template <bool DW>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(GnK p) {
+  pdl_wait();
   const int b = blockIdx.y;
   const int C = p.c1 + p.c2;
   const int nchunk = C >> 3;
@@ -215,6 +218,7 @@ static constexpr int kDwTW = 16, kDwTH = 8, kDwHW = kDwTW + 2, kDwHH = kDwTH + 2
 static constexpr int kDwCh = 32, kDwPitch = 144, kDwThreads = 256;
 
 __global__ void __launch_bounds__(kDwThreads) gn_dw_tile_kernel(GnK p) {
+  pdl_wait();
   __shared__ __align__(16) uint8_t s_tile[kDwHalo * kDwPitch];
   __shared__ __align__(16) float s_w[9][kDwCh];
   __shared__ __align__(16) float s_a[kDwCh], s_d[kDwCh];
@@ -324,7 +328,7 @@ int launch_gn_apply(const ddif_gn_apply_t& p, cudaStream_t s) {
     GnK k{(const bf16*)p.src1, (const bf16*)p.src2, (int)p.c1, (int)p.c2, p.stats1, p.stats2, p.gamma, p.beta,
           (bf16*)p.out, p.dw_w, (bf16*)p.out_dw, (int)p.h, (int)p.w, (int)p.act, (float)p.eps};
     const int64_t tiles = ceil_div(p.w, kDwTW) * ceil_div(p.h, kDwTH);
-    gn_dw_tile_kernel<<<dim3((unsigned)(tiles * ((p.c1 + p.c2) / kDwCh)), (unsigned)p.batch), kDwThreads, 0, s>>>(k);
+    DDIF_CUDA_CHECK(launch_pdl(gn_dw_tile_kernel, dim3(dim3((unsigned)(tiles * ((p.c1 + p.c2) / kDwCh)), (unsigned)p.batch)), dim3(kDwThreads), (size_t)(0), s, k));
     DDIF_LAUNCH_CHECK();
     return DDIF_OK;
   }
@@ -338,15 +342,16 @@ int launch_gn_apply(const ddif_gn_apply_t& p, cudaStream_t s) {
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   if (p.dw_w)
-    gn_apply_kernel<true><<<dim3((unsigned)gx, (unsigned)p.batch), kGnThreads, 0, s>>>(k);
+    DDIF_CUDA_CHECK(launch_pdl(gn_apply_kernel<true>, dim3(dim3((unsigned)gx, (unsigned)p.batch)), dim3(kGnThreads), (size_t)(0), s, k));
   else
-    gn_apply_kernel<false><<<dim3((unsigned)gx, (unsigned)p.batch), kGnThreads, 0, s>>>(k);
+    DDIF_CUDA_CHECK(launch_pdl(gn_apply_kernel<false>, dim3(dim3((unsigned)gx, (unsigned)p.batch)), dim3(kGnThreads), (size_t)(0), s, k));
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }
 
 // ---- q.softmax(dim=-2) * scale   (sr3_dwt.py:545, 561): softmax over H for every (b, x, channel) ---------
 __global__ void softmax_h_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C, float scale) {
+  pdl_wait();
   const int nchunk = C >> 3;
   const int64_t items = (int64_t)B * W * nchunk;
   const size_t row = (size_t)W * C;
@@ -385,6 +390,7 @@ __global__ void softmax_h_kernel(const bf16* __restrict__ in, bf16* __restrict__
 template <int H>
 __global__ void __launch_bounds__(128) softmax_h_reg_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t items,
                                                             int row_words, float scale) {
+  pdl_wait();
   constexpr float kLog2e = 1.4426950408889634f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / row_words;
@@ -422,7 +428,7 @@ template <int H>
 static int launch_softmax_h_reg(const ddif_softmax_h_t& p, cudaStream_t s) {
   const int row_words = (int)(p.w * p.c / 2);
   const int64_t items = p.batch * (int64_t)row_words;
-  softmax_h_reg_kernel<H><<<grid_for(items, 128, 148 * 24), 128, 0, s>>>((const uint32_t*)p.in, (uint32_t*)p.out, items, row_words, (float)p.scale);
+  DDIF_CUDA_CHECK(launch_pdl(softmax_h_reg_kernel<H>, dim3(grid_for(items, 128, 148 * 24)), dim3(128), (size_t)(0), s, (const uint32_t*)p.in, (uint32_t*)p.out, items, row_words, (float)p.scale));
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }
@@ -432,8 +438,8 @@ int launch_softmax_h(const ddif_softmax_h_t& p, cudaStream_t s) {
   if (p.h == 32) return launch_softmax_h_reg<32>(p, s);
   if (p.h == 16) return launch_softmax_h_reg<16>(p, s);
   if (p.h == 8) return launch_softmax_h_reg<8>(p, s);
-  softmax_h_kernel<<<grid_for(p.batch * p.w * (p.c / 8), 128), 128, 0, s>>>((const bf16*)p.in, (bf16*)p.out, (int)p.batch, (int)p.h,
-                                                                              (int)p.w, (int)p.c, (float)p.scale);
+  DDIF_CUDA_CHECK(launch_pdl(softmax_h_kernel, dim3(grid_for(p.batch * p.w * (p.c / 8), 128)), dim3(128), (size_t)(0), s, (const bf16*)p.in, (bf16*)p.out, (int)p.batch, (int)p.h,
+                                                                              (int)p.w, (int)p.c, (float)p.scale));
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }
@@ -441,6 +447,7 @@ int launch_softmax_h(const ddif_softmax_h_t& p, cudaStream_t s) {
 // ---- self-attention core (sr3_dwt.py:347-357): flash-style, one block per (b, head, 64-query tile) ---------
 template <int HD>
 __global__ void attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int ntok, int C, int heads, float scale) {
+  pdl_wait();
   __shared__ float sk[64][HD];
   __shared__ float sv[64][HD];
   const int b = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * 64;
@@ -485,17 +492,98 @@ __global__ void attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out
     for (int d = 0; d < HD; ++d) o[d] = __float2bfloat16(acc[d] * inv);
   }
 }
+// 64-token specialisation (the UNet attends only at the 8x8 level): one block per (b, head), one thread per query.  The
+// token's [q | k | v] head slice is 3*HD contiguous bf16 -> 16-byte loads; K/V live in shared memory as fp32 and are
+// read as broadcast float4; the 64 scores stay in registers (independent dot products, one exp2 per score instead of
+// the online-softmax's two exps and a serial rescale chain per key).
+template <int HD>
+__global__ void __launch_bounds__(64) attn64_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int C, float scale_log2e) {
+  pdl_wait();
+  __shared__ __align__(16) float sk[64][HD];
+  __shared__ __align__(16) float sv[64][HD];
+  const int b = blockIdx.y, head = blockIdx.x, tid = threadIdx.x;
+  const bf16* row = qkv + ((size_t)b * 64 + tid) * (size_t)(3 * C) + head * 3 * HD;
+  float q[HD];
+#pragma unroll
+  for (int c = 0; c < HD / 8; ++c) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(row + c * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[c * 8 + j] = f[j] * scale_log2e;
+    unpack8(*reinterpret_cast<const bf16x8*>(row + HD + c * 8), f);
+    *reinterpret_cast<float4*>(&sk[tid][c * 8]) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(&sk[tid][c * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
+    unpack8(*reinterpret_cast<const bf16x8*>(row + 2 * HD + c * 8), f);
+    *reinterpret_cast<float4*>(&sv[tid][c * 8]) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(&sv[tid][c * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  __syncthreads();
+  float sc[64];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) {
+      const float4 kk = *reinterpret_cast<const float4*>(&sk[j][d]);
+      a0 = fmaf(q[d], kk.x, a0);
+      a1 = fmaf(q[d + 1], kk.y, a1);
+      a2 = fmaf(q[d + 2], kk.z, a2);
+      a3 = fmaf(q[d + 3], kk.w, a3);
+    }
+    sc[j] = (a0 + a1) + (a2 + a3);
+    m = fmaxf(m, sc[j]);
+  }
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    sc[j] = exp2f(sc[j] - m);
+    l += sc[j];
+  }
+  float acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) {
+      const float4 vv = *reinterpret_cast<const float4*>(&sv[j][d]);
+      acc[d] = fmaf(sc[j], vv.x, acc[d]);
+      acc[d + 1] = fmaf(sc[j], vv.y, acc[d + 1]);
+      acc[d + 2] = fmaf(sc[j], vv.z, acc[d + 2]);
+      acc[d + 3] = fmaf(sc[j], vv.w, acc[d + 3]);
+    }
+  }
+  const float inv = 1.0f / l;
+  bf16* o = out + ((size_t)b * 64 + tid) * C + head * HD;
+#pragma unroll
+  for (int c = 0; c < HD / 8; ++c) {
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = acc[c * 8 + j] * inv;
+    *reinterpret_cast<bf16x8*>(o + c * 8) = pack8(f);
+  }
+}
 int launch_attn(const ddif_attn_t& p, cudaStream_t s) {
   if (p.c % p.heads != 0) return DDIF_ERR_SHAPE;
   const int hd = (int)(p.c / p.heads);
+  if (p.ntok == 64 && (hd == 16 || hd == 8) && p.c % 8 == 0) {
+    const float sl2 = (float)(p.scale * 1.4426950408889634);
+    const dim3 g64((unsigned)p.heads, (unsigned)p.batch);
+    if (hd == 16)
+      DDIF_CUDA_CHECK(launch_pdl(attn64_kernel<16>, g64, dim3(64), (size_t)0, s, (const bf16*)p.qkv, (bf16*)p.out, (int)p.c, sl2));
+    else
+      DDIF_CUDA_CHECK(launch_pdl(attn64_kernel<8>, g64, dim3(64), (size_t)0, s, (const bf16*)p.qkv, (bf16*)p.out, (int)p.c, sl2));
+    return DDIF_OK;
+  }
   dim3 grid((unsigned)ceil_div(p.ntok, 64), (unsigned)p.heads, (unsigned)p.batch);
   const bf16* in = (const bf16*)p.qkv;
   bf16* out = (bf16*)p.out;
   switch (hd) {
-    case 8: attn_kernel<8><<<grid, 64, 0, s>>>(in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale); break;
-    case 16: attn_kernel<16><<<grid, 64, 0, s>>>(in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale); break;
-    case 32: attn_kernel<32><<<grid, 64, 0, s>>>(in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale); break;
-    case 64: attn_kernel<64><<<grid, 64, 0, s>>>(in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale); break;
+    case 8: DDIF_CUDA_CHECK(launch_pdl(attn_kernel<8>, dim3(grid), dim3(64), (size_t)(0), s, in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale)); break;
+    case 16: DDIF_CUDA_CHECK(launch_pdl(attn_kernel<16>, dim3(grid), dim3(64), (size_t)(0), s, in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale)); break;
+    case 32: DDIF_CUDA_CHECK(launch_pdl(attn_kernel<32>, dim3(grid), dim3(64), (size_t)(0), s, in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale)); break;
+    case 64: DDIF_CUDA_CHECK(launch_pdl(attn_kernel<64>, dim3(grid), dim3(64), (size_t)(0), s, in, out, (int)p.ntok, (int)p.c, (int)p.heads, (float)p.scale)); break;
     default: return DDIF_ERR_SHAPE;
   }
   DDIF_LAUNCH_CHECK();

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // prologue above overlaps the previous kernel's tail; everything below reads what earlier kernels wrote
 
   int total_iters = 0;
   for (int s = 0; s < p.nseg; ++s) total_iters += p.taps[s] * p.kchunks[s];
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
           ++img_grp;
         }
       }
+      pdl_trigger();  // all loads of this CTA are in flight: the next kernel's CTAs may take over SMs as ours exit
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (converged warp, elected lane issues; see common.cuh) =====================
@@ -428,8 +430,7 @@ int gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   if (L.variant == 1) return conv3_launch(L, stream);
   if (L.variant == 2) return conv3_halo_launch(L, stream);
   const GemmKParams& p = *reinterpret_cast<const GemmKParams*>(L.kparams);
-  conv_igemm_tc_kernel<<<dim3(L.grid_x, L.grid_y), kGemmThreads, L.smem_bytes, stream>>>(p);
-  DDIF_LAUNCH_CHECK();
+  DDIF_CUDA_CHECK(launch_pdl(conv_igemm_tc_kernel, dim3(L.grid_x, L.grid_y), dim3(kGemmThreads), (size_t)L.smem_bytes, stream, p));
   return DDIF_OK;
 }
 

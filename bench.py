@@ -47,7 +47,7 @@ def peaks():
     if os.path.exists(path):
         p = json.load(open(path))
         return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
-    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -218,29 +218,42 @@ def main():
     ms_e2e = timed(True, a.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # roofline of the dominant kernel (conv_igemm_tc_kernel): per-launch CUDA events over one denoise step
+    # roofline of the dominant kernel (conv3x3_halo_tc_kernel: every 3x3 stride-1 conv of the UNet): CUDA events around each
+    # launch of one eager replay of the denoise-step plan, on the stream the kernels are launched on
     roof = None
     if rank == 0:
         pk = peaks()
         rows = rt.sch.fwd.profile(rt.stream)
         rows = rt.sch.fwd.profile(rt.stream)
-        gm = [r for r in rows if r[1] == "ddif_gemm_t"]
-        g_ms, tot_ms = sum(r[2] for r in gm), sum(r[2] for r in rows)
-        import oracle.unet_oracle as uo  # FLOP count of the reference forward (algorithmic work), not on the product path
-        kw2 = dict(kw); kw2.pop("dropout")
-        conv_flops_ref = 8.268e9 * B  # conv FLOPs of one WV3 patch-forward (cond-only part included)
-        executed = sum(r[3] for r in gm)
+        var = rt.sch.fwd.variants()
+        ops = rt.sch.fwd.ops
+        tot_ms = sum(r[2] for r in rows)
+        names = {0: "conv_igemm_tc_kernel", 1: "conv3x3_fused_tc_kernel", 2: "conv3x3_halo_tc_kernel"}
+        per = {}
+        for i, r in enumerate(rows):
+            if var[i] >= 0:
+                d = per.setdefault(names[var[i]], dict(ms=0.0, ref_flops=0.0, executed_flops=0.0, bytes=0.0, launches=0))
+                d["ms"] += r[2]; d["ref_flops"] += ops[i].ref_flops; d["executed_flops"] += r[3]; d["bytes"] += r[4]; d["launches"] += 1
+        dom = max(per, key=lambda k: per[k]["ms"])
+        d = per[dom]
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("conv_igemm_tc_kernel_dram_bytes_per_launch")
-        ach = executed / (g_ms * 1e-3) / 1e12
-        roof = dict(bound="tensor", kernel="conv_igemm_tc_kernel", achieved=ach, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+            traffic = json.load(open(tp)).get(dom + "_dram_bytes_per_launch")
+        ach = d["ref_flops"] / (d["ms"] * 1e-3) / 1e12
+        gemm_ms = sum(v["ms"] for v in per.values())
+        roof = dict(bound="tensor", kernel=dom, achieved=ach, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
                     frac=ach / pk["bf16_tflops_sustained"], traffic=traffic, peak_source=pk["source"] + ":bf16_tflops_sustained",
-                    launches_per_denoise_step=len(gm), avg_launch_ms=g_ms / len(gm), share_of_step=g_ms / tot_ms,
-                    algorithmic_flops_per_step=executed, reference_conv_flops_per_step=conv_flops_ref,
-                    hbm=dict(achieved=sum(r[4] for r in gm) / (g_ms * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s",
-                             frac=sum(r[4] for r in gm) / (g_ms * 1e-3) / 1e9 / pk["hbm_gbs"]),
+                    launches_per_denoise_step=d["launches"], avg_launch_ms=d["ms"] / d["launches"], share_of_step=d["ms"] / tot_ms,
+                    algorithmic_flops_per_launch=d["ref_flops"] / d["launches"], executed_flops_per_launch=d["executed_flops"] / d["launches"],
+                    algorithmic_bytes_per_launch=d["bytes"] / d["launches"],
+                    hbm=dict(achieved=d["bytes"] / (d["ms"] * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s",
+                             frac=d["bytes"] / (d["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"]),
+                    all_conv_kernels=dict(share_of_step=gemm_ms / tot_ms, launches=sum(v["launches"] for v in per.values()),
+                                          achieved=sum(v["ref_flops"] for v in per.values()) / (gemm_ms * 1e-3) / 1e12),
+                    whole_step=dict(reference_flops=8.378e9 * B, ms_graph=ms_dev / a.steps / T,
+                                    achieved=8.378e9 * B / (ms_dev / a.steps / T * 1e-3) / 1e12,
+                                    frac=8.378e9 * B / (ms_dev / a.steps / T * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]),
                     unet_step_ms_events=tot_ms)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

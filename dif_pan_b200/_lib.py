@@ -85,6 +85,7 @@ def load() -> ctypes.CDLL:
     lib.ddif_plan_add.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     lib.ddif_plan_size.argtypes = [ctypes.c_void_p]
     lib.ddif_plan_launches.argtypes = [ctypes.c_void_p]
+    lib.ddif_plan_op_variant.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.ddif_plan_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.ddif_plan_graph_build.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     lib.ddif_plan_graph_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p]

@@ -175,6 +175,12 @@ int ddif_plan_add(ddif_plan_t* plan, int kind, const void* params) {
   return (int)plan->ops.size() - 1;
 }
 
+int ddif_plan_op_variant(const ddif_plan_t* plan, int index) {
+  if (!plan || index < 0 || index >= (int)plan->ops.size()) return DDIF_ERR_ARG;
+  const ddif::Op& op = plan->ops[index];
+  return op.kind == DDIF_OP_GEMM && op.gemm ? op.gemm->variant : -1;
+}
+
 int ddif_plan_size(const ddif_plan_t* plan) { return plan ? (int)plan->ops.size() : DDIF_ERR_ARG; }
 int ddif_plan_launches(const ddif_plan_t* plan) { return plan ? (int)plan->ops.size() : DDIF_ERR_ARG; }
 

@@ -67,22 +67,43 @@ __global__ void time_embed_kernel(ddif_time_embed_t p) {
     enc[i] = i < count ? sinf(e) : cosf(e);
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < hid; j += blockDim.x) {
-    float a = p.b1[j];
-    for (int k = 0; k < inner; ++k) a += p.w1[j * inner + k] * enc[k];
-    h[j] = a / (1.0f + expf(-a));
+  // warp-cooperative mat-vecs: a warp reads one weight row with coalesced loads (lanes split K) and reduces by shuffles;
+  // thread-per-row reads touched 32 cache lines per load instruction (97 us for 73 k MACs per sample).
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < hid; j += nwarps) {
+    float a = 0.f;
+    for (int k = lane; k < inner; k += 32) a = fmaf(p.w1[j * inner + k], enc[k], a);
+    a = warp_sum(a) + p.b1[j];
+    if (lane == 0) h[j] = a / (1.0f + expf(-a));
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < inner; j += blockDim.x) {
-    float a = p.b2[j];
-    for (int k = 0; k < hid; ++k) a += p.w2[j * hid + k] * h[k];
-    te[j] = a;
+  for (int j = warp; j < inner; j += nwarps) {
+    float a = 0.f;
+    for (int k = lane; k < hid; k += 32) a = fmaf(p.w2[j * hid + k], h[k], a);
+    a = warp_sum(a) + p.b2[j];
+    if (lane == 0) te[j] = a;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < (int)p.nfilm; j += blockDim.x) {
-    float a = p.bf[j];
-    for (int k = 0; k < inner; ++k) a += p.wf[(size_t)j * inner + k] * te[k];
-    p.film[(size_t)b * p.nfilm + j] = a;
+  if (inner == 32) {
+    const float tk = te[lane];
+    float* dst = p.film + (size_t)b * p.nfilm;
+    for (int j0 = warp * 4; j0 < (int)p.nfilm; j0 += nwarps * 4) {  // 4 independent rows per iteration (nfilm % 4 == 0 for the UNet)
+      float a[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = (j0 + r < (int)p.nfilm) ? p.wf[(size_t)(j0 + r) * 32 + lane] * tk : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
+      if (lane < 4 && j0 + lane < (int)p.nfilm) dst[j0 + lane] = (lane == 0 ? a[0] : lane == 1 ? a[1] : lane == 2 ? a[2] : a[3]) + p.bf[j0 + lane];
+    }
+  } else {
+    for (int j = warp; j < (int)p.nfilm; j += nwarps) {
+      float a = 0.f;
+      for (int k = lane; k < inner; k += 32) a = fmaf(p.wf[(size_t)j * inner + k], te[k], a);
+      a = warp_sum(a) + p.bf[j];
+      if (lane == 0) p.film[(size_t)b * p.nfilm + j] = a;
+    }
   }
 }
 int launch_time_embed(const ddif_time_embed_t& p, cudaStream_t s) {

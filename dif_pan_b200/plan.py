@@ -39,6 +39,7 @@ class SymOp:
     label: str = ""
     flops: float = 0.0
     bytes: float = 0.0
+    ref_flops: float = -1.0  # FLOPs of the reference ops this launch replaces (== flops unless the launch restructures them)
 
 
 def _round_up(x: int, a: int) -> int:
@@ -92,7 +93,8 @@ class PlanBuilder:
         return tensor.data_ptr()
 
     # -- ops ----------------------------------------------------------------------------------------------
-    def add(self, struct: str, kind: Optional[str] = None, label: str = "", flops: float = 0.0, traffic: float = 0.0, **fields) -> int:
+    def add(self, struct: str, kind: Optional[str] = None, label: str = "", flops: float = 0.0, traffic: float = 0.0, ref_flops: float = -1.0,
+            **fields) -> int:
         idx = len(self.ops)
 
         def visit(v):
@@ -106,7 +108,7 @@ class PlanBuilder:
 
         for v in fields.values():
             visit(v)
-        self.ops.append(SymOp(struct, fields, kind, label, flops, traffic))
+        self.ops.append(SymOp(struct, fields, kind, label, flops, traffic, flops if ref_flops < 0 else ref_flops))
         return idx
 
     def layout(self) -> int:
@@ -156,6 +158,11 @@ class PlanBuilder:
         kinds = (ctypes.c_int * n)()
         _lib.check(_lib.load().ddif_plan_profile(self.handle, ctypes.c_void_p(stream), ms, kinds, n), "ddif_plan_profile")
         return [(op.label, op.struct, float(ms[i]), op.flops, op.bytes) for i, op in enumerate(self.ops)]
+
+    def variants(self) -> List[int]:
+        """Kernel variant of every op (GEMM ops: 0 generic TMA, 1 fused LDG 3x3, 2 halo 3x3; others -1)."""
+        lib = _lib.load()
+        return [int(lib.ddif_plan_op_variant(self.handle, i)) for i in range(len(self.ops))]
 
     def __len__(self) -> int:
         return len(self.ops)

@@ -375,7 +375,7 @@ class Schedule:
 
     def _gemm(self, pb, label, srcs, weights, n_valid, out: Optional[Act], *, taps, stride=1, bias=None, film=None,
               film_ld=0, mod=None, residual: Optional[Act] = None, act=0, out_nchw=None, per_sample=(0, 0), w_s=None, out_hw=None,
-              gn=None, a_up=0, w_k=None):
+              gn=None, a_up=0, w_k=None, ref_flops=-1.0):
         """gn = (gamma_addr, beta_addr, act): fuse GroupNorm(+Swish) of the (single) source into the conv's loader, using the
         source's own statistics; a_up = 1: read the source through a nearest x2 up-sampling."""
         a0 = srcs[0]
@@ -405,7 +405,7 @@ class Schedule:
             nbytes += m * n_valid * 2
         if mod is not None:
             nbytes += m * n_valid * 4
-        return pb.add("ddif_gemm_t", label=label, flops=2.0 * m * n_valid * k_total, traffic=nbytes, **fields)
+        return pb.add("ddif_gemm_t", label=label, flops=2.0 * m * n_valid * k_total, traffic=nbytes, ref_flops=ref_flops, **fields)
 
     def _gn(self, pb, label, src: Act, gamma, beta, act, src2: Optional[Act] = None, dw_w=None, name="gn"):
         C = src.C + (src2.C if src2 else 0)
@@ -587,7 +587,8 @@ class Schedule:
                 # GroupNorm fused into its loader; x_hat itself is only needed by attn_res below
                 xh, _ = self._gn(pb, q + ".prenorm", x, A[q + ".gamma"], A[q + ".beta"], 0, src2=skip, name=q + ".xh")
                 self._gemm(pb, q + ".qconv", [x, skip], [A[q + ".qc.w"], A[q + ".qc.w"] + 2 * x.C], dim, qt, taps=[9, 9], bias=A[q + ".q1.b"],
-                           gn=(A[q + ".gamma"], A[q + ".beta"], 0), w_k=[dim, dim])
+                           gn=(A[q + ".gamma"], A[q + ".beta"], 0), w_k=[dim, dim],
+                           ref_flops=2.0 * B * x.H * x.W * dim * (9 + dim))  # reference: depthwise 3x3 + 1x1
             else:
                 xh, xdw = self._gn(pb, q + ".prenorm+dw", x, A[q + ".gamma"], A[q + ".beta"], 0, src2=skip, dw_w=A[q + ".q0"], name=q + ".xh")
                 self._gemm(pb, q + ".q1", [xdw], [A[q + ".q1.w"]], dim, qt, taps=[1], bias=A[q + ".q1.b"])
@@ -604,7 +605,8 @@ class Schedule:
             f1 = self._act(pb, q + ".f1", B, x.H, x.W, 2 * o)
             self._gemm(pb, q + ".ffn0", [y], [A[q + ".ffn0.w"]], 2 * o, f1, taps=[9], act=1)
             z = self._act(pb, q + ".z", B, x.H, x.W, o, stats=True)
-            self._gemm(pb, q + ".ffn23", [f1], [A[q + ".ffn23.w"]], o, z, taps=[9], bias=A[q + ".ffn23.b"], residual=y)
+            self._gemm(pb, q + ".ffn23", [f1], [A[q + ".ffn23.w"]], o, z, taps=[9], bias=A[q + ".ffn23.b"], residual=y,
+                       ref_flops=2.0 * B * x.H * x.W * o * (2 * o * 9 + o))  # reference: ffn.2 (3x3, 2o -> o) + ffn.3 (1x1)
             x = self._res_block(z, p + ".res_block")
             if m.with_attn:
                 x = self._attention(x, p + ".attn")

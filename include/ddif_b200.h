@@ -177,6 +177,9 @@ void ddif_plan_destroy(ddif_plan_t* plan);
 /* Record an op (parameters are copied; GEMM tensor maps are encoded once here). Returns op index or <0. */
 int ddif_plan_add(ddif_plan_t* plan, int kind, const void* params);
 int ddif_plan_size(const ddif_plan_t* plan);
+/* Which kernel a recorded DDIF_OP_GEMM resolved to: 0 conv_igemm_tc_kernel, 1 conv3x3_fused_tc_kernel,
+ * 2 conv3x3_halo_tc_kernel; -1 for every other op kind (used by bench.py to attribute time per kernel). */
+int ddif_plan_op_variant(const ddif_plan_t* plan, int index);
 /* Enqueue ops [first, last) on `stream` (last<0 = all). */
 int ddif_plan_run(ddif_plan_t* plan, int first, int last, ddif_stream_t stream);
 /* Capture the whole plan into a CUDA graph once, then replay it. */

@@ -68,20 +68,20 @@ def test_packed_weights_layout():
 def test_schedule_structure(dataset, B, H, W):
     net, P, s = _schedule(dataset, B, H, W)
     kinds = [op.struct for op in s.fwd.ops]
-    # 12 enc x (x_conv, 2 conv) + 16 dec x (q1, attn, ffn0, ffn23, 2 conv) + mid 2x2 + 8 attn x 2 + conv0 + 3 down + 3 up + final
+    # 12 enc x (x_conv, 2 conv) + 16 dec x (q1 | qconv, attn, ffn0, ffn23, 2 conv) + mid 2x2 + 8 attn x 2 + conv0 + 3 down + 3 up + final
     assert kinds.count("ddif_gemm_t") == 12 * 3 + 16 * 6 + 4 + 8 * 2 + 1 + 3 + 3 + 1
     assert kinds.count("ddif_attn_t") == 8
     assert kinds.count("ddif_softmax_h_t") == 16
-    # GroupNorm+Swish of the 3x3 convs is fused into the conv loader except at the 8-pixel-wide level (9 resblocks);
-    # stand-alone launches left: 8 attention norms + 16 FWM prenorm(+dw) + 9 x 2
-    assert kinds.count("ddif_gn_apply_t") == 8 + 16 + 9 * 2
+    # GroupNorm+Swish of every 3x3 conv is fused into the conv's loader (all 30 resblocks x 2 + final conv);
+    # stand-alone normalisation launches left: 8 attention norms + 16 FWM prenorm(+dw)
+    assert kinds.count("ddif_gn_apply_t") == 8 + 16
     assert kinds.count("ddif_upsample2x_t") == 0  # nearest x2 folded into the following conv
     fused = [op for op in s.fwd.ops if op.struct == "ddif_gemm_t" and op.fields.get("gn_stats") is not None]
-    # 21 resblocks x 2 + final conv, + the FWM q path (prenorm -> DW3x3 -> 1x1 composed into one 3x3 conv with the
+    # 30 resblocks x 2 + final conv, + the FWM q path (prenorm -> DW3x3 -> 1x1 composed into one 3x3 conv with the
     # GroupNorm in its loader) of every decoder block with H >= 16, W >= 8, dim <= 192
     qconv = [op for op in fused if op.label.endswith(".qconv")]
     assert len(qconv) == (13 if (H, W) == (128, 64) else 12)
-    assert len(fused) - len(qconv) == 21 * 2 + 1
+    assert len(fused) - len(qconv) == 30 * 2 + 1
     assert len(s.mod) == 12 and len(s.weff) == 16
     flops = sum(op.flops for op in s.fwd.ops) + sum(op.flops for op in s.cnd.ops)
     assert flops > 0

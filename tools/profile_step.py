@@ -78,7 +78,7 @@ def main():
     rows = rt.sch.fwd.profile(rt.stream)
     rows = rt.sch.fwd.profile(rt.stream)
     cats = {}
-    for label, struct, ms, fl, by in rows:
+    for label, struct, ms, fl, by in rows:  # noqa
         c = cats.setdefault(category(label, struct), dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
         c["ms"] += ms; c["flops"] += fl; c["bytes"] += by; c["n"] += 1
     tot = sum(c["ms"] for c in cats.values())

@@ -87,15 +87,19 @@ __global__ void time_embed_kernel(ddif_time_embed_t p) {
   if (inner == 32) {
     const float tk = te[lane];
     float* dst = p.film + (size_t)b * p.nfilm;
-    for (int j0 = warp * 4; j0 < (int)p.nfilm; j0 += nwarps * 4) {  // 4 independent rows per iteration (nfilm % 4 == 0 for the UNet)
-      float a[4];
+    constexpr int R = 8;  // independent rows per warp iteration: 8 L2 loads in flight per lane (the loop is latency-bound)
+    for (int j0 = warp * R; j0 < (int)p.nfilm; j0 += nwarps * R) {
+      float a[R];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) a[r] = (j0 + r < (int)p.nfilm) ? p.wf[(size_t)(j0 + r) * 32 + lane] * tk : 0.f;
+      for (int r = 0; r < R; ++r) a[r] = (j0 + r < (int)p.nfilm) ? __ldg(p.wf + (size_t)(j0 + r) * 32 + lane) * tk : 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
-      if (lane < 4 && j0 + lane < (int)p.nfilm) dst[j0 + lane] = (lane == 0 ? a[0] : lane == 1 ? a[1] : lane == 2 ? a[2] : a[3]) + p.bf[j0 + lane];
+        for (int r = 0; r < R; ++r) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
+      float mine = a[0];
+#pragma unroll
+      for (int r = 1; r < R; ++r) mine = lane == r ? a[r] : mine;
+      if (lane < R && j0 + lane < (int)p.nfilm) dst[j0 + lane] = mine + __ldg(p.bf + j0 + lane);
     }
   } else {
     for (int j = warp; j < (int)p.nfilm; j += nwarps) {
@@ -108,7 +112,7 @@ __global__ void time_embed_kernel(ddif_time_embed_t p) {
 }
 int launch_time_embed(const ddif_time_embed_t& p, cudaStream_t s) {
   if (p.inner % 2 != 0 || p.inner > 256) return DDIF_ERR_SHAPE;
-  DDIF_CUDA_CHECK(launch_pdl(time_embed_kernel, dim3((int)p.batch), dim3(256), (size_t)((size_t)(6 * p.inner) * sizeof(float)), s, p));
+  DDIF_CUDA_CHECK(launch_pdl(time_embed_kernel, dim3((int)p.batch), dim3(1024), (size_t)((size_t)(6 * p.inner) * sizeof(float)), s, p));
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }
@@ -371,22 +375,23 @@ int launch_gn_apply(const ddif_gn_apply_t& p, cudaStream_t s) {
 }
 
 // ---- q.softmax(dim=-2) * scale   (sr3_dwt.py:545, 561): softmax over H for every (b, x, channel) ---------
-__global__ void softmax_h_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C, float scale) {
+__global__ void softmax_h_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C, int ld, float scale) {
   pdl_wait();
   const int nchunk = C >> 3;
   const int64_t items = (int64_t)B * W * nchunk;
-  const size_t row = (size_t)W * C;
+  const size_t row = (size_t)W * C, row_in = (size_t)W * ld;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / ((int64_t)W * nchunk));
-    const int r = (int)(i - (int64_t)b * W * nchunk);  // (x, chunk) linear == offset/8 inside a row
-    const bf16* src = in + (size_t)b * H * row + (size_t)r * 8;
+    const int r = (int)(i - (int64_t)b * W * nchunk);  // (x, chunk) linear == offset/8 inside a dense row
+    const int x = r / nchunk, ch = r - x * nchunk;
+    const bf16* src = in + (size_t)b * H * row_in + (size_t)x * ld + (size_t)ch * 8;
     bf16* dst = out + (size_t)b * H * row + (size_t)r * 8;
     float m[8], l[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; l[j] = 0.f; }
     for (int y = 0; y < H; ++y) {
       float v[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(src + (size_t)y * row), v);
+      unpack8(*reinterpret_cast<const bf16x8*>(src + (size_t)y * row_in), v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float mn = fmaxf(m[j], v[j]);
@@ -398,7 +403,7 @@ __global__ void softmax_h_kernel(const bf16* __restrict__ in, bf16* __restrict__
     for (int j = 0; j < 8; ++j) l[j] = scale / l[j];
     for (int y = 0; y < H; ++y) {
       float v[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(src + (size_t)y * row), v);
+      unpack8(*reinterpret_cast<const bf16x8*>(src + (size_t)y * row_in), v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = __expf(v[j] - m[j]) * l[j];
       *reinterpret_cast<bf16x8*>(dst + (size_t)y * row) = pack8(v);
@@ -410,17 +415,19 @@ __global__ void softmax_h_kernel(const bf16* __restrict__ in, bf16* __restrict__
 // makes ONE pass over HBM: 4 B/element instead of 6, one exp per element instead of three.
 template <int H>
 __global__ void __launch_bounds__(128) softmax_h_reg_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t items,
-                                                            int row_words, float scale) {
+                                                            int W, int cw, int ldw, float scale) {
   pdl_wait();
   constexpr float kLog2e = 1.4426950408889634f;
+  const int row_out = W * cw, row_in = W * ldw;  // words per image row (cw = c/2 output words, ldw = in_ld/2 input words per pixel)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / row_words;
-    const int r = (int)(i - b * row_words);
-    const uint32_t* src = in + (size_t)b * H * row_words + r;
-    uint32_t* dst = out + (size_t)b * H * row_words + r;
+    const int64_t b = i / row_out;
+    const int r = (int)(i - b * row_out);
+    const int x = r / cw, c = r - x * cw;
+    const uint32_t* src = in + (size_t)b * H * row_in + (size_t)x * ldw + c;
+    uint32_t* dst = out + (size_t)b * H * row_out + r;
     uint32_t w[H];
 #pragma unroll
-    for (int y = 0; y < H; ++y) w[y] = __ldg(src + (size_t)y * row_words);
+    for (int y = 0; y < H; ++y) w[y] = __ldg(src + (size_t)y * row_in);
     float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
     for (int y = 0; y < H; ++y) {
@@ -441,27 +448,26 @@ __global__ void __launch_bounds__(128) softmax_h_reg_kernel(const uint32_t* __re
 #pragma unroll
     for (int y = 0; y < H; ++y) {
       const __nv_bfloat162 t = __floats2bfloat162_rn(e0[y] * r0, e1[y] * r1);
-      dst[(size_t)y * row_words] = *reinterpret_cast<const uint32_t*>(&t);
+      dst[(size_t)y * row_out] = *reinterpret_cast<const uint32_t*>(&t);
     }
   }
 }
 template <int H>
 static int launch_softmax_h_reg(const ddif_softmax_h_t& p, cudaStream_t s) {
-  const int row_words = (int)(p.w * p.c / 2);
-  const int64_t items = p.batch * (int64_t)row_words;
-  DDIF_CUDA_CHECK(launch_pdl(softmax_h_reg_kernel<H>, dim3(grid_for(items, 128, 148 * 24)), dim3(128), (size_t)(0), s, (const uint32_t*)p.in, (uint32_t*)p.out, items, row_words, (float)p.scale));
-  DDIF_LAUNCH_CHECK();
+  const int ld = (int)(p.in_ld ? p.in_ld : p.c);
+  const int64_t items = p.batch * p.w * (p.c / 2);
+  DDIF_CUDA_CHECK(launch_pdl(softmax_h_reg_kernel<H>, dim3(grid_for(items, 128, 148 * 24)), dim3(128), (size_t)0, s, (const uint32_t*)p.in,
+                             (uint32_t*)p.out, items, (int)p.w, (int)(p.c / 2), ld / 2, (float)p.scale));
   return DDIF_OK;
 }
 int launch_softmax_h(const ddif_softmax_h_t& p, cudaStream_t s) {
-  if (p.c % 8 != 0) return DDIF_ERR_SHAPE;
+  if (p.c % 8 != 0 || p.in_ld % 8 != 0 || (p.in_ld && p.in_ld < p.c)) return DDIF_ERR_SHAPE;
   if (p.h == 64) return launch_softmax_h_reg<64>(p, s);
   if (p.h == 32) return launch_softmax_h_reg<32>(p, s);
   if (p.h == 16) return launch_softmax_h_reg<16>(p, s);
   if (p.h == 8) return launch_softmax_h_reg<8>(p, s);
-  DDIF_CUDA_CHECK(launch_pdl(softmax_h_kernel, dim3(grid_for(p.batch * p.w * (p.c / 8), 128)), dim3(128), (size_t)(0), s, (const bf16*)p.in, (bf16*)p.out, (int)p.batch, (int)p.h,
-                                                                              (int)p.w, (int)p.c, (float)p.scale));
-  DDIF_LAUNCH_CHECK();
+  DDIF_CUDA_CHECK(launch_pdl(softmax_h_kernel, dim3(grid_for(p.batch * p.w * (p.c / 8), 128)), dim3(128), (size_t)0, s, (const bf16*)p.in, (bf16*)p.out,
+                             (int)p.batch, (int)p.h, (int)p.w, (int)p.c, (int)(p.in_ld ? p.in_ld : p.c), (float)p.scale));
   return DDIF_OK;
 }
 

@@ -301,6 +301,15 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], net: "UNetSR3") -> Dict[str, to
                 P[q + ".qc.w"] = _pack_conv(torch.einsum("oc,ckl->ockl", sd[q + ".q.1.weight"].to(torch.float32)[:, :, 0, 0],
                                                           sd[q + ".q.0.weight"].to(torch.float32)[:, 0]))
                 P[q + ".q1.b"] = f32(sd[q + ".q.1.bias"])
+                if (q + ".attn_res.weight") in sd:
+                    # [q ; attn_res] as ONE 3x3 conv over x_hat: rows dim.. hold attn_res (1x1 = centre tap only), so the
+                    # q-path kernel also emits r = attn_res(x_hat) and x_hat itself never goes through HBM (sr3_dwt.py:573)
+                    o_ = sd[q + ".attn_res.weight"].shape[0]
+                    wq = torch.einsum("oc,ckl->ockl", sd[q + ".q.1.weight"].to(torch.float32)[:, :, 0, 0], sd[q + ".q.0.weight"].to(torch.float32)[:, 0])
+                    wr = torch.zeros(o_, dim, 3, 3, dtype=torch.float32, device=wq.device)
+                    wr[:, :, 1, 1] = sd[q + ".attn_res.weight"].to(torch.float32)[:, :, 0, 0]
+                    P[q + ".qcr.w"] = _pack_conv(torch.cat([wq, wr], 0))
+                    P[q + ".qcr.b"] = f32(torch.cat([sd[q + ".q.1.bias"].to(torch.float32), torch.zeros(o_, dtype=torch.float32, device=wq.device)]))
                 cd = sd[q + ".kv.0.weight"].shape[0]
                 P[q + ".kv0"] = f32(sd[q + ".kv.0.weight"].reshape(cd, 9))
                 P[q + ".kv1.w"] = f32(sd[q + ".kv.1.weight"].reshape(2 * dim, cd))
@@ -375,7 +384,7 @@ class Schedule:
 
     def _gemm(self, pb, label, srcs, weights, n_valid, out: Optional[Act], *, taps, stride=1, bias=None, film=None,
               film_ld=0, mod=None, residual: Optional[Act] = None, act=0, out_nchw=None, per_sample=(0, 0), w_s=None, out_hw=None,
-              gn=None, a_up=0, w_k=None, ref_flops=-1.0):
+              gn=None, a_up=0, w_k=None, ref_flops=-1.0, residual_off=0):
         """gn = (gamma_addr, beta_addr, act): fuse GroupNorm(+Swish) of the (single) source into the conv's loader, using the
         source's own statistics; a_up = 1: read the source through a nearest x2 up-sampling."""
         a0 = srcs[0]
@@ -391,7 +400,8 @@ class Schedule:
             w_k=(list(w_k) if w_k else [s.C for s in srcs]) + [0] * (2 - nseg), taps=list(taps) + [0] * (2 - nseg),
             w_per_sample=list(per_sample)[:nseg] + [0] * (2 - nseg), nseg=nseg, stride=stride, batch=a0.B, out_h=oh, out_w=ow,
             n_pad=n_pad, n_valid=n_valid, bias=bias, film=film, film_ld=film_ld, mod=mod,
-            residual=residual.buf if residual else None, res_ld=residual.C if residual else 0, act=act,
+            residual=((residual.buf, residual_off * 2) if residual_off else residual.buf) if residual else None,
+            res_ld=residual.C if residual else 0, act=act,
             out=out.buf if out else None, out_ld=out.C if out else 0, out_nchw=out_nchw,
             stats=out.stats if (out is not None and out.stats is not None) else None,
             gn_stats=a0.stats if gn else None, gn_gamma=gn[0] if gn else None, gn_beta=gn[1] if gn else None, gn_eps=1e-5,
@@ -581,27 +591,41 @@ class Schedule:
             q = p + ".cond_inj"
             dim, o = m.dim, m.dim_out
             assert dim == x.C + skip.C, (p, dim, x.C, skip.C)
-            qt = self._act(pb, q + ".q", B, x.H, x.W, dim)
-            if x.H >= 16 and x.W >= 8 and dim <= 192 and self.use_qconv:
-                # prenorm_x -> DW3x3 -> Conv1x1 as ONE tensor-core 3x3 conv over the virtual concat (x, skip) with the
-                # GroupNorm fused into its loader; x_hat itself is only needed by attn_res below
-                xh, _ = self._gn(pb, q + ".prenorm", x, A[q + ".gamma"], A[q + ".beta"], 0, src2=skip, name=q + ".xh")
-                self._gemm(pb, q + ".qconv", [x, skip], [A[q + ".qc.w"], A[q + ".qc.w"] + 2 * x.C], dim, qt, taps=[9, 9], bias=A[q + ".q1.b"],
+            has_res = (q + ".attn_res.w") in A
+            qconv = x.H >= 16 and x.W >= 8 and dim <= 192 and self.use_qconv
+            if qconv and has_res and dim + o <= 192:
+                # prenorm_x -> [DW3x3 -> Conv1x1 | attn_res] as ONE tensor-core 3x3 conv over the virtual concat (x, skip) with
+                # the GroupNorm fused into its loader: channels [0, dim) = q, [dim, dim + o) = r = attn_res(x_hat)
+                qr = self._act(pb, q + ".qr", B, x.H, x.W, dim + o)
+                self._gemm(pb, q + ".qconv", [x, skip], [A[q + ".qcr.w"], A[q + ".qcr.w"] + 2 * x.C], dim + o, qr, taps=[9, 9], bias=A[q + ".qcr.b"],
                            gn=(A[q + ".gamma"], A[q + ".beta"], 0), w_k=[dim, dim],
-                           ref_flops=2.0 * B * x.H * x.W * dim * (9 + dim))  # reference: depthwise 3x3 + 1x1
+                           ref_flops=2.0 * B * x.H * x.W * dim * (9 + dim + o))  # reference: depthwise 3x3 + 1x1 (q) + 1x1 (attn_res)
+                qs = self._act(pb, q + ".qs", B, x.H, x.W, dim)
+                pb.add("ddif_softmax_h_t", label=q + ".softmax_h", traffic=B * x.H * x.W * dim * 4, **{"in": qr.buf}, out=qs.buf, batch=B,
+                       h=x.H, w=x.W, c=dim, scale=1.0, in_ld=dim + o)
+                y = self._act(pb, q + ".y", B, x.H, x.W, o)
+                self._gemm(pb, q + ".attn_out", [qs], [("cache", self.weff[p])], o, y, taps=[1], bias=A[q + ".attn.b"], per_sample=(1,), w_s=[B],
+                           residual=qr, residual_off=dim, ref_flops=2.0 * B * x.H * x.W * o * dim)
             else:
-                xh, xdw = self._gn(pb, q + ".prenorm+dw", x, A[q + ".gamma"], A[q + ".beta"], 0, src2=skip, dw_w=A[q + ".q0"], name=q + ".xh")
-                self._gemm(pb, q + ".q1", [xdw], [A[q + ".q1.w"]], dim, qt, taps=[1], bias=A[q + ".q1.b"])
-            qs = self._act(pb, q + ".qs", B, x.H, x.W, dim)
-            pb.add("ddif_softmax_h_t", label=q + ".softmax_h", traffic=B * x.H * x.W * dim * 6, **{"in": qt.buf}, out=qs.buf, batch=B,
-                   h=x.H, w=x.W, c=dim, scale=1.0)
-            y = self._act(pb, q + ".y", B, x.H, x.W, o)
-            weff = ("cache", self.weff[p])
-            if (q + ".attn_res.w") in A:
-                self._gemm(pb, q + ".attn_out+res", [qs, xh], [weff, A[q + ".attn_res.w"]], o, y, taps=[1, 1], bias=A[q + ".attn.b"],
-                           per_sample=(1, 0), w_s=[B, 1])
-            else:
-                self._gemm(pb, q + ".attn_out", [qs], [weff], o, y, taps=[1], bias=A[q + ".attn.b"], per_sample=(1,), w_s=[B], residual=xh)
+                qt = self._act(pb, q + ".q", B, x.H, x.W, dim)
+                if qconv:
+                    xh, _ = self._gn(pb, q + ".prenorm", x, A[q + ".gamma"], A[q + ".beta"], 0, src2=skip, name=q + ".xh")
+                    self._gemm(pb, q + ".qconv", [x, skip], [A[q + ".qc.w"], A[q + ".qc.w"] + 2 * x.C], dim, qt, taps=[9, 9], bias=A[q + ".q1.b"],
+                               gn=(A[q + ".gamma"], A[q + ".beta"], 0), w_k=[dim, dim],
+                               ref_flops=2.0 * B * x.H * x.W * dim * (9 + dim))  # reference: depthwise 3x3 + 1x1
+                else:
+                    xh, xdw = self._gn(pb, q + ".prenorm+dw", x, A[q + ".gamma"], A[q + ".beta"], 0, src2=skip, dw_w=A[q + ".q0"], name=q + ".xh")
+                    self._gemm(pb, q + ".q1", [xdw], [A[q + ".q1.w"]], dim, qt, taps=[1], bias=A[q + ".q1.b"])
+                qs = self._act(pb, q + ".qs", B, x.H, x.W, dim)
+                pb.add("ddif_softmax_h_t", label=q + ".softmax_h", traffic=B * x.H * x.W * dim * 4, **{"in": qt.buf}, out=qs.buf, batch=B,
+                       h=x.H, w=x.W, c=dim, scale=1.0, in_ld=0)
+                y = self._act(pb, q + ".y", B, x.H, x.W, o)
+                weff = ("cache", self.weff[p])
+                if has_res:
+                    self._gemm(pb, q + ".attn_out+res", [qs, xh], [weff, A[q + ".attn_res.w"]], o, y, taps=[1, 1], bias=A[q + ".attn.b"],
+                               per_sample=(1, 0), w_s=[B, 1])
+                else:
+                    self._gemm(pb, q + ".attn_out", [qs], [weff], o, y, taps=[1], bias=A[q + ".attn.b"], per_sample=(1,), w_s=[B], residual=xh)
             f1 = self._act(pb, q + ".f1", B, x.H, x.W, 2 * o)
             self._gemm(pb, q + ".ffn0", [y], [A[q + ".ffn0.w"]], 2 * o, f1, taps=[9], act=1)
             z = self._act(pb, q + ".z", B, x.H, x.W, o, stats=True)

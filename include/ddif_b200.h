@@ -104,7 +104,8 @@ typedef struct {
   int64_t batch, h, w, act; double eps;
 } ddif_gn_apply_t;
 
-typedef struct { const void* in; void* out; int64_t batch, h, w, c; double scale; } ddif_softmax_h_t;
+/* in: [B, h, w, in_ld] (first c channels of every pixel; in_ld = 0 means c), out: [B, h, w, c] */
+typedef struct { const void* in; void* out; int64_t batch, h, w, c; double scale; int64_t in_ld; } ddif_softmax_h_t;
 /* qkv: [B, ntok, 3*C] with per-head channel blocks [q(hd) k(hd) v(hd)]; out: [B, ntok, C] */
 typedef struct { const void* qkv; void* out; int64_t batch, ntok, c, heads; double scale; } ddif_attn_t;
 typedef struct { const void* in; void* out; int64_t batch, h, w, c; } ddif_upsample2x_t;

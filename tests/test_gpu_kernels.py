@@ -102,6 +102,14 @@ def test_softmax_h_and_attention():
     _lib.launch("ddif_softmax_h_t", stream(), **{"in": q.data_ptr()}, out=out.data_ptr(), batch=B, h=H, w=W, c=C, scale=0.25)
     ref = to_nchw_f32(q).softmax(dim=-2) * 0.25
     assert rel_err(to_nchw_f32(out), ref) < 4e-3
+    # every register-resident height (one pass, H values per thread), the generic two-pass kernel (H = 24), and a pitched input
+    # (the first c channels of a wider tensor: q inside the [q | attn_res(x_hat)] output of the FWM q conv)
+    for H2, W2, C2, ld in ((64, 16, 64, 0), (32, 8, 96, 0), (8, 8, 256, 0), (24, 8, 64, 0), (24, 8, 64, 96), (64, 16, 64, 96), (16, 8, 128, 192)):
+        wide = nhwc_bf16(_rand(B, ld or C2, H2, W2, seed=12, scale=3.0))
+        out2 = torch.zeros(B, H2, W2, C2, dtype=torch.bfloat16, device=DEV)
+        _lib.launch("ddif_softmax_h_t", stream(), **{"in": wide.data_ptr()}, out=out2.data_ptr(), batch=B, h=H2, w=W2, c=C2, scale=0.5, in_ld=ld)
+        ref2 = to_nchw_f32(wide)[:, :C2].softmax(dim=-2) * 0.5
+        assert rel_err(to_nchw_f32(out2), ref2) < 4e-3, (H2, W2, C2, ld)
     for ntok_hw, Cc in (((8, 8), 128), ((12, 8), 64)):
         h, w = ntok_hw
         qkv = nhwc_bf16(_rand(B, 3 * Cc, h, w, seed=10))

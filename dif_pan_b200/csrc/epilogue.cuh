@@ -189,7 +189,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& e, EpiPrefetch& p
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar);
     }
+#ifndef DDIF_VAR_G_NO_EPI
     process(r, cc);
+#endif
   }
   if (e.stats && active) {
     // all rows of one warp belong to one sample

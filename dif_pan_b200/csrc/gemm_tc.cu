@@ -41,7 +41,9 @@ struct alignas(64) GemmKParams {
   uint32_t idesc;
   uint32_t layout_type;
   uint32_t tmem_cols;      // `groups` accumulators of bn columns, rounded to a power of two >= 32
-  int groups;              // TMEM accumulators = epilogue warp groups working on different tiles (2 or 4)
+  int groups;              // epilogue warp groups working on different tiles (generic: 2 or 4; lean: 1)
+  int naccs;               // TMEM accumulators (generic: = groups; lean: 2)
+  int lean;                // kLean* flags of the compile-time epilogue, 0 = generic
   const float* bias;
   const float* film;
   int film_ld;
@@ -61,6 +63,21 @@ static constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MM
 // Persistent, warp-specialised: each CTA owns one N tile (blockIdx.y) and walks M tiles blockIdx.x, +gridDim.x, ...
 // Three pipelines: smem full/empty ring (TMA <-> MMA) running ACROSS tiles, TMEM full/empty (MMA <-> epilogue, two
 // accumulators so tile i's epilogue overlaps tile i+1's MMAs), and the static tile walk.
+// F = 0: generic run-time epilogue (epilogue.cuh), tile groups.  F & 1: lean epilogue for N <= 64 with 32-byte aligned rows --
+// compile-time operand set (kLeanMod / kLeanRes / kLeanStats), one 16-channel chunk per thread, all 16 warps on one tile, and
+// the NEXT tile's residual / modulation vectors requested before the current tile is processed (the generic path exposed
+// one L2/DRAM round trip per tile and chunk: 80 us instead of 30 for the 64x64-level 1x1 convs,
+// profiles/r01s4_gemm1x1_ablation.txt).
+enum : int { kLean = 1, kLeanMod = 2, kLeanRes = 4, kLeanStats = 8 };
+
+template <int F>
+struct LeanOperands {
+  uint32_t res[(F & kLeanRes) ? 8 : 1];
+  uint32_t sc[(F & kLeanMod) ? 8 : 1];
+  uint32_t sh[(F & kLeanMod) ? 8 : 1];
+};
+
+template <int F>
 __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -94,9 +111,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
         mbar_init(&full_bar[i], 1);
         mbar_init(&empty_bar[i], 1);
       }
-      for (int i = 0; i < p.groups; ++i) {
+      for (int i = 0; i < p.naccs; ++i) {
         mbar_init(&tmem_full_bar[i], 1);
-        mbar_init(&tmem_empty_bar[i], kEpiWarps / p.groups);  // one arrive per epilogue warp of the group
+        mbar_init(&tmem_empty_bar[i], kEpiWarps / p.groups);  // one arrive per epilogue warp of the group that drains it
       }
       mbar_fence_init();
     }
@@ -143,12 +160,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
             const int bz = p.b_per_sample[s] ? n0 : tap;
             for (int kc = 0; kc < nkc; ++kc, ++j) {
               mbar_wait(&empty_bar[stage], phase ^ 1u);
+#ifdef DDIF_VAR_G_NO_TMA
+              mbar_arrive(&full_bar[stage]);
+#else
               mbar_expect_tx(&full_bar[stage], tx_bytes);
               tma_load_4d(&p.tmA[s], &full_bar[stage], a_dst, kc * p.bk, cw0 + dx, ch0 + dy, n0);
               if (load_b) {
                 const int slot = p.resident_b ? j : (int)stage;
                 tma_load_3d(&p.tmB[s], &full_bar[stage], smem_b + (size_t)slot * b_slot_bytes, kc * p.bk, n_tile * p.bn, bz);
               }
+#endif
               a_dst += a_stage_bytes;
               if (++stage == nstages) {
                 stage = 0;
@@ -182,7 +203,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
       const uint32_t a_step = (uint32_t)a_stage_bytes >> 4, b_step = (uint32_t)b_slot_bytes >> 4;
       const bool resident = p.resident_b != 0;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      const uint32_t ngroups = (uint32_t)p.groups;
+      const uint32_t ngroups = (uint32_t)p.naccs;
       for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
@@ -194,9 +215,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
           const uint64_t da = desc_a0 + (uint64_t)(stage * a_step);
           const uint64_t db = desc_b0 + (uint64_t)(resident ? b_res : stage * b_step);
           const uint32_t accum = j != 0 ? 1u : 0u;
+#ifndef DDIF_VAR_G_NO_MMA
           if (ksteps == 4) umma_bf16_ss_steps<4>(tmem_d, da, db, p.idesc, accum);
           else if (ksteps == 2) umma_bf16_ss_steps<2>(tmem_d, da, db, p.idesc, accum);
           else umma_bf16_ss_steps<1>(tmem_d, da, db, p.idesc, accum);
+#endif
           umma_commit_elect(&empty_bar[stage]);
           b_res += b_step;
           if (++stage == nstages) {
@@ -219,6 +242,129 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
     // 128 x 32 tile, profiles/r01_step_profile_B256_s4.txt x_conv rows).
     const int q = warp & 3;
     const int sub = (warp - 2) >> 2;
+    if constexpr ((F & kLean) != 0) {
+      constexpr bool kMod = (F & kLeanMod) != 0, kRes = (F & kLeanRes) != 0, kStats = (F & kLeanStats) != 0;
+      const int cg = sub;                      // this thread's 16-channel chunk
+      const int row = q * 32 + lane;
+      const int px_per_img = p.tw * p.th;
+      const int tn_i = row / px_per_img;
+      const int r_in = row - tn_i * px_per_img;
+      const int ry = r_in / p.tw, rx = r_in % p.tw;
+      const bool active = (cg < (p.bn >> 4)) && (q * 32 < p.a_rows);
+      const int ng = cg * 16;
+      float bv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bv[j] = (active && p.bias) ? __ldg(p.bias + ng + j) : 0.f;
+      const int step = (int)gridDim.x;
+      LeanOperands<F> nxt;
+      bool nxt_ok = false;
+      size_t nxt_pix = 0;
+      int nxt_b = 0;
+      auto locate = [&](int m_tile, size_t& pix, int& b) -> bool {
+        const int img_grp = m_tile / tiles_per_img;
+        const int t_in = m_tile - img_grp * tiles_per_img;
+        const int y = (t_in / p.tiles_x) * p.th + ry;
+        const int x = (t_in % p.tiles_x) * p.tw + rx;
+        b = img_grp * p.tn + tn_i;
+        pix = ((size_t)b * p.out_h + y) * p.out_w + x;
+        return active && (row < p.a_rows) && (b < p.batch) && (y < p.out_h) && (x < p.out_w);
+      };
+      auto fetch = [&](LeanOperands<F>& o, size_t pix, bool ok) {
+        if (kRes && ok) ldg256(p.residual + pix * (size_t)p.res_ld + ng, o.res);
+        if (kMod && ok) {
+          const bf16* m = p.mod + pix * (size_t)(2 * p.n_valid) + ng;
+          ldg256(m, o.sc);
+          ldg256(m + p.n_valid, o.sh);
+        }
+      };
+      int m_tile = (int)blockIdx.x;
+      if (m_tile < p.num_m_tiles) {
+        nxt_ok = locate(m_tile, nxt_pix, nxt_b);
+        fetch(nxt, nxt_pix, nxt_ok);
+      }
+      for (uint32_t tcount = 0; m_tile < p.num_m_tiles; m_tile += step, ++tcount) {
+        const LeanOperands<F> cur = nxt;
+        const bool row_ok = nxt_ok;
+        const size_t pix = nxt_pix;
+        const int b = nxt_b;
+        if (m_tile + step < p.num_m_tiles) {
+          nxt_ok = locate(m_tile + step, nxt_pix, nxt_b);
+          fetch(nxt, nxt_pix, nxt_ok);  // next tile's operands travel while this tile is processed
+        }
+        float fv[16];
+        if (p.film) {
+          const float* f = p.film + (size_t)b * p.film_ld + ng;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 t = row_ok ? __ldg(reinterpret_cast<const float4*>(f + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            fv[j] = t.x; fv[j + 1] = t.y; fv[j + 2] = t.z; fv[j + 3] = t.w;
+          }
+        }
+        const uint32_t acc = tcount & 1u;
+        mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1u);
+        tc_fence_after();
+        uint32_t r[16];
+        if (active) {
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.bn + (uint32_t)ng, r);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        float s1 = 0.f, s2 = 0.f;
+        if (row_ok) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + bv[j];
+          if (p.film) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += fv[j];
+          }
+          if (kMod) {
+            float sc[16], sh[16];
+            unpack16(cur.sc, sc);
+            unpack16(cur.sh, sh);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v[j] * (1.0f + sc[j]) + sh[j];
+          }
+          if (kRes) {
+            float rr[16];
+            unpack16(cur.res, rr);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += rr[j];
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = swish_half(0.5f * v[j]);
+          }
+          if (kStats) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              s1 += v[j];
+              s2 = fmaf(v[j], v[j], s2);
+            }
+          }
+          uint32_t w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            w[j] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+          stg256(p.out + pix * (size_t)p.out_ld + ng, w);
+        }
+        if (kStats && active) {  // all rows of one warp belong to one sample
+          s1 = warp_sum(s1);
+          s2 = warp_sum(s2);
+          const int img_grp = m_tile / tiles_per_img;
+          const int stat_sample = img_grp * p.tn + (q * 32) / px_per_img;
+          if (lane == 0 && stat_sample < p.batch) {
+            atomicAdd(p.stats + 2 * (size_t)stat_sample, (double)s1);
+            atomicAdd(p.stats + 2 * (size_t)stat_sample + 1, (double)s2);
+          }
+        }
+      }
+      tc_fence_before();
+    } else {
     const int grp = p.groups == 4 ? sub : (sub & 1);
     const int cg = p.groups == 4 ? 0 : (sub >> 1);
     const int row = q * 32 + lane;
@@ -250,6 +396,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
         epilogue_tile<2>(e, pf, tm, &tmem_empty_bar[grp], p.bn, n_tile, cg, lane, active, row_ok, b, y, x, pix, n0 + (q * 32) / px_per_img);
     }
     tc_fence_before();
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -294,6 +441,20 @@ static CUtensorMapSwizzle swizzle_for_span(int span) {
   return span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
+typedef void (*IgemmKernel)(const GemmKParams);
+static IgemmKernel igemm_kernel(int f) {
+  switch (f) {
+    case 0: return conv_igemm_tc_kernel<0>;
+    case kLean: return conv_igemm_tc_kernel<kLean>;
+    case kLean | kLeanMod: return conv_igemm_tc_kernel<kLean | kLeanMod>;
+    case kLean | kLeanRes: return conv_igemm_tc_kernel<kLean | kLeanRes>;
+    case kLean | kLeanStats: return conv_igemm_tc_kernel<kLean | kLeanStats>;
+    case kLean | kLeanMod | kLeanStats: return conv_igemm_tc_kernel<kLean | kLeanMod | kLeanStats>;
+    case kLean | kLeanRes | kLeanStats: return conv_igemm_tc_kernel<kLean | kLeanRes | kLeanStats>;
+    default: return nullptr;
+  }
+}
+
 int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   const bool wants_fused = g.gn_stats != nullptr || g.a_up != 0;
   if (!g.force_tma && conv3_halo_applicable(g)) {
@@ -310,7 +471,10 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   if (!enc) return DDIF_ERR_DRIVER;
   static bool smem_attr_set = false;  // outside any stream capture: gemm_prepare runs at plan-build time
   if (!smem_attr_set) {
-    DDIF_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int f = 0; f < 16; ++f) {
+      IgemmKernel k = igemm_kernel(f);
+      if (k) DDIF_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
     smem_attr_set = true;
   }
   if (g.nseg < 1 || g.nseg > 2) return DDIF_ERR_ARG;
@@ -352,9 +516,13 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   }
   p.bn = bn;
   p.n_valid = (int)g.n_valid;
-  p.groups = 4 * bn <= 512 ? 4 : 2;
+  const bool lean = bn <= 64 && g.n_pad == bn && g.n_valid % 16 == 0 && g.out && !g.out_nchw && g.out_ld % 16 == 0 &&
+                    (!g.residual || g.res_ld % 16 == 0) && (!g.film || g.film_ld % 4 == 0) && !(g.mod && g.residual);
+  p.lean = lean ? (kLean | (g.mod ? kLeanMod : 0) | (g.residual ? kLeanRes : 0) | (g.stats ? kLeanStats : 0)) : 0;
+  p.groups = lean ? 1 : (4 * bn <= 512 ? 4 : 2);
+  p.naccs = lean ? 2 : p.groups;
   uint32_t cols = 32;
-  while ((int)cols < p.groups * bn) cols <<= 1;
+  while ((int)cols < p.naccs * bn) cols <<= 1;
   p.tmem_cols = cols;
   // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 at bit 17, M>>4 at bit 24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -430,7 +598,9 @@ int gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   if (L.variant == 1) return conv3_launch(L, stream);
   if (L.variant == 2) return conv3_halo_launch(L, stream);
   const GemmKParams& p = *reinterpret_cast<const GemmKParams*>(L.kparams);
-  DDIF_CUDA_CHECK(launch_pdl(conv_igemm_tc_kernel, dim3(L.grid_x, L.grid_y), dim3(kGemmThreads), (size_t)L.smem_bytes, stream, p));
+  IgemmKernel k = igemm_kernel(p.lean);
+  if (!k) return DDIF_ERR_STATE;
+  DDIF_CUDA_CHECK(launch_pdl(k, dim3(L.grid_x, L.grid_y), dim3(kGemmThreads), (size_t)L.smem_bytes, stream, p));
   return DDIF_OK;
 }
 

@@ -19,6 +19,8 @@
 //
 // Measured floors (profiles/r01_microbench_*.txt): one M128xNxK16 MMA = max(44.8, N/2) cycles, so a 32->32 tile
 // (18 MMAs) needs >= 810 cycles; the TMA halo feed needs 420 (C=32) / 750 (C=64) cycles per tile.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ddif_internal.h"
 #include "epilogue.cuh"
@@ -37,6 +39,9 @@ struct alignas(64) HaloKParams {
   CUtensorMap tmA[2];  // activations of K segment 0 / 1 (virtual channel concat: torch.cat((x, skip), 1), sr3_dwt.py:212)
   CUtensorMap tmB[2];  // weights of segment 0 / 1
   CUtensorMap tmR;     // residual tile box (L2 prefetch only)
+  CUtensorMap tmO[2];  // output tile boxes for the TMA store: [0] 64-channel slabs (SWIZZLE_128B), [1] 32-channel remainder (SWIZZLE_64B)
+  int ostore;          // 1: epilogue stages the bf16 tile in shared memory and stores it with TMA (full 128-byte lines)
+  uint32_t o_bytes;    // bytes of one staging buffer (128 rows x bn channels); 4 buffers (2 per epilogue group)
   int has_res_map;
   int cin, kslab, nslab, span;
   int nslab0;          // slabs that come from segment 0
@@ -280,7 +285,7 @@ enum : int { kEpiRes = 1, kEpiAct = 2, kEpiStats = 4, kEpiNchw = 8 };
 
 template <int F>
 __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int warp,
-                                                   int lane, int my_tiles, long long* dts, float* s_add) {
+                                                   int lane, int my_tiles, long long* dts, float* s_add, uint8_t* smem_o) {
   constexpr bool kRes = (F & kEpiRes) != 0, kAct = (F & kEpiAct) != 0, kStats = (F & kEpiStats) != 0, kNchw = (F & kEpiNchw) != 0;
   const int q = warp & 3;
   const int grp = (warp - 10) >> 2;
@@ -302,6 +307,15 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
   const size_t hw = (size_t)out_h * out_w;
   const uint32_t tm_lane0 = tmem_base + ((uint32_t)(q * 32) << 16);
   const bool four = p.nacc == 4;
+  // TMA-store path: per-thread 32-byte stores at a pixel pitch >= 128 B reach ~55 % of the HBM rate of full-line writes
+  // (profiles/r01_microbench_gran_copy.txt), so the tile is staged in shared memory in the swizzled box layout and one
+  // elected thread of the group stores it with cp.async.bulk.tensor (two staging buffers per group).
+  const bool ost = !kNchw && p.ostore != 0;
+  const uint32_t so_base = smem_u32(smem_o) + (uint32_t)(grp * 2) * p.o_bytes;
+  const uint32_t so_row128 = (uint32_t)row * 128u, so_sw128 = (uint32_t)(row & 7);
+  const uint32_t so_row64 = (uint32_t)row * 64u, so_sw64 = (uint32_t)((row >> 1) & 3);
+  const int full_slabs = p.bn >> 6;  // 64-channel slabs; a 32-channel remainder slab follows when bn % 64 == 32
+  const bool issuer = (warp - 10) == grp * 4 && lane == 0;
   // per-warp additive vector (bias, or FiLM row of the tile's sample [+ bias]) in shared memory: with ~200 KB of dynamic
   // smem the L1 is a few KB, so per-tile __ldg of these vectors paid an L2 round trip per 16-channel chunk
   float* addv = s_add + (warp - 10) * 256;
@@ -362,6 +376,11 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
       __syncwarp();
     }
     f32x2 s1 = pk2(0.f, 0.f), s2 = pk2(0.f, 0.f);
+    const uint32_t so = so_base + (it & 1u) * p.o_bytes;
+    if (ost) {  // staging buffer (it & 1) was handed to TMA two tiles ago: wait until that store has read it
+      if (issuer) tma_store_wait_read<1>();
+      named_bar_sync(1 + grp, 128);
+    }
     auto process = [&](const uint32_t (&acc)[16], const uint32_t (&rs)[8], int cc) {
       const int ng = cc * 16;
       const int nrem = n_valid - ng;
@@ -407,7 +426,23 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
           uint32_t w[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) w[j] = f2_to_bf2(v[j]);
-          stg256(outp + pix * (size_t)out_ld + ng, w);
+          if (ost) {
+            const int slab = cc >> 2;
+            uint32_t a0s, a1s;
+            if (slab < full_slabs) {
+              const uint32_t u = (uint32_t)(cc & 3) * 2u, sb = so + (uint32_t)slab * 16384u + so_row128;
+              a0s = sb + ((u ^ so_sw128) << 4);
+              a1s = sb + (((u + 1u) ^ so_sw128) << 4);
+            } else {
+              const uint32_t u = (uint32_t)(cc & 1) * 2u, sb = so + (uint32_t)full_slabs * 16384u + so_row64;
+              a0s = sb + ((u ^ so_sw64) << 4);
+              a1s = sb + (((u + 1u) ^ so_sw64) << 4);
+            }
+            h_sts128(a0s, make_uint4(w[0], w[1], w[2], w[3]));
+            h_sts128(a1s, make_uint4(w[4], w[5], w[6], w[7]));
+          } else {
+            stg256(outp + pix * (size_t)out_ld + ng, w);
+          }
         }
       } else {  // ragged last chunk (n_valid % 16 != 0): scalar path
         float ss1 = 0.f, ss2 = 0.f;
@@ -447,6 +482,16 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
       if (two) process(a1, rs1, cc + 1);
 #endif
     }
+    if (ost) {
+      h_fence_proxy_async();
+      named_bar_sync(1 + grp, 128);
+      if (issuer) {
+        const int cx = tx * 8, cy = ty * 16;
+        for (int sl = 0; sl < full_slabs; ++sl) tma_store_4d(&p.tmO[0], smem_o + (so - smem_u32(smem_o)) + (size_t)sl * 16384, n0 + sl * 64, cx, cy, b);
+        if (p.bn & 32) tma_store_4d(&p.tmO[1], smem_o + (so - smem_u32(smem_o)) + (size_t)full_slabs * 16384, n0 + full_slabs * 64, cx, cy, b);
+        tma_store_commit();
+      }
+    }
     if (warp == 10 && lane == 0) h_ts(dts, 2, t, 2);
     if (kStats) {
       float l1, h1, l2, h2;
@@ -463,6 +508,7 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
     if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
     if (ty >= tiles_y) { ty -= tiles_y; ++b; }
   }
+  if (ost && issuer) tma_store_wait_all();  // shared memory must outlive the last store's reads
 }
 
 template <int F>
@@ -472,7 +518,8 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + (size_t)p.stages * p.stage_bytes;
+  uint8_t* smem_o = smem + (size_t)p.stages * p.stage_bytes;  // [4][o_bytes] output staging (1024-byte aligned), only with ostore
+  uint8_t* smem_b = smem_o + (p.ostore ? 4u * p.o_bytes : 0u);
   float* s_gamma = reinterpret_cast<float*>(smem_b + (size_t)(9 * p.nslab) * p.b_slot_bytes);
   float* s_beta = s_gamma + p.cin;
   float2* s_stat = reinterpret_cast<float2*>(s_beta + p.cin);
@@ -496,6 +543,10 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   if (warp == 18 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB[0]);
+    if (p.ostore) {
+      tma_prefetch_desc(&p.tmO[0]);
+      tma_prefetch_desc(&p.tmO[1]);
+    }
     if (p.nslab0 < p.nslab) {
       tma_prefetch_desc(&p.tmA[1]);
       tma_prefetch_desc(&p.tmB[1]);
@@ -589,7 +640,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
     }
   } else if (warp >= 10 && warp < 18) {
     // ===================== epilogue (warps 10..17): two groups of 4 warps, one TMEM accumulator each =====================
-    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, dts, s_add);
+    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, dts, s_add, smem_o);
     tc_fence_before();
   }
   __syncthreads();
@@ -641,7 +692,7 @@ static cudaError_t halo_set_attrs() {
 }
 
 struct HaloGeom {
-  int cin, kslab, nslab, nslab0, span, stages, stage_bytes, b_slot, n_stat, misc, smem, split, bn;
+  int cin, kslab, nslab, nslab0, span, stages, stage_bytes, b_slot, n_stat, misc, smem, split, bn, ostore, o_bytes;
 };
 
 static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
@@ -670,21 +721,30 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
   h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + (3 * kHMaxStages + 12) * 8 + 64 + 1024;
   // Resident weights of one CTA (9 taps x all K slabs x bn rows) must leave room for two rings of >= 2 halo stages:
   // split N over blockIdx.y (1, 2, 4 CTAs per tile) and, before splitting further, halve the K slab (smaller stages).
-  for (int pass = 0; pass < 2; ++pass) {  // pass 0: >= 4 stages; pass 1: accept 2
+  // The TMA-store epilogue is OFF by default: measured on B200 it is correct but slower for N >= 64 (32->64 @64^2: 57.7 -> 72.4 us,
+  // 64->128 @32^2: 35.1 -> 41.9 us) -- the staging writes + TMA reads add 2 x 16-32 KB of shared-memory traffic per tile to a kernel
+  // whose tcgen05 operand fetch already saturates shared-memory bandwidth -- and only +4 % for N = 32.  DDIF_OSTORE=1 enables it.
+  static const bool no_ostore = getenv("DDIF_OSTORE") == nullptr;
+  for (int pass = 0; pass < 3; ++pass) {  // pass 0: >= 4 stages + TMA-store staging; pass 1: >= 4 stages; pass 2: accept 2
     for (int split = 1; split <= 4; split *= 2) {
       if (g.n_pad % (16 * split) != 0) break;
       if (split > 1 && g.out_nchw) break;
       const int bn = (int)g.n_pad / split;
+      // TMA store: bf16 NHWC output, 32-channel granules, no padded channels, 16-byte aligned pixel rows
+      const bool can_ost = !no_ostore && g.out && !g.out_nchw && bn % 32 == 0 && g.n_valid == g.n_pad && g.out_ld % 8 == 0 && g.out_w % 8 == 0;
+      if (pass == 0 && !can_ost) continue;
+      const int o_bytes = pass == 0 ? 128 * bn * 2 : 0;
       for (int kslab = gcd; kslab >= 16; kslab >>= 1) {
         const int span = kslab * 2;
         const int stage_bytes = (kHPx * span + 1023) & ~1023;
         const int b_total = 9 * cin * bn * 2;  // independent of the slab size
-        int st = ((227 * 1024 - h.misc - b_total) / stage_bytes) & ~1;
+        int st = ((227 * 1024 - h.misc - b_total - 4 * o_bytes) / stage_bytes) & ~1;
         if (st > kHMaxStages) st = kHMaxStages;
-        if (st >= (pass == 0 ? 4 : 2)) {
+        if (st >= (pass <= 1 ? 4 : 2)) {
           h.kslab = kslab; h.nslab = cin / kslab; h.nslab0 = (int)g.a_c[0] / kslab; h.span = span;
           h.stage_bytes = stage_bytes; h.split = split; h.bn = bn; h.b_slot = bn * span; h.stages = st;
-          h.smem = st * stage_bytes + b_total + h.misc;
+          h.ostore = pass == 0 ? 1 : 0; h.o_bytes = o_bytes;
+          h.smem = st * stage_bytes + 4 * o_bytes + b_total + h.misc;
           return true;
         }
       }
@@ -748,6 +808,22 @@ int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
       cuuint32_t es[3] = {1, 1, 1};
       CUresult r = enc(&p.tmB[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(g.w[s]), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
+    }
+  }
+  p.ostore = h.ostore;
+  p.o_bytes = (uint32_t)h.o_bytes;
+  if (p.ostore) {
+    for (int k = 0; k < 2; ++k) {
+      const int chans = k == 0 ? 64 : 32;
+      if (k == 0 && p.bn < 64) continue;
+      if (k == 1 && !(p.bn & 32)) continue;
+      cuuint64_t dims[4] = {(cuuint64_t)g.n_valid, (cuuint64_t)g.out_w, (cuuint64_t)g.out_h, (cuuint64_t)g.batch};
+      cuuint64_t strides[3] = {(cuuint64_t)g.out_ld * 2, (cuuint64_t)g.out_w * g.out_ld * 2, (cuuint64_t)g.out_h * g.out_w * g.out_ld * 2};
+      cuuint32_t box[4] = {(cuuint32_t)chans, 8, 16, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = enc(&p.tmO[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, g.out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       k == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
     }
   }

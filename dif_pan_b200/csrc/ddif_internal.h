@@ -10,7 +10,7 @@ namespace ddif {
 
 // A GEMM op resolved to kernel parameters (tensor maps encoded) + launch geometry.
 struct alignas(64) GemmLaunch {
-  unsigned char kparams[1024];
+  unsigned char kparams[1536];
   int grid_x, grid_y, smem_bytes;
   int flags;    // variant 2: compile-time epilogue specialisation (kEpi* bits)
   int variant;  // 0: conv_igemm_tc_kernel (TMA tap boxes), 1: conv3x3_fused_tc_kernel (LDG halo, 3 shifted copies; nearest-x2 loader),

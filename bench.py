@@ -142,8 +142,10 @@ def main():
         line = dict(impl="reference", metric=METRIC, value=r["value"], unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                     ms_per_step=r["ms_per_denoise_step"] * a.timesteps * (a.batch / a.cpu_batch), higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload="WV3 64x64x8 patches, DDPM cosine T=%d, CPU oracle port (reference algorithm)" % a.timesteps,
-                                cpu_batch=a.cpu_batch, timesteps=a.timesteps),
+                    config=dict(workload="BASELINE configs[1]: WV3 64x64x8 patches, batch %d per GPU, full DDPM loop cosine T=%d, clip (0,1), "
+                                         "x_start, self-cond" % (a.batch, a.timesteps), batch_per_gpu=a.batch, timesteps=a.timesteps,
+                                sample="reference algorithm (oracle port, torch CPU fp32) on the host cores: one denoise step of %d patches per "
+                                       "bench step, extrapolated to the full workload" % a.cpu_batch),
                     cpu_baseline=dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"]),
                     e2e=dict(value=r["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
         print(json.dumps(line))

@@ -34,12 +34,23 @@ static constexpr int kHThreads = kHxfThreads + 64 + 32 * kHEpiWarps + 32;  // + 
 static constexpr int kHW = 10, kHH = 18, kHPx = kHW * kHH;  // halo of an 8 x 16 tile
 static constexpr int kHMaxStages = 8;
 static constexpr int kHMaxStat = 1024;
+// The TMA-store epilogue is compiled in only with -DDDIF_OSTORE_BUILD (tools/ experiments): even disabled at run time its extra
+// live values cost the epilogue registers (spills at the 96-register cap) and 10 % on the GN+conv layers.
+#ifdef DDIF_OSTORE_BUILD
+static constexpr bool kOstoreBuild = true;
+#else
+static constexpr bool kOstoreBuild = false;
+#endif
 
 struct alignas(64) HaloKParams {
   CUtensorMap tmA[2];  // activations of K segment 0 / 1 (virtual channel concat: torch.cat((x, skip), 1), sr3_dwt.py:212)
   CUtensorMap tmB[2];  // weights of segment 0 / 1
   CUtensorMap tmR;     // residual tile box (L2 prefetch only)
   CUtensorMap tmO[2];  // output tile boxes for the TMA store: [0] 64-channel slabs (SWIZZLE_128B), [1] 32-channel remainder (SWIZZLE_64B)
+  const float* dw_w;   // depthwise mode (see ddif_gemm_t.dw_w): [9][cin] fp32
+  int dw_n;            // leading output channels fed by the depthwise result; the rest read the normalised input itself
+  int ntap_w;          // weight taps resident per K slab: 9, or 1 in depthwise mode
+  uint32_t idesc_q, idesc_r, dw_bytes;  // depthwise mode: instruction descriptors (N = dw_n / bn - dw_n), bytes of one A buffer
   int ostore;          // 1: epilogue stages the bf16 tile in shared memory and stores it with TMA (full 128-byte lines)
   uint32_t o_bytes;    // bytes of one staging buffer (128 rows x bn channels); 4 buffers (2 per epilogue group)
   int has_res_map;
@@ -276,6 +287,195 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
   }
 }
 
+// ---- depthwise mode (FWM q path) ------------------------------------------------------------------------------------------
+// q = Conv1x1(DW3x3(x_hat)) and r = attn_res(x_hat) (sr3_dwt.py:509-517,541,573) without the 9x dense-conv FLOPs of the composed
+// formulation: the transform group normalises the landed halo stage in place (as above), synchronises, and then computes the
+// depthwise 3x3 of the 8 x 16 centre pixels from the normalised halo (fp32, sliding 3x3 window in registers: 3 new LDS.32 per
+// output word) into a K-major swizzled A buffer.  The MMA warp then issues ONE tap: q columns from that buffer, r columns from
+// the centre-tap view of the stage itself.  Two A buffers per half-pipeline, released by tcgen05.commit.
+template <int NCK>
+__device__ __forceinline__ uint32_t halo_sw(uint32_t r) {
+  return NCK == 8 ? (r & 7u) : (NCK == 4 ? ((r >> 1) & 3u) : ((r >> 2) & 1u));
+}
+
+template <int NCK>
+__device__ __forceinline__ void halo_transform_dw_loop(const HaloKParams& p, uint32_t a_base, uint32_t dw_base, uint64_t* a_tma, uint64_t* a_ready,
+                                                       uint64_t* dw_empty, const float* s_gamma, const float* s_beta, const float2* s_stat,
+                                                       const float* s_dw, int tid) {
+  constexpr int RPP = kHxfGroup / NCK;
+  constexpr int NPASS = (kHPx + RPP - 1) / RPP;
+  constexpr int BATCH = NPASS % 6 == 0 ? 6 : 3;
+  constexpr int WPR = NCK * 4;            // bf16x2 words per row of the slab: 8 / 16 / 32
+  constexpr int NCG = kHxfGroup / WPR;    // column groups: 16 / 8 / 4
+  constexpr uint32_t SPAN = NCK * 16;
+  const int grp = tid / kHxfGroup, lt = tid % kHxfGroup;
+  const int c = lt % NCK;
+  const int r0 = lt / NCK;
+  const float hs = p.gn_act ? 0.5f : 1.0f;
+  const uint32_t nst = (uint32_t)p.stages >> 1;
+  uint32_t soff[NPASS];
+  int hyx[NPASS];
+#pragma unroll
+  for (int k = 0; k < NPASS; ++k) {
+    const int r = r0 + k * RPP;
+    const int hy = r / kHW, hx = r - hy * kHW;
+    soff[k] = (uint32_t)r * SPAN + (((uint32_t)c ^ halo_sw<NCK>((uint32_t)r)) << 4);
+    hyx[k] = r < kHPx ? ((hy << 8) | hx) : (255 << 8);
+  }
+  // depthwise work split: word w of the slab row, column group cgp
+  const int w = lt % WPR, cgp = lt / WPR;
+  const uint32_t wchunk = (uint32_t)w >> 2, wsub = ((uint32_t)w & 3u) << 2;
+  constexpr int UNITS = NCG == 4 ? 2 : 1;           // columns per thread
+  constexpr int NROWS = NCG == 16 ? 8 : 16;         // output rows per unit
+  const int col0 = NCG == 16 ? (cgp & 7) : (NCG == 8 ? cgp : cgp * 2);
+  const int row0 = NCG == 16 ? (cgp >> 3) * 8 : 0;
+  const bool act = p.gn_act != 0;
+  const unsigned H = (unsigned)p.out_h, W = (unsigned)p.out_w;
+  HaloIter it;
+  it.init(p, (int)blockIdx.x + grp * (int)gridDim.x, 2 * (int)gridDim.x);
+  a_tma += grp * nst; a_ready += grp * nst;
+  a_base += (uint32_t)grp * nst * p.stage_bytes;
+  dw_base += (uint32_t)(grp * 2) * p.dw_bytes;
+  dw_empty += grp * 2;
+  uint32_t stage = 0, phase = 0, dbuf = 0, dphase = 0;
+  int cur_b = -1, cur_slab = -1;
+  f32x2 a2[4], d2[4], wt[9];
+  for (; it.remaining > 0; it.next()) {
+    if (it.b != cur_b || it.slab != cur_slab) {
+      if (it.slab != cur_slab) {
+        const int ch = it.slab * p.kslab + 2 * w;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wt[t] = pk2(s_dw[t * p.cin + ch], s_dw[t * p.cin + ch + 1]);
+      }
+      cur_b = it.b; cur_slab = it.slab;
+      const float2 mr = it.b < kHMaxStat ? s_stat[it.b] : halo_mean_rstd(p, it.b);
+      const int ch0 = it.slab * p.kslab + c * 8;
+      const float sc = hs * mr.y;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a0 = sc * s_gamma[ch0 + 2 * j], a1 = sc * s_gamma[ch0 + 2 * j + 1];
+        a2[j] = pk2(a0, a1);
+        d2[j] = pk2(fmaf(-mr.x, a0, hs * s_beta[ch0 + 2 * j]), fmaf(-mr.x, a1, hs * s_beta[ch0 + 2 * j + 1]));
+      }
+    }
+    const int y0 = it.ty * 16 - 1, x0 = it.tx * 8 - 1;
+    const uint32_t sbase = a_base + stage * p.stage_bytes;
+    mbar_wait(&a_tma[stage], phase);
+    // phase 1: GroupNorm affine (+Swish) in place, branch-free (see halo_transform_loop)
+#pragma unroll
+    for (int k0 = 0; k0 < NPASS; k0 += BATCH) {
+      uint4 v[BATCH];
+      bool ok[BATCH];
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k) {
+        ok[k] = (unsigned)(y0 + (hyx[k0 + k] >> 8)) < H && (unsigned)(x0 + (hyx[k0 + k] & 255)) < W;
+        v[k] = h_lds128(sbase + soff[k0 + k]);
+      }
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k) {
+        const uint32_t ww[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          f32x2 t = fma2(bf2_to_f2(ww[q]), a2[q], d2[q]);
+          if (act) t = swish_half2(t);
+          o[q] = f2_to_bf2(t);
+        }
+        v[k] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+#pragma unroll
+      for (int k = 0; k < BATCH; ++k)
+        if (ok[k]) h_sts128(sbase + soff[k0 + k], v[k]);
+    }
+    named_bar_sync(3 + grp, kHxfGroup);  // the whole normalised halo is visible to the group
+    // phase 2: depthwise 3x3 of the centre pixels -> A buffer `dbuf`
+    mbar_wait(&dw_empty[dbuf], dphase ^ 1u);
+    const uint32_t dbase = dw_base + dbuf * p.dw_bytes;
+    auto ldw = [&](int hy, int hx) -> f32x2 {
+      const uint32_t r = (uint32_t)(hy * kHW + hx);
+      uint32_t word;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(word) : "r"(sbase + r * SPAN + ((wchunk ^ halo_sw<NCK>(r)) << 4) + wsub) : "memory");
+      return bf2_to_f2(word);
+    };
+#pragma unroll
+    for (int u = 0; u < UNITS; ++u) {
+      const int col = col0 + u;  // output column ox; halo columns col, col+1, col+2
+      f32x2 ra[3], rb[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        ra[j] = ldw(row0, col + j);
+        rb[j] = ldw(row0 + 1, col + j);
+      }
+#pragma unroll
+      for (int oy = 0; oy < NROWS; ++oy) {
+        f32x2 rc[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) rc[j] = ldw(row0 + oy + 2, col + j);
+        // three independent chains (one per window row) instead of nine dependent FMAs
+        f32x2 acc0 = fma2(ra[2], wt[2], fma2(ra[1], wt[1], mul2(ra[0], wt[0])));
+        f32x2 acc1 = fma2(rb[2], wt[5], fma2(rb[1], wt[4], mul2(rb[0], wt[3])));
+        f32x2 acc2 = fma2(rc[2], wt[8], fma2(rc[1], wt[7], mul2(rc[0], wt[6])));
+        const f32x2 acc = add2(add2(acc0, acc1), acc2);
+        const uint32_t ro = (uint32_t)((row0 + oy) * 8 + col);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dbase + ro * SPAN + ((wchunk ^ halo_sw<NCK>(ro)) << 4) + wsub), "r"(f2_to_bf2(acc)) : "memory");
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          ra[j] = rb[j];
+          rb[j] = rc[j];
+        }
+      }
+    }
+    h_fence_proxy_async();
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&a_ready[stage]);
+    if (++stage == nst) { stage = 0; phase ^= 1u; }
+    if (++dbuf == 2u) { dbuf = 0; dphase ^= 1u; }
+  }
+}
+
+template <int KSTEPS>
+__device__ __forceinline__ void halo_mma_dw_loop(const HaloKParams& p, uint32_t a_base, uint32_t dw_base, uint32_t b_base, uint64_t* a_full,
+                                                 uint64_t* a_empty, uint64_t* dw_empty, uint64_t* b_full, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                                 uint32_t tmem_base, int my_tiles, int w) {
+  const uint32_t span = (uint32_t)p.span;
+  const uint32_t stage16 = p.stage_bytes >> 4, b16 = p.b_slot_bytes >> 4, dw16 = p.dw_bytes >> 4;
+  const uint32_t centre = ((uint32_t)(kHW + 1) * span) >> 4;  // centre tap of the halo: one line + one pixel
+  const uint32_t nst = (uint32_t)p.stages >> 1;
+  a_full += (uint32_t)w * nst; a_empty += (uint32_t)w * nst;
+  dw_empty += w * 2;
+  a_base += (uint32_t)w * nst * p.stage_bytes;
+  dw_base += (uint32_t)(w * 2) * p.dw_bytes;
+  const uint64_t desc_s0 = make_smem_desc(a_base, (uint32_t)kHW * span, p.layout_type);  // stage view: SBO = one halo line
+  const uint64_t desc_d0 = make_smem_desc(dw_base, 8u * span, p.layout_type);             // depthwise buffer: dense 8-row groups
+  const uint64_t desc_bq = make_smem_desc(b_base, 8u * span, p.layout_type);
+  const uint64_t desc_br = desc_bq + (uint64_t)(((uint32_t)p.dw_n * span) >> 4);
+  const bool has_r = p.dw_n < p.bn;
+  uint32_t stage = 0, phase = 0, dbuf = 0;
+  mbar_wait(b_full, 0u);
+  tc_fence_after();
+  const bool four = p.nacc == 4;
+  uint32_t itn = 0;
+  for (int t = w; t < my_tiles; t += 2, ++itn) {
+    const uint32_t acc = (uint32_t)w + (four ? 2u * (itn & 1u) : 0u);
+    const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.bn;
+    mbar_wait(&tmem_empty[acc], ((four ? itn >> 1 : itn) & 1u) ^ 1u);
+    tc_fence_after();
+    for (int slab = 0; slab < p.nslab; ++slab) {
+      mbar_wait(&a_full[stage], phase);
+      tc_fence_after();
+      const uint64_t db = (uint64_t)((uint32_t)slab * b16);
+      umma_bf16_ss_steps<KSTEPS>(tmem_d, desc_d0 + (uint64_t)(dbuf * dw16), desc_bq + db, p.idesc_q, slab != 0 ? 1u : 0u);
+      if (has_r)
+        umma_bf16_ss_steps<KSTEPS>(tmem_d + (uint32_t)p.dw_n, desc_s0 + (uint64_t)(stage * stage16 + centre), desc_br + db, p.idesc_r, slab != 0 ? 1u : 0u);
+      umma_commit_elect(&a_empty[stage]);
+      umma_commit_elect(&dw_empty[dbuf]);
+      if (++stage == nst) { stage = 0; phase ^= 1u; }
+      dbuf ^= 1u;
+    }
+    umma_commit_elect(&tmem_full[acc]);
+  }
+}
+
 // ---- epilogue --------------------------------------------------------------------------------------------------------
 // Two groups of 4 warps; group g owns TMEM accumulator g (tiles t = g, g+2, ...), so a warp has two tile periods for one
 // tile and the per-tile fixed cost (coordinates, barrier, statistics reduction) is paid once per 32 rows x ALL columns.
@@ -310,7 +510,7 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
   // TMA-store path: per-thread 32-byte stores at a pixel pitch >= 128 B reach ~55 % of the HBM rate of full-line writes
   // (profiles/r01_microbench_gran_copy.txt), so the tile is staged in shared memory in the swizzled box layout and one
   // elected thread of the group stores it with cp.async.bulk.tensor (two staging buffers per group).
-  const bool ost = !kNchw && p.ostore != 0;
+  const bool ost = kOstoreBuild && !kNchw && p.ostore != 0;
   const uint32_t so_base = smem_u32(smem_o) + (uint32_t)(grp * 2) * p.o_bytes;
   const uint32_t so_row128 = (uint32_t)row * 128u, so_sw128 = (uint32_t)(row & 7);
   const uint32_t so_row64 = (uint32_t)row * 64u, so_sw64 = (uint32_t)((row >> 1) & 3);
@@ -511,7 +711,7 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
   if (ost && issuer) tma_store_wait_all();  // shared memory must outlive the last store's reads
 }
 
-template <int F>
+template <int F, bool DW>
 __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __grid_constant__ HaloKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -519,20 +719,23 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   uint8_t* smem = smem_raw + (base - raw);
   uint8_t* smem_a = smem;
   uint8_t* smem_o = smem + (size_t)p.stages * p.stage_bytes;  // [4][o_bytes] output staging (1024-byte aligned), only with ostore
-  uint8_t* smem_b = smem_o + (p.ostore ? 4u * p.o_bytes : 0u);
-  float* s_gamma = reinterpret_cast<float*>(smem_b + (size_t)(9 * p.nslab) * p.b_slot_bytes);
+  uint8_t* smem_dw = smem_o + (p.ostore ? 4u * p.o_bytes : 0u);  // [4][dw_bytes] depthwise A buffers (2 per half-pipeline), only in depthwise mode
+  uint8_t* smem_b = smem_dw + (DW ? 4u * p.dw_bytes : 0u);
+  float* s_gamma = reinterpret_cast<float*>(smem_b + (size_t)(p.ntap_w * p.nslab) * p.b_slot_bytes);
   float* s_beta = s_gamma + p.cin;
   float2* s_stat = reinterpret_cast<float2*>(s_beta + p.cin);
   const int n_stat = p.gn_stats ? (p.batch < kHMaxStat ? p.batch : kHMaxStat) : 0;
   float* s_add = reinterpret_cast<float*>(s_stat + ((n_stat + 1) & ~1));  // [8 epilogue warps][256], 16-byte aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_add + kHEpiWarps * 256);
+  float* s_dw = s_add + kHEpiWarps * 256;                                  // [9][cin] depthwise weights (depthwise mode)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dw + (DW ? ((9 * p.cin + 3) & ~3) : 0));
   uint64_t* a_tma = bars;                       // [stages] TMA landed
   uint64_t* a_ready = bars + kHMaxStages;       // [stages] transformed (count 256)
   uint64_t* a_empty = bars + 2 * kHMaxStages;   // [stages] MMAs done
   uint64_t* tmem_full = bars + 3 * kHMaxStages; // [4]
   uint64_t* tmem_empty = tmem_full + 4;         // [4]
   uint64_t* b_full = tmem_empty + 4;            // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint64_t* dw_empty = b_full + 1;              // [4] depthwise A buffer consumed by the MMAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dw_empty + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -564,6 +767,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
         mbar_init(&tmem_empty[i], kHEpiWarps / 2);
       }
       mbar_init(b_full, 1);
+      for (int i = 0; i < 4; ++i) mbar_init(&dw_empty[i], 1);
       mbar_fence_init();
     }
     __syncwarp();
@@ -576,10 +780,10 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   const uint32_t tmem_base = *tmem_slot;
   // Resident weights: static data, requested BEFORE the dependency wait so that the load overlaps the previous kernel's tail.
   if (warp == 18 && lane == 0) {
-    mbar_expect_tx(b_full, (uint32_t)(9 * p.nslab) * p.b_slot_bytes);
+    mbar_expect_tx(b_full, (uint32_t)(p.ntap_w * p.nslab) * p.b_slot_bytes);
     for (int slab = 0; slab < p.nslab; ++slab)
-      for (int tap = 0; tap < 9; ++tap)
-        tma_load_3d(&p.tmB[slab >= p.nslab0], b_full, smem_b + (size_t)(slab * 9 + tap) * p.b_slot_bytes,
+      for (int tap = 0; tap < p.ntap_w; ++tap)
+        tma_load_3d(&p.tmB[slab >= p.nslab0], b_full, smem_b + (size_t)(slab * p.ntap_w + tap) * p.b_slot_bytes,
                     (slab >= p.nslab0 ? slab - p.nslab0 : slab) * p.kslab, (int)blockIdx.y * p.bn, tap);
   }
   pdl_wait();  // everything below reads what earlier kernels of the step wrote
@@ -589,12 +793,19 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
       s_beta[i] = p.gn_beta[i];
     }
     for (int i = threadIdx.x; i < n_stat; i += blockDim.x) s_stat[i] = halo_mean_rstd(p, i);  // fp64 once per CTA
+    if (DW)
+      for (int i = threadIdx.x; i < 9 * p.cin; i += blockDim.x) s_dw[i] = p.dw_w[i];
     __syncthreads();
   }
 
   if (warp < 8) {
     // ===================== transform warps (only with the GroupNorm prologue) =====================
-    if (gn) {
+    if constexpr (DW) {
+      const uint32_t a_base = smem_u32(smem_a), dwb = smem_u32(smem_dw);
+      if (p.kslab == 64) halo_transform_dw_loop<8>(p, a_base, dwb, a_tma, a_ready, dw_empty, s_gamma, s_beta, s_stat, s_dw, threadIdx.x);
+      else if (p.kslab == 32) halo_transform_dw_loop<4>(p, a_base, dwb, a_tma, a_ready, dw_empty, s_gamma, s_beta, s_stat, s_dw, threadIdx.x);
+      else halo_transform_dw_loop<2>(p, a_base, dwb, a_tma, a_ready, dw_empty, s_gamma, s_beta, s_stat, s_dw, threadIdx.x);
+    } else if (gn) {
       const uint32_t a_base = smem_u32(smem_a);
       if (p.kslab == 64) halo_transform_loop<8>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x, dts);
       else if (p.kslab == 32) halo_transform_loop<4>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x, dts);
@@ -604,6 +815,12 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
     // ===================== MMA issuers (converged warps, elected lane issues) =====================
     uint64_t* a_full = gn ? a_ready : a_tma;
     const int w = warp - 8;
+    if constexpr (DW) {
+      const uint32_t sa = smem_u32(smem_a), sd = smem_u32(smem_dw), sb = smem_u32(smem_b);
+      if (p.kslab == 64) halo_mma_dw_loop<4>(p, sa, sd, sb, a_full, a_empty, dw_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w);
+      else if (p.kslab == 32) halo_mma_dw_loop<2>(p, sa, sd, sb, a_full, a_empty, dw_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w);
+      else halo_mma_dw_loop<1>(p, sa, sd, sb, a_full, a_empty, dw_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w);
+    } else
     if (p.kslab == 64) halo_mma_loop<4>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
     else if (p.kslab == 32) halo_mma_loop<2>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
     else halo_mma_loop<1>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
@@ -666,25 +883,26 @@ typedef void (*HaloKernel)(const HaloKParams);
 static int halo_flags(const ddif_gemm_t& g) {
   return (g.residual ? kEpiRes : 0) | (g.act ? kEpiAct : 0) | (g.stats ? kEpiStats : 0) | (g.out_nchw ? kEpiNchw : 0);
 }
-static HaloKernel halo_kernel(int f) {
+static HaloKernel halo_kernel(int f, bool dw = false) {
+  if (dw) return f == 0 ? conv3x3_halo_tc_kernel<0, true> : nullptr;  // the q path: bias only, bf16 NHWC output
   switch (f) {
-    case 0: return conv3x3_halo_tc_kernel<0>;
-    case 1: return conv3x3_halo_tc_kernel<1>;
-    case 2: return conv3x3_halo_tc_kernel<2>;
-    case 3: return conv3x3_halo_tc_kernel<3>;
-    case 4: return conv3x3_halo_tc_kernel<4>;
-    case 5: return conv3x3_halo_tc_kernel<5>;
-    case 6: return conv3x3_halo_tc_kernel<6>;
-    case 7: return conv3x3_halo_tc_kernel<7>;
-    case 8: return conv3x3_halo_tc_kernel<8>;
+    case 0: return conv3x3_halo_tc_kernel<0, false>;
+    case 1: return conv3x3_halo_tc_kernel<1, false>;
+    case 2: return conv3x3_halo_tc_kernel<2, false>;
+    case 3: return conv3x3_halo_tc_kernel<3, false>;
+    case 4: return conv3x3_halo_tc_kernel<4, false>;
+    case 5: return conv3x3_halo_tc_kernel<5, false>;
+    case 6: return conv3x3_halo_tc_kernel<6, false>;
+    case 7: return conv3x3_halo_tc_kernel<7, false>;
+    case 8: return conv3x3_halo_tc_kernel<8, false>;
     default: return nullptr;
   }
 }
 static cudaError_t halo_set_attrs() {
   static bool done = false;
   if (done) return cudaSuccess;
-  for (int f = 0; f <= 8; ++f) {
-    cudaError_t e = cudaFuncSetAttribute(halo_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  for (int f = 0; f <= 9; ++f) {
+    cudaError_t e = cudaFuncSetAttribute(f == 9 ? halo_kernel(0, true) : halo_kernel(f), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
   }
   done = true;
@@ -692,7 +910,7 @@ static cudaError_t halo_set_attrs() {
 }
 
 struct HaloGeom {
-  int cin, kslab, nslab, nslab0, span, stages, stage_bytes, b_slot, n_stat, misc, smem, split, bn, ostore, o_bytes;
+  int cin, kslab, nslab, nslab0, span, stages, stage_bytes, b_slot, n_stat, misc, smem, split, bn, ostore, o_bytes, ntap_w, dw_bytes;
 };
 
 static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
@@ -709,8 +927,10 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
     cin += (int)g.a_c[s];
   }
   if (cin > 512) return false;
+  const bool dw = g.dw_w != nullptr;
+  if (dw && (!g.gn_stats || g.dw_n < 16 || g.dw_n % 16 != 0 || g.dw_n > g.n_pad || (g.n_pad - g.dw_n) % 16 != 0 || g.n_valid != g.n_pad)) return false;
   if (g.nseg == 2 && g.gn_stats && !g.gn_stats2) return false;
-  if (g.mod || halo_kernel(halo_flags(g)) == nullptr) return false;  // CSM modulation / fp32 store + residual: generic kernel
+  if (g.mod || halo_kernel(halo_flags(g), g.dw_w != nullptr) == nullptr) return false;  // CSM modulation / fp32 store + residual: generic kernel
   if (g.out && g.out_nchw) return false;
   if (g.out && g.out_ld % 16 != 0) return false;                       // 32-byte stores
   if (g.residual && g.res_ld % 16 != 0) return false;
@@ -718,17 +938,18 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
   if (!g.out && !g.out_nchw) return false;
   h.cin = cin;
   h.n_stat = g.gn_stats ? (int)(g.batch < kHMaxStat ? g.batch : kHMaxStat) : 0;
-  h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + (3 * kHMaxStages + 12) * 8 + 64 + 1024;
+  h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + (dw ? ((9 * cin + 3) & ~3) * 4 : 0) + (3 * kHMaxStages + 16) * 8 + 64 + 1024;
+  h.ntap_w = dw ? 1 : 9;
   // Resident weights of one CTA (9 taps x all K slabs x bn rows) must leave room for two rings of >= 2 halo stages:
   // split N over blockIdx.y (1, 2, 4 CTAs per tile) and, before splitting further, halve the K slab (smaller stages).
   // The TMA-store epilogue is OFF by default: measured on B200 it is correct but slower for N >= 64 (32->64 @64^2: 57.7 -> 72.4 us,
   // 64->128 @32^2: 35.1 -> 41.9 us) -- the staging writes + TMA reads add 2 x 16-32 KB of shared-memory traffic per tile to a kernel
-  // whose tcgen05 operand fetch already saturates shared-memory bandwidth -- and only +4 % for N = 32.  DDIF_OSTORE=1 enables it.
-  static const bool no_ostore = getenv("DDIF_OSTORE") == nullptr;
+  // whose tcgen05 operand fetch already saturates shared-memory bandwidth -- and only +4 % for N = 32.  Build with -DDDIF_OSTORE_BUILD and set DDIF_OSTORE=1 to enable it.
+  static const bool no_ostore = !kOstoreBuild || getenv("DDIF_OSTORE") == nullptr;
   for (int pass = 0; pass < 3; ++pass) {  // pass 0: >= 4 stages + TMA-store staging; pass 1: >= 4 stages; pass 2: accept 2
     for (int split = 1; split <= 4; split *= 2) {
       if (g.n_pad % (16 * split) != 0) break;
-      if (split > 1 && g.out_nchw) break;
+      if (split > 1 && (g.out_nchw || dw)) break;
       const int bn = (int)g.n_pad / split;
       // TMA store: bf16 NHWC output, 32-channel granules, no padded channels, 16-byte aligned pixel rows
       const bool can_ost = !no_ostore && g.out && !g.out_nchw && bn % 32 == 0 && g.n_valid == g.n_pad && g.out_ld % 8 == 0 && g.out_w % 8 == 0;
@@ -737,14 +958,16 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
       for (int kslab = gcd; kslab >= 16; kslab >>= 1) {
         const int span = kslab * 2;
         const int stage_bytes = (kHPx * span + 1023) & ~1023;
-        const int b_total = 9 * cin * bn * 2;  // independent of the slab size
-        int st = ((227 * 1024 - h.misc - b_total - 4 * o_bytes) / stage_bytes) & ~1;
+        const int b_total = h.ntap_w * cin * bn * 2;  // independent of the slab size
+        const int dw_bytes = dw ? 128 * span : 0;
+        int st = ((227 * 1024 - h.misc - b_total - 4 * o_bytes - 4 * dw_bytes) / stage_bytes) & ~1;
         if (st > kHMaxStages) st = kHMaxStages;
         if (st >= (pass <= 1 ? 4 : 2)) {
           h.kslab = kslab; h.nslab = cin / kslab; h.nslab0 = (int)g.a_c[0] / kslab; h.span = span;
           h.stage_bytes = stage_bytes; h.split = split; h.bn = bn; h.b_slot = bn * span; h.stages = st;
           h.ostore = pass == 0 ? 1 : 0; h.o_bytes = o_bytes;
-          h.smem = st * stage_bytes + 4 * o_bytes + b_total + h.misc;
+          h.dw_bytes = dw_bytes;
+          h.smem = st * stage_bytes + 4 * o_bytes + 4 * dw_bytes + b_total + h.misc;
           return true;
         }
       }
@@ -811,6 +1034,14 @@ int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
       if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
     }
   }
+  p.dw_w = g.dw_w;
+  p.dw_n = (int)g.dw_n;
+  p.ntap_w = h.ntap_w;
+  p.dw_bytes = (uint32_t)h.dw_bytes;
+  if (g.dw_w) {
+    p.idesc_q = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.dw_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    p.idesc_r = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((p.bn - p.dw_n) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  }
   p.ostore = h.ostore;
   p.o_bytes = (uint32_t)h.o_bytes;
   if (p.ostore) {
@@ -855,7 +1086,7 @@ int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
 
 int conv3_halo_launch(const GemmLaunch& L, cudaStream_t stream) {
   const HaloKParams& p = *reinterpret_cast<const HaloKParams*>(L.kparams);
-  HaloKernel k = halo_kernel(L.flags);
+  HaloKernel k = halo_kernel(L.flags, p.dw_w != nullptr);
   if (!k) return DDIF_ERR_STATE;
   DDIF_CUDA_CHECK(launch_pdl(k, dim3(L.grid_x, L.grid_y), dim3(kHThreads), (size_t)L.smem_bytes, stream, p));
   return DDIF_OK;

@@ -309,6 +309,8 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], net: "UNetSR3") -> Dict[str, to
                     wr = torch.zeros(o_, dim, 3, 3, dtype=torch.float32, device=wq.device)
                     wr[:, :, 1, 1] = sd[q + ".attn_res.weight"].to(torch.float32)[:, :, 0, 0]
                     P[q + ".qcr.w"] = _pack_conv(torch.cat([wq, wr], 0))
+                    # depthwise mode of the same kernel: 1x1 weights [q.1 ; attn_res], the depthwise 3x3 runs inside the kernel
+                    P[q + ".q1r.w"] = _pack_conv(torch.cat([sd[q + ".q.1.weight"].to(torch.float32), sd[q + ".attn_res.weight"].to(torch.float32)], 0))
                     P[q + ".qcr.b"] = f32(torch.cat([sd[q + ".q.1.bias"].to(torch.float32), torch.zeros(o_, dtype=torch.float32, device=wq.device)]))
                 cd = sd[q + ".kv.0.weight"].shape[0]
                 P[q + ".kv0"] = f32(sd[q + ".kv.0.weight"].reshape(cd, 9))
@@ -364,6 +366,7 @@ class Schedule:
         self.film_offsets = None
         self.first_body_op = 0
         self.use_qconv = os.environ.get("DDIF_NO_QCONV") is None  # A/B switch for profiling only
+        self.use_dwq = os.environ.get("DDIF_NO_DWQ") is None      # A/B switch: in-kernel depthwise q path vs composed dense 3x3
 
     @staticmethod
     def _levels(net) -> int:
@@ -384,7 +387,7 @@ class Schedule:
 
     def _gemm(self, pb, label, srcs, weights, n_valid, out: Optional[Act], *, taps, stride=1, bias=None, film=None,
               film_ld=0, mod=None, residual: Optional[Act] = None, act=0, out_nchw=None, per_sample=(0, 0), w_s=None, out_hw=None,
-              gn=None, a_up=0, w_k=None, ref_flops=-1.0, residual_off=0):
+              gn=None, a_up=0, w_k=None, ref_flops=-1.0, residual_off=0, dw=None):
         """gn = (gamma_addr, beta_addr, act): fuse GroupNorm(+Swish) of the (single) source into the conv's loader, using the
         source's own statistics; a_up = 1: read the source through a nearest x2 up-sampling."""
         a0 = srcs[0]
@@ -406,7 +409,7 @@ class Schedule:
             stats=out.stats if (out is not None and out.stats is not None) else None,
             gn_stats=a0.stats if gn else None, gn_gamma=gn[0] if gn else None, gn_beta=gn[1] if gn else None, gn_eps=1e-5,
             gn_act=gn[2] if gn else 0, a_up=a_up, force_tma=0,
-            gn_stats2=srcs[1].stats if (gn and nseg == 2) else None)
+            gn_stats2=srcs[1].stats if (gn and nseg == 2) else None, dw_w=dw[0] if dw else None, dw_n=dw[1] if dw else 0)
         if gn:
             assert all(s.stats is not None for s in srcs), label
         m = a0.B * oh * ow
@@ -415,7 +418,11 @@ class Schedule:
             nbytes += m * n_valid * 2
         if mod is not None:
             nbytes += m * n_valid * 4
-        return pb.add("ddif_gemm_t", label=label, flops=2.0 * m * n_valid * k_total, traffic=nbytes, ref_flops=ref_flops, **fields)
+        flops = 2.0 * m * n_valid * k_total
+        if dw:  # in-kernel depthwise 3x3 (CUDA cores) + ONE tap on the tensor cores
+            cin = sum(s.C for s in srcs)
+            flops = 2.0 * m * cin * (9 + n_valid)
+        return pb.add("ddif_gemm_t", label=label, flops=flops, traffic=nbytes, ref_flops=ref_flops, **fields)
 
     def _gn(self, pb, label, src: Act, gamma, beta, act, src2: Optional[Act] = None, dw_w=None, name="gn"):
         C = src.C + (src2.C if src2 else 0)
@@ -597,9 +604,14 @@ class Schedule:
                 # prenorm_x -> [DW3x3 -> Conv1x1 | attn_res] as ONE tensor-core 3x3 conv over the virtual concat (x, skip) with
                 # the GroupNorm fused into its loader: channels [0, dim) = q, [dim, dim + o) = r = attn_res(x_hat)
                 qr = self._act(pb, q + ".qr", B, x.H, x.W, dim + o)
-                self._gemm(pb, q + ".qconv", [x, skip], [A[q + ".qcr.w"], A[q + ".qcr.w"] + 2 * x.C], dim + o, qr, taps=[9, 9], bias=A[q + ".qcr.b"],
-                           gn=(A[q + ".gamma"], A[q + ".beta"], 0), w_k=[dim, dim],
-                           ref_flops=2.0 * B * x.H * x.W * dim * (9 + dim + o))  # reference: depthwise 3x3 + 1x1 (q) + 1x1 (attn_res)
+                if self.use_dwq:  # depthwise 3x3 inside the kernel, one tensor-core tap (q from dw(x_hat), r from x_hat)
+                    self._gemm(pb, q + ".qconv", [x, skip], [A[q + ".q1r.w"], A[q + ".q1r.w"] + 2 * x.C], dim + o, qr, taps=[9, 9], w_s=[1, 1],
+                               bias=A[q + ".qcr.b"], gn=(A[q + ".gamma"], A[q + ".beta"], 0), w_k=[dim, dim], dw=(A[q + ".q0"], dim),
+                               ref_flops=2.0 * B * x.H * x.W * dim * (9 + dim + o))
+                else:             # composed dense 3x3 (9x the 1x1 FLOPs on the tensor cores)
+                    self._gemm(pb, q + ".qconv", [x, skip], [A[q + ".qcr.w"], A[q + ".qcr.w"] + 2 * x.C], dim + o, qr, taps=[9, 9], bias=A[q + ".qcr.b"],
+                               gn=(A[q + ".gamma"], A[q + ".beta"], 0), w_k=[dim, dim],
+                               ref_flops=2.0 * B * x.H * x.W * dim * (9 + dim + o))  # reference: depthwise 3x3 + 1x1 (q) + 1x1 (attn_res)
                 qs = self._act(pb, q + ".qs", B, x.H, x.W, dim)
                 pb.add("ddif_softmax_h_t", label=q + ".softmax_h", traffic=B * x.H * x.W * dim * 4, **{"in": qr.buf}, out=qs.buf, batch=B,
                        h=x.H, w=x.W, c=dim, scale=1.0, in_ld=dim + o)

@@ -84,6 +84,11 @@ typedef struct {
    * the fused GroupNorm then runs over the concatenation: gn_stats2 = (sum, sumsq) of segment 1, gamma/beta in concat
    * order.  Used for FWM q = Conv1x1(DW3x3(GN(cat))) with the two convs composed into one dense 3x3 (sr3_dwt.py:507-541). */
   const double* gn_stats2;
+  /* Depthwise mode of the fused 3x3 kernel (FWM q path, sr3_dwt.py:509-517,541,573): dw_w != NULL -> the (normalised) input goes
+   * through a depthwise 3x3 with weights dw_w[9][sum a_c] (fp32, tap = ky*3+kx, zero padding of the normalised tensor) INSIDE the
+   * kernel and `w` holds 1x1 weights ([1][n_pad][K], w_s = 1): output channels [0, dw_n) = w[0:dw_n] . dw3x3(a), channels
+   * [dw_n, n_valid) = w[dw_n:] . a (the un-convolved normalised input: attn_res(x_hat)).  Needs gn_stats. */
+  const float* dw_w; int64_t dw_n;
 } ddif_gemm_t;
 
 typedef struct { const float* x; const float* self_cond; void* out; int64_t batch, c, h, w, c_pad; } ddif_in_convert_t;

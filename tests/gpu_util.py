@@ -35,7 +35,8 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
 
 
 def gemm(srcs, weights, n_valid, *, taps, stride=1, bias=None, film=None, mod=None, residual=None, act=0,
-         per_sample=None, want_nchw=False, want_stats=False, out_hw=None, gn=None, a_up=0, force_tma=0, reuse=None, sync=True):
+         per_sample=None, want_nchw=False, want_stats=False, out_hw=None, gn=None, a_up=0, force_tma=0, reuse=None, sync=True, dw=None,
+         w_s=None):
     """Run DDIF_OP_GEMM on NHWC bf16 tensors; returns (out_nhwc_bf16 | out_nchw_f32, stats | None).
     gn = (stats[B,2] f64, gamma, beta, act) fuses GroupNorm(+Swish) of the source into the 3x3 kernel."""
     a0 = srcs[0]
@@ -55,7 +56,7 @@ def gemm(srcs, weights, n_valid, *, taps, stride=1, bias=None, film=None, mod=No
         "ddif_gemm_t", stream(),
         a=pad2([s.data_ptr() for s in srcs], None), a_ld=pad2([s.shape[3] for s in srcs], 0), a_c=pad2([s.shape[3] for s in srcs], 0),
         a_h=pad2([s.shape[1] for s in srcs], 0), a_w=pad2([s.shape[2] for s in srcs], 0), w=pad2([w.data_ptr() for w in weights], None),
-        w_s=pad2([w.shape[0] for w in weights], 0), w_k=pad2([w.shape[2] for w in weights], 0), taps=pad2(taps, 0),
+        w_s=pad2(list(w_s) if w_s else [w.shape[0] for w in weights], 0), w_k=pad2([w.shape[2] for w in weights], 0), taps=pad2(taps, 0),
         w_per_sample=pad2(ps, 0), nseg=nseg, stride=stride, batch=B, out_h=oh, out_w=ow, n_pad=n_pad, n_valid=n_valid,
         bias=bias.data_ptr() if bias is not None else None, film=film.data_ptr() if film is not None else None,
         film_ld=film.shape[1] if film is not None else 0, mod=mod.data_ptr() if mod is not None else None,
@@ -64,7 +65,8 @@ def gemm(srcs, weights, n_valid, *, taps, stride=1, bias=None, film=None, mod=No
         out_nchw=out_nchw.data_ptr() if out_nchw is not None else None, stats=stats.data_ptr() if stats is not None else None,
         gn_stats=gn[0].data_ptr() if gn else None, gn_gamma=gn[1].data_ptr() if gn else None, gn_beta=gn[2].data_ptr() if gn else None,
         gn_eps=1e-5, gn_act=gn[3] if gn else 0, a_up=a_up, force_tma=force_tma,
-        gn_stats2=gn[4].data_ptr() if (gn and len(gn) > 4 and gn[4] is not None) else None)
+        gn_stats2=gn[4].data_ptr() if (gn and len(gn) > 4 and gn[4] is not None) else None,
+        dw_w=dw[0].data_ptr() if dw else None, dw_n=dw[1] if dw else 0)
     if sync:
         torch.cuda.synchronize()
     return (out_nchw if want_nchw else out), stats

@@ -137,6 +137,56 @@ def test_concat_gn_conv3x3(name, B, H, W, c1, c2, Cout, act):
     _close(to_nchw_f32(plain), F.conv2d(torch.cat([f1, f2], 1), w.to(torch.bfloat16).float(), bias, padding=1), name + " plain")
 
 
+DWQ = [
+    # name, B, H, W, c1, c2 (0 = one segment), o (attn_res channels, 0 = none), act
+    ("dw64_32",    3, 64, 64, 32, 32, 32, 0),   # kslab 32: 64x64 level (dim 64, o 32)
+    ("dw96_32",    2, 64, 64, 64, 32, 32, 0),   # segments of different width (kslab 32)
+    ("dw128_64",   2, 32, 32, 64, 64, 64, 0),   # kslab 64: two columns per thread
+    ("dw48_16",    2, 24, 40, 32, 16, 16, 1),   # kslab 16, partial tiles, Swish
+    ("dw_single",  2, 16, 16, 64, 0, 0, 0),     # one segment, no attn_res part
+    ("dw_many",   40, 64, 64, 32, 32, 32, 0),   # persistent CTAs walk several tiles (both A buffers, both rings)
+    ("dw_many128", 48, 32, 32, 64, 64, 64, 0),
+]
+
+
+@pytest.mark.parametrize("name,B,H,W,c1,c2,o,act", DWQ, ids=[c[0] for c in DWQ])
+def test_depthwise_q_path(name, B, H, W, c1, c2, o, act):
+    """Depthwise mode: [q | r] = [Conv1x1(DW3x3(x_hat)) | attn_res(x_hat)], x_hat = GN(cat(x, skip)), with the depthwise 3x3
+    computed inside the kernel and ONE tensor-core tap (sr3_dwt.py:507-517,541,573)."""
+    x1 = _rand(B, c1, H, W, seed=51, scale=1.5) + 0.4
+    C = c1 + c2
+    wdw = _rand(C, 1, 3, 3, seed=53, scale=0.4)
+    wq = _rand(C, C, 1, 1, seed=54, scale=1.0 / math.sqrt(C))
+    wr = _rand(o, C, 1, 1, seed=55, scale=1.0 / math.sqrt(C)) if o else None
+    bias = _rand(C + o, seed=56)
+    gamma, beta = 1 + 0.1 * _rand(C, seed=57), 0.1 * _rand(C, seed=58)
+    st = lambda f: torch.stack([f.double().sum(dim=(1, 2, 3)), (f.double() ** 2).sum(dim=(1, 2, 3))], dim=1).contiguous()
+    a1 = nhwc_bf16(x1)
+    f1 = to_nchw_f32(a1)
+    srcs, feats, stats = [a1], [f1], [st(f1)]
+    if c2:
+        a2 = nhwc_bf16(_rand(B, c2, H, W, seed=52, scale=0.7) - 0.2)
+        srcs.append(a2); feats.append(to_nchw_f32(a2)); stats.append(st(feats[1]))
+    w11 = torch.cat([wq, wr], 0) if o else wq
+    ws = [pack_w(w11[:, :c1].contiguous())] + ([pack_w(w11[:, c1:].contiguous())] if c2 else [])
+    dw_flat = wdw.reshape(C, 9).t().contiguous()  # [9][C]
+    out, _ = gemm(srcs, ws, C + o, taps=[9] * len(srcs), w_s=[1] * len(srcs), bias=bias,
+                  gn=(stats[0], gamma, beta, act, stats[1] if c2 else None), dw=(dw_flat, C))
+    h = F.group_norm(torch.cat(feats, 1), 1, gamma, beta, eps=1e-5)
+    if act:
+        h = h * torch.sigmoid(h)
+    hb = h.to(torch.bfloat16).float()
+    d = F.conv2d(hb, wdw, None, padding=1, groups=C).to(torch.bfloat16).float()
+    ref = F.conv2d(d, wq.to(torch.bfloat16).float(), bias[:C])
+    if o:
+        ref = torch.cat([ref, F.conv2d(hb, wr.to(torch.bfloat16).float(), bias[C:])], 1)
+    got = to_nchw_f32(out)
+    assert rel_err(got[:, :C], ref[:, :C]) < 6e-3, rel_err(got[:, :C], ref[:, :C])
+    if o:
+        assert rel_err(got[:, C:], ref[:, C:]) < 6e-3, rel_err(got[:, C:], ref[:, C:])
+    assert float((got - ref).abs().max()) < 0.06 * float(ref.abs().max())
+
+
 def test_fused_upsample_conv_and_epilogue():
     B, H, W, C = 2, 16, 16, 64
     x = _rand(B, C, H, W, seed=31)

@@ -108,10 +108,9 @@ def test_executed_flops_match_reference_count():
     _, _, s = _schedule("wv3", 1, 64, 64)
     step = sum(op.flops for op in s.fwd.ops)
     cond = sum(op.flops for op in s.cnd.ops)
-    # 7.27 GF of reference-equivalent convs + 3.8 GF because the FWM q path (DW3x3 -> 1x1) and attn_res (1x1) run as one dense
-    # 3x3 on the tensor cores at the 16/32/64-pixel levels (9x the 1x1s' FLOPs, but neither the depthwise pass nor x_hat
-    # goes through HBM); the schedule also records the reference-equivalent FLOPs of every launch
-    assert 10.5e9 < step < 11.5e9
+    # executed == reference-equivalent work within a few percent: the FWM q path runs its depthwise 3x3 inside the conv kernel
+    # (CUDA cores) and ONE tensor-core tap; only the dim-192 block at the 16-pixel level still uses the composed dense 3x3
+    assert 7.2e9 < step < 7.9e9
     ref = sum(op.ref_flops for op in s.fwd.ops)
     assert 7.0e9 < ref < 7.6e9
 

@@ -46,6 +46,7 @@ struct alignas(64) HaloKParams {
   CUtensorMap tmA[2];  // activations of K segment 0 / 1 (virtual channel concat: torch.cat((x, skip), 1), sr3_dwt.py:212)
   CUtensorMap tmB[2];  // weights of segment 0 / 1
   CUtensorMap tmR;     // residual tile box (L2 prefetch only)
+  CUtensorMap tmRA;    // residual-as-operand mode: halo box of the residual tensor (kslab_r x 10 x 18 x 1), see `nslab_r`
   CUtensorMap tmO[2];  // output tile boxes for the TMA store: [0] 64-channel slabs (SWIZZLE_128B), [1] 32-channel remainder (SWIZZLE_64B)
   const float* dw_w;   // depthwise mode (see ddif_gemm_t.dw_w): [9][cin] fp32
   int dw_n;            // leading output channels fed by the depthwise result; the rest read the normalised input itself
@@ -56,6 +57,12 @@ struct alignas(64) HaloKParams {
   int has_res_map;
   int cin, kslab, nslab, span;
   int nslab0;          // slabs that come from segment 0
+  // Residual-as-operand mode (nslab_r > 0): the residual add `conv(x) + r` (sr3_dwt.py:326) runs on the tensor pipe as one more
+  // K segment with IDENTITY weights and only the centre tap, accumulated into the same TMEM tile.  The epilogue then has no
+  // residual loads (whose L2/HBM latency it could not hide: 25 % of the 64 -> 64 layers) and no residual math.  bf16 x 1.0 in fp32 is exact.
+  int nslab_r;         // residual slabs per tile (bn / kslab_r), appended after the `nslab` conv slabs; nslab_t = nslab + nslab_r
+  int nslab_t, kslab_r, span_r, ksteps_r;
+  uint32_t layout_r, r_slot_bytes;
   int batch, out_h, out_w;
   int tiles_x, tiles_y, num_tiles;
   int bn;
@@ -114,7 +121,7 @@ struct HaloIter {
   int sb, sy, sx, tiles_x, tiles_y, nslab;
   __device__ __forceinline__ void init(const HaloKParams& p, int start, int stride) {
     const int tpi = p.tiles_x * p.tiles_y;
-    tiles_x = p.tiles_x; tiles_y = p.tiles_y; nslab = p.nslab;
+    tiles_x = p.tiles_x; tiles_y = p.tiles_y; nslab = p.nslab_t;
     b = start / tpi;
     int r = start - b * tpi;
     ty = r / tiles_x; tx = r - ty * tiles_x;
@@ -150,15 +157,16 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
   const float hs = p.gn_act ? 0.5f : 1.0f;  // swish(t) = h*tanh(h) + h with h = t/2: the affine is pre-halved
   const uint32_t nst = (uint32_t)p.stages >> 1;  // stages of this group's ring
   // per-thread tables (tile independent): swizzled smem offset and halo (line, column) of each of the thread's chunks
-  uint32_t soff[NPASS];
-  int hyx[NPASS];  // hy << 8 | hx; rows past the halo get hy = 255 (never in bounds)
+  // one packed word per chunk (soff < 2^15: a stage is < 32 KB): bits 0..15 smem offset, 16..23 hx, 24..31 hy; rows past the halo
+  // get hy = 255 (never in bounds).  Two separate tables spilled to local memory at NPASS = 12 under the 96-register cap.
+  uint32_t tab[NPASS];
 #pragma unroll
   for (int k = 0; k < NPASS; ++k) {
     const int r = r0 + k * RPP;
     const int hy = r / kHW, hx = r - hy * kHW;
     const uint32_t sw = NCK == 8 ? ((uint32_t)r & 7u) : (NCK == 4 ? (((uint32_t)r >> 1) & 3u) : (((uint32_t)r >> 2) & 1u));
-    soff[k] = (uint32_t)r * (uint32_t)(NCK * 16) + (((uint32_t)c ^ sw) << 4);
-    hyx[k] = r < kHPx ? ((hy << 8) | hx) : (255 << 8);
+    const uint32_t so = (uint32_t)r * (uint32_t)(NCK * 16) + (((uint32_t)c ^ sw) << 4);
+    tab[k] = so | (r < kHPx ? (((uint32_t)hy << 24) | ((uint32_t)hx << 16)) : (255u << 24));
   }
   const bool act = p.gn_act != 0;
   const unsigned H = (unsigned)p.out_h, W = (unsigned)p.out_w;
@@ -170,6 +178,13 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
   int cur_b = -1, cur_slab = -1, tcount = 0;
   f32x2 a2[4], d2[4];
   for (; it.remaining > 0; it.next()) {
+    if (it.slab >= p.nslab) {  // residual slab (identity-weight K segment): TMA -> MMA untouched, this group only relays the barrier
+      mbar_wait(&a_tma[stage], phase);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&a_ready[stage]);
+      if (++stage == nst) { stage = 0; phase ^= 1u; }
+      continue;
+    }
     if (it.b != cur_b || it.slab != cur_slab) {
       cur_b = it.b; cur_slab = it.slab;
       float mean, rstd;
@@ -205,8 +220,8 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
       bool ok[BATCH];
 #pragma unroll
       for (int k = 0; k < BATCH; ++k) {
-        ok[k] = (unsigned)(y0 + (hyx[k0 + k] >> 8)) < H && (unsigned)(x0 + (hyx[k0 + k] & 255)) < W;
-        v[k] = h_lds128(sbase + soff[k0 + k]);
+        ok[k] = (unsigned)(y0 + (int)(tab[k0 + k] >> 24)) < H && (unsigned)(x0 + (int)((tab[k0 + k] >> 16) & 255u)) < W;
+        v[k] = h_lds128(sbase + (tab[k0 + k] & 0xffffu));
       }
 #pragma unroll
       for (int k = 0; k < BATCH; ++k) {
@@ -215,14 +230,16 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           f32x2 t = fma2(bf2_to_f2(w[q]), a2[q], d2[q]);
+#ifndef DDIF_VAR_NO_TANH
           if (act) t = swish_half2(t);
+#endif
           o[q] = f2_to_bf2(t);
         }
         v[k] = make_uint4(o[0], o[1], o[2], o[3]);
       }
 #pragma unroll
       for (int k = 0; k < BATCH; ++k)
-        if (ok[k]) h_sts128(sbase + soff[k0 + k], v[k]);
+        if (ok[k]) h_sts128(sbase + (tab[k0 + k] & 0xffffu), v[k]);
     }
 #endif
     if (tid == 0) h_ts(dts, 3, tcount, 2);
@@ -254,6 +271,11 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
   a_full += (uint32_t)w * nst; a_empty += (uint32_t)w * nst;
   a_base += (uint32_t)w * nst * p.stage_bytes;
   const uint64_t desc_a0 = make_smem_desc(a_base, (uint32_t)kHW * span, p.layout_type);  // SBO = one halo line (10 rows)
+  // residual-as-operand: centre tap (one line + one pixel into the halo) of a stage holding rows of span_r bytes; identity weights
+  // sit behind the conv weights
+  const uint32_t span_r = (uint32_t)p.span_r;
+  const uint64_t desc_r0 = make_smem_desc(a_base + (uint32_t)(kHW + 1) * span_r, (uint32_t)kHW * span_r, p.layout_r);
+  const uint64_t desc_br0 = make_smem_desc(b_base + (uint32_t)(9 * p.nslab) * p.b_slot_bytes, 8u * span_r, p.layout_r);
   uint32_t stage = 0, phase = 0;
   mbar_wait(b_full, 0u);
   tc_fence_after();
@@ -279,6 +301,15 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
         db += b16;
       }
 #endif
+      umma_commit_elect(&a_empty[stage]);
+      if (++stage == nst) { stage = 0; phase ^= 1u; }
+    }
+    for (int rs = 0; rs < p.nslab_r; ++rs) {  // + residual: centre tap of the residual's halo stage x identity weights
+      mbar_wait(&a_full[stage], phase);
+      tc_fence_after();
+      const uint64_t da = desc_r0 + (uint64_t)(stage * stage16);
+      const uint64_t dbr = desc_br0 + (uint64_t)((uint32_t)rs * (p.r_slot_bytes >> 4));
+      for (int k = 0; k < p.ksteps_r; ++k) umma_bf16_ss_steps<1>(tmem_d, da + (uint64_t)(2 * k), dbr + (uint64_t)(2 * k), p.idesc, 1u);
       umma_commit_elect(&a_empty[stage]);
       if (++stage == nst) { stage = 0; phase ^= 1u; }
     }
@@ -556,11 +587,17 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
       }
     }
     uint32_t rs0[8], rs1[8];
+#ifdef DDIF_VAR_NO_RESLD
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rs0[j] = rs1[j] = 0u;
+#endif
     if (kRes) {  // first two 16-channel chunks of the residual travel while the MMAs finish
+#ifndef DDIF_VAR_NO_RESLD
       if (row_ok) {
         ldg256(res_px, rs0);
         if (nch > 1) ldg256(res_px + 16, rs1);
       }
+#endif
     }
     const uint32_t acc = (uint32_t)grp + (four ? 2u * (it & 1u) : 0u);
     const uint32_t tm_lane = tm_lane0 + acc * (uint32_t)p.bn;
@@ -641,7 +678,9 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
             h_sts128(a0s, make_uint4(w[0], w[1], w[2], w[3]));
             h_sts128(a1s, make_uint4(w[4], w[5], w[6], w[7]));
           } else {
+#ifndef DDIF_VAR_NO_STG
             stg256(outp + pix * (size_t)out_ld + ng, w);
+#endif
           }
         }
       } else {  // ragged last chunk (n_valid % 16 != 0): scalar path
@@ -664,10 +703,12 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
     for (int cc = 0; cc < nch; cc += 2) {
       uint32_t a0[16], a1[16];
       const bool two = cc + 1 < nch;
+#ifndef DDIF_VAR_NO_RESLD
       if (kRes && cc > 0 && row_ok) {
         ldg256(res_px + cc * 16, rs0);
         if (two) ldg256(res_px + cc * 16 + 16, rs1);
       }
+#endif
       tmem_ld16(tm_lane + (uint32_t)(cc * 16), a0);
       if (two) tmem_ld16(tm_lane + (uint32_t)(cc * 16 + 16), a1);
       tmem_ld_wait();
@@ -693,6 +734,7 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
       }
     }
     if (warp == 10 && lane == 0) h_ts(dts, 2, t, 2);
+#ifndef DDIF_VAR_NO_STATRED
     if (kStats) {
       float l1, h1, l2, h2;
       upk2(s1, l1, h1);
@@ -703,6 +745,9 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
         atomicAdd(stats + 2 * (size_t)b + 1, (double)t2);
       }
     }
+#else
+    if (kStats) { float l1, h1; upk2(add2(s1, s2), l1, h1); if (l1 + h1 == 1.2345f) atomicAdd(stats, 1.0); }
+#endif
     if (warp == 10 && lane == 0) h_ts(dts, 2, t, 3);
     tx += sx; ty += sy; b += sb;
     if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
@@ -721,7 +766,8 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   uint8_t* smem_o = smem + (size_t)p.stages * p.stage_bytes;  // [4][o_bytes] output staging (1024-byte aligned), only with ostore
   uint8_t* smem_dw = smem_o + (p.ostore ? 4u * p.o_bytes : 0u);  // [4][dw_bytes] depthwise A buffers (2 per half-pipeline), only in depthwise mode
   uint8_t* smem_b = smem_dw + (DW ? 4u * p.dw_bytes : 0u);
-  float* s_gamma = reinterpret_cast<float*>(smem_b + (size_t)(p.ntap_w * p.nslab) * p.b_slot_bytes);
+  uint8_t* smem_id = smem_b + (size_t)(p.ntap_w * p.nslab) * p.b_slot_bytes;  // [nslab_r][bn rows x span_r] identity weights (residual-as-operand)
+  float* s_gamma = reinterpret_cast<float*>(smem_id + (size_t)p.nslab_r * p.r_slot_bytes);
   float* s_beta = s_gamma + p.cin;
   float2* s_stat = reinterpret_cast<float2*>(s_beta + p.cin);
   const int n_stat = p.gn_stats ? (p.batch < kHMaxStat ? p.batch : kHMaxStat) : 0;
@@ -750,6 +796,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
       tma_prefetch_desc(&p.tmO[0]);
       tma_prefetch_desc(&p.tmO[1]);
     }
+    if (p.nslab_r) tma_prefetch_desc(&p.tmRA);
     if (p.nslab0 < p.nslab) {
       tma_prefetch_desc(&p.tmA[1]);
       tma_prefetch_desc(&p.tmB[1]);
@@ -774,6 +821,21 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
+  if (p.nslab_r) {
+    // Identity weights, K-major rows in the UMMA swizzle of span_r (address bits [4, 4+b) ^= bits [7, 7+b)): row n (output channel
+    // n0 + n of this CTA) has its single 1.0 at residual channel n, i.e. slab n / kslab_r, column n % kslab_r.
+    const uint32_t idb = smem_u32(smem_id), words = ((uint32_t)p.nslab_r * p.r_slot_bytes) >> 4;
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) h_sts128(idb + (i << 4), make_uint4(0u, 0u, 0u, 0u));
+    __syncthreads();
+    const uint32_t msk = p.span_r == 128 ? 7u : (p.span_r == 64 ? 3u : 1u);
+    for (int n = threadIdx.x; n < p.bn; n += blockDim.x) {
+      const uint32_t rs = (uint32_t)n / (uint32_t)p.kslab_r, k = (uint32_t)n % (uint32_t)p.kslab_r;
+      uint32_t a = idb + rs * p.r_slot_bytes + (uint32_t)n * (uint32_t)p.span_r + k * 2u;
+      a ^= ((a >> 7) & msk) << 4;
+      asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"((unsigned short)0x3F80) : "memory");  // bf16 1.0
+    }
+    h_fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -787,18 +849,20 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
                     (slab >= p.nslab0 ? slab - p.nslab0 : slab) * p.kslab, (int)blockIdx.y * p.bn, tap);
   }
   pdl_wait();  // everything below reads what earlier kernels of the step wrote
-  if (gn) {
-    for (int i = threadIdx.x; i < p.cin; i += blockDim.x) {
-      s_gamma[i] = p.gn_gamma[i];
-      s_beta[i] = p.gn_beta[i];
-    }
-    for (int i = threadIdx.x; i < n_stat; i += blockDim.x) s_stat[i] = halo_mean_rstd(p, i);  // fp64 once per CTA
-    if (DW)
-      for (int i = threadIdx.x; i < 9 * p.cin; i += blockDim.x) s_dw[i] = p.dw_w[i];
-    __syncthreads();
-  }
 
   if (warp < 8) {
+    if (gn) {
+      // GroupNorm tables are private to the transform warps: the TMA producer, the MMA issuers and the epilogue warps start
+      // their loops right after the dependency wait instead of behind this block's global loads + fp64 math.
+      for (int i = threadIdx.x; i < p.cin; i += kHxfThreads) {
+        s_gamma[i] = p.gn_gamma[i];
+        s_beta[i] = p.gn_beta[i];
+      }
+      for (int i = threadIdx.x; i < n_stat; i += kHxfThreads) s_stat[i] = halo_mean_rstd(p, i);  // fp64 once per CTA
+      if (DW)
+        for (int i = threadIdx.x; i < 9 * p.cin; i += kHxfThreads) s_dw[i] = p.dw_w[i];
+      named_bar_sync(5, kHxfThreads);
+    }
     // ===================== transform warps (only with the GroupNorm prologue) =====================
     if constexpr (DW) {
       const uint32_t a_base = smem_u32(smem_a), dwb = smem_u32(smem_dw);
@@ -831,27 +895,40 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
       const uint32_t nst = (uint32_t)p.stages >> 1;  // per ring
       HaloIter it;
       it.init(p, (int)blockIdx.x, (int)gridDim.x);
-      uint32_t rs[2] = {0u, 0u}, rp[2] = {0u, 0u};  // (stage, phase) of ring 0 / 1
+      // (stage, phase) of ring 0 / 1 as scalars: a run-time indexed rs[ring] lives in LOCAL memory (LDL/STL on the producer's
+      // dependent chain every tile)
+      uint32_t st0 = 0u, ph0 = 0u, st1 = 0u, ph1 = 0u;
       uint32_t ring = 0;
       int u = 0;
       for (; it.remaining > 0; it.next(), ++u) {
-        const uint32_t stage = ring * nst + rs[ring];
+        const uint32_t rs = ring ? st1 : st0, rp = ring ? ph1 : ph0;
+        const uint32_t stage = ring * nst + rs;
         h_ts(dts, 0, u, 0);
-        mbar_wait(&a_empty[stage], rp[ring] ^ 1u);
+        mbar_wait(&a_empty[stage], rp ^ 1u);
         h_ts(dts, 0, u, 1);
 #ifdef DDIF_VAR_NO_TMA
         mbar_arrive(&a_tma[stage]);
 #else
-        mbar_expect_tx(&a_tma[stage], tx);
-        const int seg = it.slab >= p.nslab0;
-        tma_load_4d(&p.tmA[seg], &a_tma[stage], smem_a + (size_t)stage * p.stage_bytes, (seg ? it.slab - p.nslab0 : it.slab) * p.kslab, it.tx * 8 - 1,
-                    it.ty * 16 - 1, it.b);
+        if (it.slab >= p.nslab) {  // residual slab of this CTA's N range
+          mbar_expect_tx(&a_tma[stage], (uint32_t)(kHPx * p.span_r));
+          tma_load_4d(&p.tmRA, &a_tma[stage], smem_a + (size_t)stage * p.stage_bytes, (int)blockIdx.y * p.bn + (it.slab - p.nslab) * p.kslab_r,
+                      it.tx * 8 - 1, it.ty * 16 - 1, it.b);
+        } else {
+          mbar_expect_tx(&a_tma[stage], tx);
+          const int seg = it.slab >= p.nslab0;
+          tma_load_4d(&p.tmA[seg], &a_tma[stage], smem_a + (size_t)stage * p.stage_bytes, (seg ? it.slab - p.nslab0 : it.slab) * p.kslab, it.tx * 8 - 1,
+                      it.ty * 16 - 1, it.b);
+        }
 #endif
 #ifndef DDIF_VAR_NO_RESPF
         if (p.has_res_map && it.slab == 0) tma_prefetch_l2_4d(&p.tmR, (int)blockIdx.y * p.bn, it.tx * 8, it.ty * 16, it.b);  // residual tile -> L2, `stages` tiles ahead
 #endif
-        if (++rs[ring] == nst) { rs[ring] = 0; rp[ring] ^= 1u; }
-        if (it.slab == p.nslab - 1) ring ^= 1u;  // next tile -> other half-pipeline
+        {
+          uint32_t ns = rs + 1u, np = rp;
+          if (ns == nst) { ns = 0u; np ^= 1u; }
+          if (ring) { st1 = ns; ph1 = np; } else { st0 = ns; ph0 = np; }
+        }
+        if (it.slab == p.nslab_t - 1) ring ^= 1u;  // next tile -> other half-pipeline
       }
       pdl_trigger();  // all loads of this CTA are in flight: the next kernel's CTAs may take over SMs as ours exit
     }
@@ -880,8 +957,17 @@ PFN_encodeTiled ddif_get_encode();
 int ddif_sm_count();
 
 typedef void (*HaloKernel)(const HaloKParams);
+// Residual-as-operand (HaloKParams::nslab_r): needs a TMA-addressable residual (16-byte aligned base and pixel pitch).
+// DDIF_NO_RESMMA=1 keeps the epilogue-side residual add (A/B switch for profiling).
+static bool halo_res_mma(const ddif_gemm_t& g) {
+  static const bool off = getenv("DDIF_NO_RESMMA") != nullptr;
+  // Measured on B200 (layer_bench, B = 256): 32 -> 32 @64^2 66.9 -> 65.8 us, 64 -> 32 @64^2 71.4 -> 67.3 us, but 64 -> 64 @32^2 35.4 -> 38.7 us and
+  // 128 -> 64 @32^2 40.9 -> 58.8 us: with N >= 64 the resident weights leave only 2-3 halo stages per ring and the extra residual
+  // stage per tile starves the conv slabs.  Enabled for N <= 32 only.
+  return !off && g.residual && !g.dw_w && g.n_pad <= 32 && g.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(g.residual) & 15u) == 0;
+}
 static int halo_flags(const ddif_gemm_t& g) {
-  return (g.residual ? kEpiRes : 0) | (g.act ? kEpiAct : 0) | (g.stats ? kEpiStats : 0) | (g.out_nchw ? kEpiNchw : 0);
+  return ((g.residual && !halo_res_mma(g)) ? kEpiRes : 0) | (g.act ? kEpiAct : 0) | (g.stats ? kEpiStats : 0) | (g.out_nchw ? kEpiNchw : 0);
 }
 static HaloKernel halo_kernel(int f, bool dw = false) {
   if (dw) return f == 0 ? conv3x3_halo_tc_kernel<0, true> : nullptr;  // the q path: bias only, bf16 NHWC output
@@ -910,7 +996,7 @@ static cudaError_t halo_set_attrs() {
 }
 
 struct HaloGeom {
-  int cin, kslab, nslab, nslab0, span, stages, stage_bytes, b_slot, n_stat, misc, smem, split, bn, ostore, o_bytes, ntap_w, dw_bytes;
+  int cin, kslab, nslab, nslab0, span, stages, stage_bytes, b_slot, n_stat, misc, smem, split, bn, ostore, o_bytes, ntap_w, dw_bytes, kslab_r, r_total;
 };
 
 static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
@@ -928,6 +1014,7 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
   }
   if (cin > 512) return false;
   const bool dw = g.dw_w != nullptr;
+  const bool res_mma = halo_res_mma(g);
   if (dw && (!g.gn_stats || g.dw_n < 16 || g.dw_n % 16 != 0 || g.dw_n > g.n_pad || (g.n_pad - g.dw_n) % 16 != 0 || g.n_valid != g.n_pad)) return false;
   if (g.nseg == 2 && g.gn_stats && !g.gn_stats2) return false;
   if (g.mod || halo_kernel(halo_flags(g), g.dw_w != nullptr) == nullptr) return false;  // CSM modulation / fp32 store + residual: generic kernel
@@ -960,14 +1047,21 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
         const int stage_bytes = (kHPx * span + 1023) & ~1023;
         const int b_total = h.ntap_w * cin * bn * 2;  // independent of the slab size
         const int dw_bytes = dw ? 128 * span : 0;
-        int st = ((227 * 1024 - h.misc - b_total - 4 * o_bytes - 4 * dw_bytes) / stage_bytes) & ~1;
+        int kslab_r = 0;
+        if (res_mma) {
+          kslab_r = 64;
+          while (bn % kslab_r != 0 || kslab_r > kslab) kslab_r >>= 1;  // bn % 16 == 0, kslab >= 16: terminates at >= 16
+        }
+        const int r_total = res_mma ? bn * bn * 2 : 0;  // identity weights: (bn / kslab_r) slots of bn rows x kslab_r columns
+        int st = ((227 * 1024 - h.misc - b_total - r_total - 4 * o_bytes - 4 * dw_bytes) / stage_bytes) & ~1;
         if (st > kHMaxStages) st = kHMaxStages;
         if (st >= (pass <= 1 ? 4 : 2)) {
           h.kslab = kslab; h.nslab = cin / kslab; h.nslab0 = (int)g.a_c[0] / kslab; h.span = span;
           h.stage_bytes = stage_bytes; h.split = split; h.bn = bn; h.b_slot = bn * span; h.stages = st;
           h.ostore = pass == 0 ? 1 : 0; h.o_bytes = o_bytes;
           h.dw_bytes = dw_bytes;
-          h.smem = st * stage_bytes + 4 * o_bytes + 4 * dw_bytes + b_total + h.misc;
+          h.kslab_r = kslab_r; h.r_total = r_total;
+          h.smem = st * stage_bytes + 4 * o_bytes + 4 * dw_bytes + b_total + r_total + h.misc;
           return true;
         }
       }
@@ -1058,7 +1152,22 @@ int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
       if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
     }
   }
-  if (g.residual) {
+  p.nslab_t = p.nslab;
+  p.span_r = p.span; p.layout_r = p.layout_type;  // harmless defaults (descriptors are built even when unused)
+  if (h.kslab_r) {
+    p.kslab_r = h.kslab_r; p.nslab_r = p.bn / h.kslab_r; p.nslab_t = p.nslab + p.nslab_r;
+    p.span_r = h.kslab_r * 2; p.ksteps_r = h.kslab_r / 16;
+    p.layout_r = p.span_r == 128 ? 2u : p.span_r == 64 ? 4u : 6u;
+    p.r_slot_bytes = (uint32_t)(p.bn * p.span_r);
+    cuuint64_t dims[4] = {(cuuint64_t)g.n_valid, (cuuint64_t)g.out_w, (cuuint64_t)g.out_h, (cuuint64_t)g.batch};
+    cuuint64_t strides[3] = {(cuuint64_t)g.res_ld * 2, (cuuint64_t)g.out_w * g.res_ld * 2, (cuuint64_t)g.out_h * g.out_w * g.res_ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)h.kslab_r, (cuuint32_t)kHW, (cuuint32_t)kHH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUtensorMapSwizzle swr = p.span_r == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : p.span_r == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    if (enc(&p.tmRA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g.residual), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swr,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return DDIF_ERR_DRIVER;
+  } else if (g.residual) {
     const int nb = (int)(g.n_valid < p.bn ? g.n_valid : p.bn) / 8 * 8;
     cuuint64_t dims[4] = {(cuuint64_t)g.n_valid, (cuuint64_t)g.out_w, (cuuint64_t)g.out_h, (cuuint64_t)g.batch};
     cuuint64_t strides[3] = {(cuuint64_t)g.res_ld * 2, (cuuint64_t)g.out_w * g.res_ld * 2, (cuuint64_t)g.out_h * g.out_w * g.res_ld * 2};

@@ -36,6 +36,12 @@ union OpParams {
   ddif_cond_assemble_t cond_assemble;
   ddif_randn_t randn;
   ddif_axpby_clip_t axpby_clip;
+  ddif_dpm_single_t dpm_single;
+  ddif_loss_t loss;
+  ddif_axpby_t axpby;
+  ddif_metrics_t metrics;
+  ddif_tile_t tile;
+  ddif_wavelet_cond_t wavelet_cond;
 };
 
 static size_t params_size(int kind) {
@@ -62,6 +68,12 @@ static size_t params_size(int kind) {
     case DDIF_OP_COND_ASSEMBLE: return sizeof(ddif_cond_assemble_t);
     case DDIF_OP_RANDN: return sizeof(ddif_randn_t);
     case DDIF_OP_AXPBY_CLIP: return sizeof(ddif_axpby_clip_t);
+    case DDIF_OP_DPM_SINGLE: return sizeof(ddif_dpm_single_t);
+    case DDIF_OP_LOSS: return sizeof(ddif_loss_t);
+    case DDIF_OP_AXPBY: return sizeof(ddif_axpby_t);
+    case DDIF_OP_METRICS: return sizeof(ddif_metrics_t);
+    case DDIF_OP_TILE: return sizeof(ddif_tile_t);
+    case DDIF_OP_WAVELET_COND: return sizeof(ddif_wavelet_cond_t);
     default: return 0;
   }
 }
@@ -99,6 +111,12 @@ static int dispatch(const Op& op, cudaStream_t s) {
     case DDIF_OP_COND_ASSEMBLE: return launch_cond_assemble(op.p.cond_assemble, s);
     case DDIF_OP_RANDN: return launch_randn(op.p.randn, s);
     case DDIF_OP_AXPBY_CLIP: return launch_axpby_clip(op.p.axpby_clip, s);
+    case DDIF_OP_DPM_SINGLE: return launch_dpm_single(op.p.dpm_single, s);
+    case DDIF_OP_LOSS: return launch_loss(op.p.loss, s);
+    case DDIF_OP_AXPBY: return launch_axpby(op.p.axpby, s);
+    case DDIF_OP_METRICS: return launch_metrics(op.p.metrics, s);
+    case DDIF_OP_TILE: return launch_tile(op.p.tile, s);
+    case DDIF_OP_WAVELET_COND: return launch_wavelet_cond(op.p.wavelet_cond, s);
     default: return DDIF_ERR_ARG;
   }
 }
@@ -255,6 +273,11 @@ int ddif_cond_assemble_f32(const ddif_cond_assemble_t* p, ddif_stream_t s) { ret
 int ddif_ddpm_step_f32(const ddif_ddpm_step_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_DDPM_STEP, p, s); }
 int ddif_ddim_step_f32(const ddif_ddim_step_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_DDIM_STEP, p, s); }
 int ddif_dpmpp_step_f32(const ddif_dpmpp_step_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_DPMPP_STEP, p, s); }
+int ddif_dpm_single_f32(const ddif_dpm_single_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_DPM_SINGLE, p, s); }
+int ddif_loss_f32(const ddif_loss_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_LOSS, p, s); }
+int ddif_metrics_f32(const ddif_metrics_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_METRICS, p, s); }
+int ddif_tile_f32(const ddif_tile_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_TILE, p, s); }
+int ddif_wavelet_cond_f32(const ddif_wavelet_cond_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_WAVELET_COND, p, s); }
 int ddif_q_sample_f32(const ddif_q_sample_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_Q_SAMPLE, p, s); }
 int ddif_conv_igemm_bf16(const ddif_gemm_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_GEMM, p, s); }
 

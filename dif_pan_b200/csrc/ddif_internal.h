@@ -51,5 +51,11 @@ int launch_haar_idwt2(const ddif_haar_t& p, cudaStream_t s);
 int launch_cond_assemble(const ddif_cond_assemble_t& p, cudaStream_t s);
 int launch_randn(const ddif_randn_t& p, cudaStream_t s);
 int launch_axpby_clip(const ddif_axpby_clip_t& p, cudaStream_t s);
+int launch_dpm_single(const ddif_dpm_single_t& p, cudaStream_t s);
+int launch_loss(const ddif_loss_t& p, cudaStream_t s);
+int launch_axpby(const ddif_axpby_t& p, cudaStream_t s);
+int launch_metrics(const ddif_metrics_t& p, cudaStream_t s);
+int launch_tile(const ddif_tile_t& p, cudaStream_t s);
+int launch_wavelet_cond(const ddif_wavelet_cond_t& p, cudaStream_t s);
 
 }  // namespace ddif

@@ -1,0 +1,241 @@
+// Kernels on either side of the sampling loop (SURVEY.md section 8(f) "next" rows N1, N2, N4 and the forward half of S9):
+//   fused conditioning prep  raw lms, pan -> cond        /root/reference/dataset/pan_dataset.py:73-142, dataset/hisr.py:48-59,
+//                                                        diffusion_engine.py:221-228
+//   scene <-> patch batch    tiling / overlap-averaged stitching around diffusion_engine.py:351-505 (the reference feeds whole scenes)
+//   training objective       sum_b w[t_b] * l1/l2        diffusion_ddpm_pan.py:725-762
+//   per-sample axpby         predict_start_from_noise / predict_v / predict_start_from_v   diffusion_ddpm_pan.py:284-312
+//   validation metrics       SAM / ERGAS / PSNR / CC partial sums   utils/_metric_legacy.py:299-346,365
+// All memory-bound, fp32 in / fp64 accumulators, coalesced along the pixel axis.
+#include "common.cuh"
+#include "ddif_internal.h"
+
+namespace ddif {
+
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define SUB(a, b) __fsub_rn((a), (b))
+#define DIV(a, b) __fdiv_rn((a), (b))
+
+static inline int pgrid(int64_t items, int threads = 256) {
+  int64_t b = ceil_div(items, threads);
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)(b < 1 ? 1 : b);
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = l < (int)(blockDim.x >> 5) ? sh[l] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;  // valid in thread 0
+}
+
+// ---- fused conditioning prep ----------------------------------------------------------------------------------------
+// Haar coefficient k (0 LL, 1 cH, 2 cV, 3 cD) of the 2x2 block (by, bx) of one plane, divided by dv -- same expressions as
+// haar_dwt2_kernel (sampler.cu), so the fused path is bit-identical to DWT -> cat -> cond_assemble.
+__device__ __forceinline__ float haar_coef(const float* __restrict__ pl, int w, int by, int bx, int k, float dv) {
+  const float2 r0 = *reinterpret_cast<const float2*>(pl + (size_t)(2 * by) * w + 2 * bx);
+  const float2 r1 = *reinterpret_cast<const float2*>(pl + (size_t)(2 * by + 1) * w + 2 * bx);
+  const float ab = ADD(r0.x, r0.y), cd = ADD(r1.x, r1.y), amb = SUB(r0.x, r0.y), cmd = SUB(r1.x, r1.y);
+  float v;
+  if (k == 0) v = ADD(ab, cd);
+  else if (k == 1) v = SUB(ab, cd);
+  else if (k == 2) v = ADD(amb, cmd);
+  else v = SUB(amb, cmd);
+  return DIV(MUL(v, 0.5f), dv);
+}
+
+__global__ void wavelet_cond_kernel(ddif_wavelet_cond_t p) {
+  const int c = (int)p.c, pp = (int)p.p, h = (int)p.h, w = (int)p.w, hh = h / 2, wh = w / 2;
+  const int cw = c + 3 * pp, ct = c + pp + cw;
+  const int64_t hw = (int64_t)h * w;
+  const int64_t items = p.batch * ct * hw;
+  const float dv = (float)p.divisor;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i % hw;
+    const int ch = (int)((i / hw) % ct);
+    const int64_t b = i / (hw * ct);
+    float v;
+    if (ch < c) {
+      v = DIV(p.lms[(b * c + ch) * hw + pix], dv);
+    } else if (ch < c + pp) {
+      v = DIV(p.pan[(b * pp + (ch - c)) * hw + pix], dv);
+    } else {
+      const int k = ch - c - pp;  // wavelet channel: [LL(lms) x c | pan sub-band 0 x p | sub-band 1 x p | sub-band 2 x p]
+      const float* pl;
+      int coef;
+      if (k < c) {
+        pl = p.lms + (b * c + k) * hw;
+        coef = 0;
+      } else {
+        const int g = (k - c) / pp, j = (k - c) % pp;
+        pl = p.pan + (b * pp + j) * hw;
+        coef = p.order == 0 ? (g == 0 ? 1 : (g == 1 ? 3 : 2)) : g + 1;  // Pan: h, d, v;  HISR: h, v, d
+      }
+      const int oy = (int)(pix / w), ox = (int)(pix % w);
+      float sy = 0.5f * ((float)oy + 0.5f) - 0.5f, sx = 0.5f * ((float)ox + 0.5f) - 0.5f;
+      if (sy < 0.f) sy = 0.f;
+      if (sx < 0.f) sx = 0.f;
+      int y0 = (int)sy, x0 = (int)sx;
+      if (y0 > hh - 1) y0 = hh - 1;
+      if (x0 > wh - 1) x0 = wh - 1;
+      const int y1 = y0 + (y0 < hh - 1 ? 1 : 0), x1 = x0 + (x0 < wh - 1 ? 1 : 0);
+      const float ly1 = sy - (float)y0, ly0 = 1.f - ly1, lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+      const float v00 = haar_coef(pl, w, y0, x0, coef, dv), v01 = haar_coef(pl, w, y0, x1, coef, dv);
+      const float v10 = haar_coef(pl, w, y1, x0, coef, dv), v11 = haar_coef(pl, w, y1, x1, coef, dv);
+      v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);  // same expression as cond_assemble_kernel
+      if (p.wav && !(oy & 1) && !(ox & 1))  // one thread per 2x2 block also emits the raw coefficient
+        p.wav[((b * cw + k) * hh + (oy >> 1)) * wh + (ox >> 1)] = haar_coef(pl, w, oy >> 1, ox >> 1, coef, dv);
+    }
+    p.cond[i] = v;
+  }
+}
+int launch_wavelet_cond(const ddif_wavelet_cond_t& p, cudaStream_t s) {
+  if (p.h % 2 || p.w % 2 || p.c < 1 || p.p < 1 || p.order < 0 || p.order > 1) return DDIF_ERR_SHAPE;
+  wavelet_cond_kernel<<<pgrid(p.batch * (2 * p.c + 4 * p.p) * p.h * p.w), 256, 0, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- scene <-> patch batch --------------------------------------------------------------------------------------------
+__global__ void tile_gather_kernel(ddif_tile_t p) {
+  const int64_t items = p.batch * p.ny * p.nx * p.c * p.ph * p.pw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int64_t x = r % p.pw; r /= p.pw;
+    const int64_t y = r % p.ph; r /= p.ph;
+    const int64_t ch = r % p.c; r /= p.c;
+    const int64_t ix = r % p.nx; r /= p.nx;
+    const int64_t iy = r % p.ny;
+    const int64_t b = r / p.ny;
+    p.tiles[i] = p.scene[((b * p.c + ch) * p.h + iy * p.sy + y) * p.w + ix * p.sx + x];
+  }
+}
+__global__ void tile_stitch_kernel(ddif_tile_t p) {
+  const int64_t items = p.batch * p.c * p.h * p.w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int64_t x = r % p.w; r /= p.w;
+    const int64_t y = r % p.h; r /= p.h;
+    const int64_t ch = r % p.c;
+    const int64_t b = r / p.c;
+    // tiles iy with iy*sy <= y < iy*sy + ph
+    int64_t iy1 = y / p.sy; if (iy1 > p.ny - 1) iy1 = p.ny - 1;
+    int64_t iy0 = y - p.ph + 1 <= 0 ? 0 : (y - p.ph + p.sy) / p.sy;
+    int64_t ix1 = x / p.sx; if (ix1 > p.nx - 1) ix1 = p.nx - 1;
+    int64_t ix0 = x - p.pw + 1 <= 0 ? 0 : (x - p.pw + p.sx) / p.sx;
+    float acc = 0.f;
+    int cnt = 0;
+    for (int64_t iy = iy0; iy <= iy1; ++iy)
+      for (int64_t ix = ix0; ix <= ix1; ++ix) {
+        acc += p.tiles[((((b * p.ny + iy) * p.nx + ix) * p.c + ch) * p.ph + (y - iy * p.sy)) * p.pw + (x - ix * p.sx)];
+        ++cnt;
+      }
+    p.scene[i] = cnt > 1 ? acc / (float)cnt : acc;
+  }
+}
+int launch_tile(const ddif_tile_t& p, cudaStream_t s) {
+  if (p.ph > p.h || p.pw > p.w || p.sy < 1 || p.sx < 1 || p.sy > p.ph || p.sx > p.pw) return DDIF_ERR_SHAPE;
+  if ((p.ny - 1) * p.sy + p.ph != p.h || (p.nx - 1) * p.sx + p.pw != p.w) return DDIF_ERR_SHAPE;  // tiles cover the scene exactly
+  if (p.dir == 0) tile_gather_kernel<<<pgrid(p.batch * p.ny * p.nx * p.c * p.ph * p.pw), 256, 0, s>>>(p);
+  else tile_stitch_kernel<<<pgrid(p.batch * p.c * p.h * p.w), 256, 0, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- training objective (forward) -----------------------------------------------------------------------------------------
+__global__ void loss_kernel(ddif_loss_t p) {
+  __shared__ double sh[8];
+  const int64_t n = p.batch * p.chw;
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = SUB(p.a[i], p.b[i]);
+    float l = p.squared == 0 ? fabsf(d) : MUL(d, d);
+    if (p.weight) l = MUL(l, p.weight[i / p.chw]);
+    acc += (double)l;
+  }
+  const double t = block_sum(acc, sh);
+  if (threadIdx.x == 0) atomicAdd(p.out, t);
+}
+int launch_loss(const ddif_loss_t& p, cudaStream_t s) {
+  if (p.squared < 0 || p.squared > 1 || !p.out) return DDIF_ERR_ARG;
+  loss_kernel<<<pgrid(p.batch * p.chw), 256, 0, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+__global__ void axpby_kernel(ddif_axpby_t p) {
+  const int64_t n = p.batch * p.chw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / p.chw;
+    p.out[i] = ADD(MUL(p.ca[b], p.x[i]), MUL(p.cb[b], p.y[i]));
+  }
+}
+int launch_axpby(const ddif_axpby_t& p, cudaStream_t s) {
+  axpby_kernel<<<pgrid(p.batch * p.chw), 256, 0, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- validation metrics: partial sums per image ---------------------------------------------------------------------------
+// grid (chunks, batch).  Pass 1 (blockIdx.z == 0): spectral angle per pixel; pass 2 (blockIdx.z = 1 + band): band sums.
+__global__ void metrics_kernel(ddif_metrics_t p) {
+  __shared__ double sh[8];
+  const int b = blockIdx.y;
+  const int c = (int)p.c, h = (int)p.h, w = (int)p.w;
+  const int hc = h - 1, wc = w - 1;  // bounds cut [0:-1] on both axes
+  const int64_t npix = (int64_t)hc * wc, hw = (int64_t)h * w;
+  const float* ga = p.gt + (size_t)b * c * hw;
+  const float* oa = p.out + (size_t)b * c * hw;
+  double* out = p.sums + (size_t)b * (2 + 6 * c);
+  if (blockIdx.z == 0) {
+    double tot = 0.0, num = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t off = (i / wc) * w + (i % wc);
+      float s1 = 0.f, na = 0.f, nb = 0.f;  // fp32 like the reference's torch float32 reductions over the band axis
+      for (int k = 0; k < c; ++k) {
+        const float a = ga[k * hw + off], o = oa[k * hw + off];
+        s1 += a * o; na += a * a; nb += o * o;
+      }
+      const float t = sqrtf(na * nb);
+      if (t > 0.f) num += 1.0;
+      const float ang = acosf(s1 / t);
+      if (!isnan(ang)) tot += (double)ang;
+    }
+    const double t0 = block_sum(tot, sh);
+    const double t1 = block_sum(num, sh);
+    if (threadIdx.x == 0) { atomicAdd(out, t0); atomicAdd(out + 1, t1); }
+  } else {
+    const int k = blockIdx.z - 1;
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t off = (i / wc) * w + (i % wc);
+      const float a = ga[k * hw + off], o = oa[k * hw + off];
+      const float d = a - o;
+      v[0] += (double)(d * d); v[1] += a; v[2] += o; v[3] += (double)a * a; v[4] += (double)o * o; v[5] += (double)a * o;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const double t = block_sum(v[j], sh);
+      if (threadIdx.x == 0) atomicAdd(out + 2 + 6 * k + j, t);
+    }
+  }
+}
+int launch_metrics(const ddif_metrics_t& p, cudaStream_t s) {
+  if (p.h < 2 || p.w < 2 || p.c < 1 || p.c > 1024 || p.batch < 1 || p.batch > 65535) return DDIF_ERR_SHAPE;
+  int64_t chunks = ceil_div((p.h - 1) * (p.w - 1), 256 * 4);
+  if (chunks > 64) chunks = 64;
+  metrics_kernel<<<dim3((unsigned)chunks, (unsigned)p.batch, (unsigned)(1 + p.c)), 256, 0, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+}  // namespace ddif

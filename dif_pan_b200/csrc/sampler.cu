@@ -171,7 +171,8 @@ __global__ void dpmpp_step_kernel(ddif_dpmpp_step_t p) {
       if (p.model_type == 0) noise = DIV(SUB(xv[j], MUL(al, ov[j])), sg);       // x_start -> noise (dpm_solver.py:299-300)
       else if (p.model_type == 1) noise = ov[j];                                 // noise            (:296-297)
       else noise = ADD(MUL(al, ov[j]), MUL(sg, xv[j]));                          // v -> noise       (:302-303)
-      const float m0 = DIV(SUB(xv[j], MUL(sg, noise)), al);     // data_prediction_fn (:446-447)
+      // data_prediction_fn (:446-447) for dpmsolver++; noise_prediction_fn (:435-439) for algorithm_type dpmsolver
+      const float m0 = p.predict ? noise : DIV(SUB(xv[j], MUL(sg, noise)), al);
       mv[j] = m0;
       if (p.order == 1) {
         xv[j] = SUB(MUL(cx, xv[j]), MUL(ca, m0));
@@ -193,6 +194,43 @@ __global__ void dpmpp_step_kernel(ddif_dpmpp_step_t p) {
 int launch_dpmpp_step(const ddif_dpmpp_step_t& p, cudaStream_t s) {
   if (p.n % 4 != 0 || p.order < 0 || p.order > 3) return DDIF_ERR_SHAPE;
   dpmpp_step_kernel<<<egrid(p.n / 4), 256, 0, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
+// ---- singlestep DPM-Solver stages (dpm_solver.py:555-600 first update, :602-683 second, :685-802 third) ---------------
+__global__ void dpm_single_kernel(ddif_dpm_single_t p) {
+  const float al = (float)p.alpha_e, sg = (float)p.sigma_e;
+  const float c0 = (float)p.c0, c1 = (float)p.c1, c2 = (float)p.c2;
+  const int64_t n4 = p.n / 4;
+  if (p.time_out && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < p.batch; i += blockDim.x) p.time_out[i] = (float)p.t_next_in;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 xe = reinterpret_cast<const float4*>(p.x_eval)[i];
+    const float4 o = reinterpret_cast<const float4*>(p.model_out)[i];
+    float4 xb = xe, ma = make_float4(0, 0, 0, 0);
+    if (p.mode != 2) xb = reinterpret_cast<const float4*>(p.x_base)[i];
+    if (p.mode == 1) ma = reinterpret_cast<const float4*>(p.m_a)[i];
+    const float ev[4] = {xe.x, xe.y, xe.z, xe.w}, ov[4] = {o.x, o.y, o.z, o.w}, bv[4] = {xb.x, xb.y, xb.z, xb.w}, av[4] = {ma.x, ma.y, ma.z, ma.w};
+    float mv[4], xo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float noise;
+      if (p.model_type == 0) noise = DIV(SUB(ev[j], MUL(al, ov[j])), sg);       // x_start -> noise (dpm_solver.py:299-300)
+      else if (p.model_type == 1) noise = ov[j];
+      else noise = ADD(MUL(al, ov[j]), MUL(sg, ev[j]));                          // v -> noise       (:302-303)
+      const float m = p.predict ? noise : DIV(SUB(ev[j], MUL(sg, noise)), al);
+      mv[j] = m;
+      if (p.mode == 0) xo[j] = SUB(MUL(c0, bv[j]), MUL(c1, m));
+      else xo[j] = ADD(SUB(MUL(c0, bv[j]), MUL(c1, av[j])), MUL(c2, SUB(m, av[j])));
+    }
+    if (p.m_cur) reinterpret_cast<float4*>(p.m_cur)[i] = make_float4(mv[0], mv[1], mv[2], mv[3]);
+    if (p.mode != 2) reinterpret_cast<float4*>(p.x_out)[i] = make_float4(xo[0], xo[1], xo[2], xo[3]);
+  }
+}
+int launch_dpm_single(const ddif_dpm_single_t& p, cudaStream_t s) {
+  if (p.n % 4 != 0 || p.mode < 0 || p.mode > 2 || (p.mode == 1 && !p.m_a) || (p.mode != 2 && (!p.x_out || !p.x_base))) return DDIF_ERR_SHAPE;
+  dpm_single_kernel<<<egrid(p.n / 4), 256, 0, s>>>(p);
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }

@@ -13,6 +13,7 @@ Philox4x32-10 generator seeded by `seed`.
 from __future__ import annotations
 
 import math
+import random
 from functools import partial
 from typing import Optional, Sequence
 
@@ -242,9 +243,71 @@ class GaussianDiffusion(nn.Module):
         self.space_new_betas(self.space_timesteps(self.num_timesteps, section_counts))
         return self._run_loop("ddim", x_in, len(self.betas), noise, eta=eta, clip=False)
 
-    def p_losses(self, x_start, noise=None, cond=None):
-        raise NotImplementedError("training (p_losses / backward) is not implemented on the CUDA path in this round; "
-                                  "q_sample is available as GaussianDiffusion.q_sample")
+    def _axpby(self, ca: torch.Tensor, x: torch.Tensor, cb: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """out[b] = ca[b]*x[b] + cb[b]*y[b] with per-sample fp32 coefficients gathered from the schedule buffers
+        (`extract`, diffusion_ddpm_pan.py:73-76): predict_start_from_noise / predict_v / predict_start_from_v (:284-312)."""
+        out = torch.empty_like(x)
+        _lib.launch("ddif_axpby_t", _stream(x.device), x=x.contiguous().data_ptr(), y=y.contiguous().data_ptr(),
+                    ca=ca.to(torch.float32).contiguous().data_ptr(), cb=cb.to(torch.float32).contiguous().data_ptr(), out=out.data_ptr(),
+                    batch=x.shape[0], chw=x[0].numel())
+        return out
+
+    def p_losses(self, x_start, noise=None, cond=None, *, t=None, self_cond_draw=None):
+        """Training objective, FORWARD evaluation (diffusion_ddpm_pan.py:692-766): t ~ U{0..T-1}, x_t = q_sample, the
+        optional no-grad self-conditioning pass (probability 0.5, Python `random.random()` like the reference, :702),
+        the denoiser, then mean(loss_func(target, prediction)) * mean(p2_loss_weight[t]) and recon_x0.  q_sample, the x0 / v
+        conversions and the weighted L1 / L2 reduction are fused CUDA kernels.  Returns (loss, recon_x0) like the
+        reference; there is no autograd graph (the CUDA UNet has no backward yet), so this serves validation-loss
+        evaluation and parity of the objective, not optimisation.  `t` / `self_cond_draw` pin the two random draws
+        for tests."""
+        if self.loss_type not in ("l1", "l2"):
+            raise NotImplementedError("loss_type='l1ssim' is not on the CUDA path")
+        if not x_start.is_cuda:
+            raise RuntimeError("dif_pan_b200 kernels run on CUDA only (no CPU fallback)")
+        if torch.is_grad_enabled() and getattr(self.model, "training", False) and any(p.requires_grad for p in self.model.parameters()):
+            raise NotImplementedError("dif_pan_b200: p_losses evaluates the objective forward-only; call model.eval() / torch.no_grad() "
+                                      "(training backward is not implemented on the CUDA path)")
+        b = x_start.shape[0]
+        dev = x_start.device
+        x_start = x_start.to(torch.float32).contiguous()
+        if t is None:
+            t = torch.randint(0, self.num_timesteps, (b,), device=dev).long()
+        if noise is None:
+            noise = device_randn(x_start.shape, dev, self.seed, 1 << 41)
+        noise = noise.to(torch.float32).contiguous()
+        x_noisy = self.q_sample(x_start, t, noise)
+        ex = lambda buf: buf.gather(-1, t)
+        with torch.no_grad():
+            x_self_cond = None
+            draw = random.random() if self_cond_draw is None else self_cond_draw
+            if self.self_condition and draw < 0.5:
+                mo = self.model(x_noisy, t, cond=cond, self_cond=None) if self.conditional else self.model(x_noisy, t, self_cond=None)
+                if self.pred_mode == "noise":
+                    x_self_cond = self._axpby(ex(self.sqrt_recip_alphas_cumprod), x_noisy, -ex(self.sqrt_recipm1_alphas_cumprod), mo)
+                elif self.pred_mode == "x_start":
+                    x_self_cond = mo
+                else:
+                    x_self_cond = self._axpby(ex(self.sqrt_alphas_cumprod), x_noisy, -ex(self.sqrt_one_minus_alphas_cumprod), mo)
+            if self.conditional:
+                pred = self.model(x_noisy, t, cond=cond, self_cond=x_self_cond)
+            else:
+                pred = self.model(x_noisy, t, self_cond=x_self_cond)
+            pred = pred.to(torch.float32).contiguous()
+            if self.pred_mode == "noise":
+                recon = self._axpby(ex(self.sqrt_recip_alphas_cumprod), x_noisy, -ex(self.sqrt_recipm1_alphas_cumprod), pred)
+                target = noise
+            elif self.pred_mode == "x_start":
+                recon, target = pred, x_start
+            else:
+                target = self._axpby(ex(self.sqrt_alphas_cumprod), noise, -ex(self.sqrt_one_minus_alphas_cumprod), x_start)
+                recon = self._axpby(ex(self.sqrt_alphas_cumprod), x_noisy, -ex(self.sqrt_one_minus_alphas_cumprod), target)
+            # nn.L1Loss() / nn.MSELoss() reduce to a scalar first (:189-193), so the reference's objective is
+            # mean(l) * mean_b(p2_loss_weight[t_b]) (:759-762), not a per-sample weighting
+            acc = torch.zeros(1, dtype=torch.float64, device=dev)
+            _lib.launch("ddif_loss_t", _stream(dev), a=target.data_ptr(), b=pred.data_ptr(), weight=None, out=acc.data_ptr(),
+                        batch=b, chw=x_start[0].numel(), squared=0 if self.loss_type == "l1" else 1)
+            loss = ((acc / float(x_start.numel())).to(torch.float32) * ex(self.p2_loss_weight)).mean()
+        return loss, recon
 
     def forward(self, x, mode="train", *args, **kwargs):
         if mode == "train":

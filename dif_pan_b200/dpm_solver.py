@@ -7,10 +7,12 @@ x_start -> noise -> x_start round trip (dpm.py:299-300, 446-447) plus the multis
 kernel (`ddif_dpmpp_step_f32`, csrc/sampler.cu).  With a `dif_pan_b200.UNetSR3` denoiser the loop runs in place
 on the model's device buffers: per step one CUDA-graph launch + one fused kernel.
 
-Implemented: algorithm_type 'dpmsolver++', method 'multistep' (orders 1-3, lower_order_final), skip types
-time_uniform / time_quadratic / logSNR, model types x_start / noise / v, guidance 'uncond' or 'classifier-free'
-with scale 1 (the wiring SURVEY.md §3.3 names).  The single-step / adaptive variants (dpm.py:602-802,964-1018;
-not used by any BASELINE config) raise NotImplementedError.
+Implemented: algorithm_type 'dpmsolver++' and 'dpmsolver'; method 'multistep' (orders 1-3, lower_order_final),
+'singlestep' (the "DPM-Solver-fast" order schedule, dpm.py:490-548) and 'singlestep_fixed' (orders 1-3, one fused
+`ddif_dpm_single_f32` kernel per denoiser evaluation); skip types time_uniform / time_quadratic / logSNR; model types
+x_start / noise / v; guidance 'uncond' or 'classifier-free' with scale 1 (the wiring SURVEY.md §3.3 names).
+method='adaptive' (dpm.py:964-1018), solver_type='taylor', thresholding correctors and denoise_to_zero raise
+NotImplementedError (not used by any BASELINE config).
 
 Reference quirk kept out: model_wrapper multiplies `[B]`-shaped alpha_t against `[B,C,H,W]` (dpm.py:299-300),
 which only broadcasts for B == 1 or B == W; all entries are equal, so a scalar multiply is the same arithmetic and
@@ -148,8 +150,6 @@ class DPM_Solver:
     def __init__(self, model_fn, noise_schedule, algorithm_type="dpmsolver++", correcting_x0_fn=None, correcting_xt_fn=None,
                  thresholding_max_val=1.0, dynamic_thresholding_ratio=0.995):
         assert algorithm_type in ["dpmsolver", "dpmsolver++"]
-        if algorithm_type != "dpmsolver++":
-            raise NotImplementedError("only algorithm_type='dpmsolver++' (the default) is on the CUDA path")
         if correcting_x0_fn is not None or correcting_xt_fn is not None:
             raise NotImplementedError("correcting_x0_fn / correcting_xt_fn (torch.quantile thresholding) are not on the CUDA path")
         if not isinstance(model_fn, _WrappedModel) or model_fn.model_type not in MODEL_TYPES:
@@ -173,24 +173,160 @@ class DPM_Solver:
         raise ValueError("Unsupported skip_type {}, need to be 'logSNR' or 'time_uniform' or 'time_quadratic'".format(skip_type))
 
     def _coefficients(self, t_hist: List[torch.Tensor], t_next: torch.Tensor, order: int) -> dict:
-        """fp32 scalars of one multistep update (dpm.py:569-584, 820-839, 876-901)."""
+        """fp32 scalars of one multistep update (dpm.py:569-599, 820-860, 876-912), both algorithm types.  For
+        algorithm_type='dpmsolver' the scalars carry the signs of the ++ expression the kernel evaluates
+        (x = cx*x - ca*m0 - cb*D1 at order 2, x = cx*x - ca*m0 + cb*D1 - cc*D2 at order 3)."""
         ns = self.noise_schedule
         lam = ns.marginal_lambda
         t0 = t_hist[-1]
         h = lam(t_next) - lam(t0)
-        alpha_t = torch.exp(ns.marginal_log_mean_coeff(t_next))
-        phi_1 = torch.expm1(-h)
-        c = dict(cx=ns.marginal_std(t_next) / ns.marginal_std(t0), ca=alpha_t * phi_1)
+        pp = self.algorithm_type == "dpmsolver++"
+        if pp:
+            alpha_t = torch.exp(ns.marginal_log_mean_coeff(t_next))
+            phi_1 = torch.expm1(-h)
+            scale = alpha_t
+            c = dict(cx=ns.marginal_std(t_next) / ns.marginal_std(t0), ca=alpha_t * phi_1)
+        else:
+            scale = ns.marginal_std(t_next)
+            phi_1 = torch.expm1(h)
+            c = dict(cx=torch.exp(ns.marginal_log_mean_coeff(t_next) - ns.marginal_log_mean_coeff(t0)), ca=scale * phi_1)
         if order == 2:
             r0 = (lam(t0) - lam(t_hist[-2])) / h
-            c.update(cb=0.5 * (alpha_t * phi_1), inv_r0=1.0 / r0)
+            c.update(cb=0.5 * (scale * phi_1), inv_r0=1.0 / r0)
         elif order == 3:
             r0 = (lam(t0) - lam(t_hist[-2])) / h
             r1 = (lam(t_hist[-2]) - lam(t_hist[-3])) / h
-            phi_2 = phi_1 / h + 1.0
+            phi_2 = phi_1 / h + 1.0 if pp else phi_1 / h - 1.0
             phi_3 = phi_2 / h - 0.5
-            c.update(cb=alpha_t * phi_2, cc=alpha_t * phi_3, inv_r0=1.0 / r0, inv_r1=1.0 / r1, k1=r0 / (r0 + r1), k2=1.0 / (r0 + r1))
+            cb = scale * phi_2
+            c.update(cb=cb if pp else -cb, cc=scale * phi_3, inv_r0=1.0 / r0, inv_r1=1.0 / r1, k1=r0 / (r0 + r1), k2=1.0 / (r0 + r1))
         return {k: float(v) for k, v in c.items()}
+
+    def get_orders_and_timesteps_for_singlestep_solver(self, steps, order, skip_type, t_T, t_0, device=None):
+        """dpm.py:490-548 ("DPM-Solver-fast" order schedule)."""
+        if order == 3:
+            K = steps // 3 + 1
+            if steps % 3 == 0:
+                orders = [3] * (K - 2) + [2, 1]
+            elif steps % 3 == 1:
+                orders = [3] * (K - 1) + [1]
+            else:
+                orders = [3] * (K - 1) + [2]
+        elif order == 2:
+            if steps % 2 == 0:
+                K = steps // 2
+                orders = [2] * K
+            else:
+                K = steps // 2 + 1
+                orders = [2] * (K - 1) + [1]
+        elif order == 1:
+            K = 1
+            orders = [1] * steps
+        else:
+            raise ValueError("'order' must be '1' or '2' or '3'.")
+        if skip_type == "logSNR":
+            timesteps_outer = self.get_time_steps(skip_type, t_T, t_0, K)
+        else:
+            timesteps_outer = self.get_time_steps(skip_type, t_T, t_0, steps)[torch.cumsum(torch.tensor([0] + orders), 0)]
+        return timesteps_outer, orders
+
+    def _single_coefficients(self, s, t, order, r1, r2):
+        """Stages of one singlestep update s -> t as (eval time, next eval time or None, kernel mode, c0, c1, c2), fp32 scalars in
+        the reference's operation order (dpm.py:581-599 first, :623-674 second, :714-797 third; solver_type 'dpmsolver')."""
+        ns = self.noise_schedule
+        pp = self.algorithm_type == "dpmsolver++"
+        lam_s, lam_t = ns.marginal_lambda(s), ns.marginal_lambda(t)
+        h = lam_t - lam_s
+        la, sd = ns.marginal_log_mean_coeff, ns.marginal_std
+        em = (lambda v: torch.expm1(-v)) if pp else torch.expm1
+
+        def lead(u):   # coefficient of x: sigma_u / sigma_s (++) or exp(log_alpha_u - log_alpha_s)
+            return sd(u) / sd(s) if pp else torch.exp(la(u) - la(s))
+
+        def amp(u):    # alpha_u (++) or sigma_u
+            return torch.exp(la(u)) if pp else sd(u)
+
+        f = lambda v: float(v)
+        if order == 1:
+            return [(s, None, 0, f(lead(t)), f(amp(t) * em(h)), 0.0)]
+        if order == 2:
+            r1 = 0.5 if r1 is None else r1
+            s1 = ns.inverse_lambda(lam_s + r1 * h)
+            phi_11, phi_1 = em(r1 * h), em(h)
+            c2 = (0.5 / r1) * (amp(t) * phi_1)
+            return [(s, s1, 0, f(lead(s1)), f(amp(s1) * phi_11), 0.0),
+                    (s1, None, 1, f(lead(t)), f(amp(t) * phi_1), -f(c2))]
+        r1 = 1.0 / 3.0 if r1 is None else r1
+        r2 = 2.0 / 3.0 if r2 is None else r2
+        s1, s2 = ns.inverse_lambda(lam_s + r1 * h), ns.inverse_lambda(lam_s + r2 * h)
+        phi_11, phi_12, phi_1 = em(r1 * h), em(r2 * h), em(h)
+        if pp:
+            phi_22 = torch.expm1(-r2 * h) / (r2 * h) + 1.0
+            phi_2 = phi_1 / h + 1.0
+        else:
+            phi_22 = torch.expm1(r2 * h) / (r2 * h) - 1.0
+            phi_2 = phi_1 / h - 1.0
+        c2_s2 = r2 / r1 * (amp(s2) * phi_22)
+        c2_t = (1.0 / r2) * (amp(t) * phi_2)
+        sgn = 1.0 if pp else -1.0
+        return [(s, s1, 0, f(lead(s1)), f(amp(s1) * phi_11), 0.0),
+                (s1, s2, 1, f(lead(s2)), f(amp(s2) * phi_12), sgn * f(c2_s2)),
+                (s2, None, 1, f(lead(t)), f(amp(t) * phi_1), sgn * f(c2_t))]
+
+    def _sample_singlestep(self, x, steps, order, skip_type, method, t_T, t_0, return_intermediate):
+        """dpm.py:1222-1240: every outer step s -> t evaluates the denoiser `order` times (at s, s1[, s2]); each evaluation is
+        followed by ONE fused kernel (model_wrapper round trip + prediction + the stage's linear update)."""
+        ns, wm = self.noise_schedule, self.wrapped
+        if method == "singlestep":
+            outer, orders = self.get_orders_and_timesteps_for_singlestep_solver(steps, order, skip_type, t_T, t_0)
+        else:
+            K = steps // order
+            orders = [order] * K
+            outer = self.get_time_steps(skip_type, t_T, t_0, K)
+        B, dev = x.shape[0], x.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        fast = isinstance(wm.model, UNetSR3) and wm.condition is not None and not wm.model_kwargs
+        predict = 0 if self.algorithm_type == "dpmsolver++" else 1
+        with torch.no_grad():
+            if fast:
+                rt = wm.model.runtime(B, x.shape[2], x.shape[3])
+                rt.set_cond(wm.condition)
+                xe, out, tbuf = rt.x_buf, rt.out_buf, rt.t_buf
+                xe.copy_(x)
+                tbuf.fill_(float(wm.input_time(outer[0])))
+            else:
+                xe, tbuf = x.clone().contiguous(), None
+            xs = xe.clone()                 # state at the outer time s (the stages all start from it)
+            m_s = torch.empty_like(xe)      # model_s
+            m_k = torch.empty_like(xe)      # model_s1 / model_s2 (scratch)
+            inter = []
+            for step, o in enumerate(orders):
+                s_t, t_t = outer[step], outer[step + 1]
+                inner = self.get_time_steps(skip_type, s_t.item(), t_t.item(), o)
+                lam_in = ns.marginal_lambda(inner)
+                hh = lam_in[-1] - lam_in[0]
+                r1 = None if o <= 1 else (lam_in[1] - lam_in[0]) / hh
+                r2 = None if o <= 2 else (lam_in[2] - lam_in[0]) / hh
+                stages = self._single_coefficients(s_t.reshape(1), t_t.reshape(1), o, r1, r2)
+                for k, (t_ev, t_nx, mode, c0, c1, c2) in enumerate(stages):
+                    if fast:
+                        rt.step()
+                    else:
+                        out = wm.raw(xe, t_ev.reshape(-1)[:1].to(dev).expand(B)).contiguous()
+                    last = k == len(stages) - 1
+                    nxt_label = t_nx if not last else (outer[step + 1] if step + 1 < len(orders) else None)
+                    _lib.launch(
+                        "ddif_dpm_single_t", stream, x_base=xs.data_ptr(), x_eval=xe.data_ptr(), model_out=out.data_ptr(),
+                        m_cur=(m_s if k == 0 else m_k).data_ptr(), m_a=m_s.data_ptr() if mode == 1 else None, x_out=xe.data_ptr(),
+                        time_out=tbuf.data_ptr() if (fast and nxt_label is not None) else None, n=xe.numel(), batch=B,
+                        model_type=MODEL_TYPES[wm.model_type], predict=predict, mode=mode, alpha_e=float(ns.marginal_alpha(t_ev)),
+                        sigma_e=float(ns.marginal_std(t_ev)), c0=c0, c1=c1, c2=c2,
+                        t_next_in=float(wm.input_time(nxt_label)) if nxt_label is not None else 0.0)
+                xs.copy_(xe)
+                if return_intermediate:
+                    inter.append(xe.clone())
+            res = xe.clone()
+        return (res, inter) if return_intermediate else res
 
     def sample(self, x, steps=20, t_start=None, t_end=None, order=2, skip_type="time_uniform", method="multistep",
                lower_order_final=True, denoise_to_zero=False, solver_type="dpmsolver", atol=0.0078, rtol=0.05,
@@ -200,9 +336,9 @@ class DPM_Solver:
         t_0 = 1.0 / ns.total_N if t_end is None else t_end
         t_T = ns.T if t_start is None else t_start
         assert t_0 > 0 and t_T > 0, "Time range needs to be greater than 0. For discrete-time DPMs, it needs to be in [1 / N, 1], where N is the length of betas array"
-        if method != "multistep":
-            if method in ("singlestep", "singlestep_fixed", "adaptive"):
-                raise NotImplementedError(f"method={method!r} is not on the CUDA path (multistep only)")
+        if method not in ("multistep", "singlestep", "singlestep_fixed"):
+            if method == "adaptive":
+                raise NotImplementedError("method='adaptive' (data-dependent step-size control, dpm.py:964-1018) is not on the CUDA path")
             raise ValueError("Got wrong method {}".format(method))
         if solver_type != "dpmsolver":
             if solver_type == "taylor":
@@ -212,9 +348,11 @@ class DPM_Solver:
             raise NotImplementedError("denoise_to_zero is not on the CUDA path")
         if order not in (1, 2, 3):
             raise ValueError("Solver order must be 1 or 2 or 3, got {}".format(order))
-        assert steps >= order
         if not x.is_cuda:
             raise RuntimeError("dif_pan_b200 sampler kernels run on CUDA only (no CPU fallback)")
+        if method != "multistep":
+            return self._sample_singlestep(x, steps, order, skip_type, method, t_T, t_0, return_intermediate)
+        assert steps >= order
         wm = self.wrapped
         ts = self.get_time_steps(skip_type, t_T, t_0, steps)
         assert ts.shape[0] - 1 == steps
@@ -254,7 +392,7 @@ class DPM_Solver:
                     m_prev1=m[(s - 1) % 3].data_ptr(), m_prev2=m[(s - 2) % 3].data_ptr(),
                     time_out=tbuf.data_ptr() if (fast and not last_eval) else None, n=xb.numel(), batch=B, order=o,
                     model_type=MODEL_TYPES[wm.model_type], alpha_t=float(ns.marginal_alpha(t_cur)), sigma_t=float(ns.marginal_std(t_cur)),
-                    t_next_in=float(wm.input_time(ts[nxt])), **coef)
+                    t_next_in=float(wm.input_time(ts[nxt])), predict=0 if self.algorithm_type == "dpmsolver++" else 1, **coef)
                 if return_intermediate:
                     inter.append(xb.clone())
             res = xb.clone()

@@ -76,3 +76,27 @@ def assemble_cond(lms: torch.Tensor, pan: torch.Tensor, wavelets: torch.Tensor) 
     _lib.launch("ddif_cond_assemble_t", _stream(lms), lms=lms.data_ptr(), pan=pan.data_ptr(), wav=wavelets.data_ptr(), cond=cond.data_ptr(),
                 batch=B, c=C, p=P, cw=CW, h=H, w=W, wh=wavelets.shape[2], ww=wavelets.shape[3])
     return cond
+
+
+def make_cond(lms_dn: torch.Tensor, pan_dn: torch.Tensor, division: float = 1.0, order: str = "pan", return_wavelets: bool = False):
+    """Raw `lms` [B,C,H,W] and `pan` [B,P,H,W] (digital numbers, or [0,1] data with division=1) -> `cond` [B, 2C+4P, H, W] in ONE
+    kernel (`ddif_wavelet_cond_f32`): Haar DWT of both, /division, the dataset's channel order, bilinear x2 of the wavelet stack and
+    the concat with lms/division and pan/division (pan_dataset.py:73-142, hisr.py:48-59, diffusion_engine.py:221-228).
+    Same expressions as `assemble_cond(lms/div, pan/div, wavelet_channels(...))` (wavelets bit-identical, the bilinear taps to an ulp);
+    4 B read + 4 B written per cond element instead of
+    three kernels and two intermediate tensors.  With return_wavelets also returns the [B, C+3P, H/2, W/2] stack the datasets yield."""
+    if not (lms_dn.is_cuda and pan_dn.is_cuda):
+        raise RuntimeError("dif_pan_b200.wavelet runs on CUDA only (no CPU fallback)")
+    if order not in ("pan", "hisr"):
+        raise ValueError(f"order must be 'pan' or 'hisr', got {order!r}")
+    lms_dn, pan_dn = lms_dn.to(torch.float32).contiguous(), pan_dn.to(torch.float32).contiguous()
+    B, C, H, W = lms_dn.shape
+    P = pan_dn.shape[1]
+    if pan_dn.shape[0] != B or tuple(pan_dn.shape[2:]) != (H, W) or H % 2 or W % 2:
+        raise ValueError(f"lms {tuple(lms_dn.shape)} and pan {tuple(pan_dn.shape)} must share batch and an even H x W")
+    cond = torch.empty(B, 2 * C + 4 * P, H, W, dtype=torch.float32, device=lms_dn.device)
+    wav = torch.empty(B, C + 3 * P, H // 2, W // 2, dtype=torch.float32, device=lms_dn.device) if return_wavelets else None
+    _lib.launch("ddif_wavelet_cond_t", _stream(lms_dn), lms=lms_dn.data_ptr(), pan=pan_dn.data_ptr(), cond=cond.data_ptr(),
+                wav=wav.data_ptr() if wav is not None else None, batch=B, c=C, p=P, h=H, w=W, order=0 if order == "pan" else 1,
+                divisor=float(division))
+    return (cond, wav) if return_wavelets else cond

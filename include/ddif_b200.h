@@ -52,7 +52,14 @@ enum ddif_op_kind {
   DDIF_OP_HAAR_IDWT2 = 19,   /* inverse of the above (no reference call site)                      */
   DDIF_OP_COND_ASSEMBLE = 20,/* cond = cat[lms, pan, bilinear(wavelets)]                           diffusion_engine.py:221-228 */
   DDIF_OP_RANDN = 21,        /* Philox4x32-10 + Box-Muller standard normal (replaces torch.randn)  diffusion_ddpm_pan.py:86,484 */
-  DDIF_OP_AXPBY_CLIP = 22    /* sr = clip(sample + lms, 0, 1)                                      diffusion_engine.py:446-447 */
+  DDIF_OP_AXPBY_CLIP = 22,   /* sr = clip(sample + lms, 0, 1)                                      diffusion_engine.py:446-447 */
+  DDIF_OP_DPM_SINGLE = 23,   /* one stage of the singlestep DPM-Solver / DPM-Solver++ updates      dpm_solver.py:555-600,602-802 */
+  DDIF_OP_LOSS = 24,         /* sum_b w[b] * sum |a-b| or (a-b)^2 (training objective, forward)    diffusion_ddpm_pan.py:725-762 */
+  DDIF_OP_AXPBY = 25,        /* out = ca[b]*x + cb[b]*y per sample (predict_start_from_noise / _v)  diffusion_ddpm_pan.py:284-312 */
+  DDIF_OP_METRICS = 26,      /* per-image partial sums of SAM / ERGAS / PSNR / CC                  utils/_metric_legacy.py:299-346 */
+  DDIF_OP_TILE = 27,         /* scene -> patch batch (gather) and patch batch -> scene (overlap-averaged stitch) */
+  DDIF_OP_WAVELET_COND = 28  /* raw lms, pan -> cond in one pass: Haar DWT, /division, channel order, bilinear up, concat
+                                dataset/pan_dataset.py:73-142, dataset/hisr.py:48-59, diffusion_engine.py:221-228 */
 };
 
 /* ---- DDIF_OP_GEMM ------------------------------------------------------------------------------------------
@@ -162,8 +169,39 @@ typedef struct {
   float* x; const float* model_out; float* m_cur; const float* m_prev1; const float* m_prev2; float* time_out;
   int64_t n, batch, order, model_type; /* model_type: 0 x_start, 1 noise, 2 v (dpm_solver.py:296-303) */
   double alpha_t, sigma_t, cx, ca, cb, cc, inv_r0, inv_r1, k1, k2, t_next_in;
+  int64_t predict; /* 0: m = data prediction (algorithm_type dpmsolver++), 1: m = noise prediction (dpmsolver; the host passes
+                      that algorithm's scalars in cx..cc with the signs of the ++ expression: dpm_solver.py:589-599,840-845,902-912) */
 } ddif_dpmpp_step_t;
 typedef struct { const float* x0; const float* noise; float* out; const float* sa; const float* s1ma; const int64_t* t; int64_t batch, chw; } ddif_q_sample_t;
+/* One stage of a singlestep solver (DPM-Solver-1/2/3, both algorithm types).  m_cur = prediction at the evaluation point
+ * (x_eval, alpha_e, sigma_e) from the denoiser output, through the same model_wrapper round trip as DDIF_OP_DPMPP_STEP:
+ * predict 0 = data prediction (dpmsolver++), 1 = noise prediction (dpmsolver).  Then, with host-computed fp32 scalars,
+ *   mode 0: x_out = c0*x_base - c1*m_cur                          (first update; stage x_s1)       dpm_solver.py:581-599,639-642
+ *   mode 1: x_out = c0*x_base - c1*m_a + c2*(m_cur - m_a)         (2nd/3rd-order final; stage x_s2) dpm_solver.py:645-649,745-757
+ *   mode 2: only m_cur is stored
+ * x_out may alias x_base or x_eval.  time_out (optional): float[batch] receives t_next_in. */
+typedef struct {
+  const float* x_base; const float* x_eval; const float* model_out; float* m_cur; const float* m_a; float* x_out; float* time_out;
+  int64_t n, batch, model_type, predict, mode;
+  double alpha_e, sigma_e, c0, c1, c2, t_next_in;
+} ddif_dpm_single_t;
+/* out[0] += sum_b weight[b] * sum_i l(a[b,i], b[b,i]); squared 0: |a-b| (l1), 1: (a-b)^2 (l2).  weight may be NULL (= 1).
+ * `out` is a device double the caller zeroes; the mean is out[0] / (batch*chw). */
+typedef struct { const float* a; const float* b; const float* weight; double* out; int64_t batch, chw, squared; } ddif_loss_t;
+/* out[b,i] = ca[b]*x[b,i] + cb[b]*y[b,i]  (ca, cb: float[batch] on the device) */
+typedef struct { const float* x; const float* y; const float* ca; const float* cb; float* out; int64_t batch, chw; } ddif_axpby_t;
+/* gt, out: [batch, c, h, w] fp32.  Only pixels y < h-1, x < w-1 enter (the reference's bounds cut `[0:-1]`, :300-302).
+ * sums: double[batch][2 + 6*c], zeroed by the caller: {sum of spectral angles, pixels with |a||b| > 0,
+ * per band: sum (a-b)^2, sum a, sum b, sum a^2, sum b^2, sum a*b}  with a = gt, b = out. */
+typedef struct { const float* gt; const float* out; double* sums; int64_t batch, c, h, w; } ddif_metrics_t;
+/* dir 0: tiles[(b*ny + iy)*nx + ix, c, :, :] = scene[b, c, iy*sy : iy*sy+ph, ix*sx : ix*sx+pw]
+ * dir 1: scene[b, c, y, x] = mean over the tiles covering (y, x) (uniform average of overlaps; sy <= ph, sx <= pw) */
+typedef struct { float* scene; float* tiles; int64_t batch, c, h, w, ph, pw, sy, sx, ny, nx, dir; } ddif_tile_t;
+/* cond[b] = cat(lms/div, pan/div, up2(LL(lms)/div), up2(pan sub-bands / div))  in ONE pass from the raw arrays.
+ * lms [batch, c, h, w], pan [batch, p, h, w] raw values; order 0 = Pan datasets (cH, cD, cV; pan_dataset.py:139-141),
+ * 1 = HISR (cH, cV, cD; hisr.py:57-59); up2 = bilinear x2, align_corners=False (diffusion_engine.py:224-226).
+ * wav (optional): [batch, c + 3p, h/2, w/2] also receives the wavelet stack the reference datasets return. */
+typedef struct { const float* lms; const float* pan; float* cond; float* wav; int64_t batch, c, p, h, w, order; double divisor; } ddif_wavelet_cond_t;
 /* x: [planes, h, w] fp32 (output for IDWT); 4 sub-bands each [planes, h/2, w/2] (LL, cH, cV, cD).
  * DWT: every coefficient is divided by `divisor` (the dataset "division", pan_dataset.py:127-134); IDWT ignores it. */
 typedef struct { float* x; float* ll; float* ch; float* cv; float* cd; int64_t planes, h, w; double divisor; } ddif_haar_t;
@@ -210,6 +248,11 @@ int ddif_ddim_step_f32(const ddif_ddim_step_t* p, ddif_stream_t s);
 int ddif_dpmpp_step_f32(const ddif_dpmpp_step_t* p, ddif_stream_t s);
 int ddif_q_sample_f32(const ddif_q_sample_t* p, ddif_stream_t s);
 int ddif_conv_igemm_bf16(const ddif_gemm_t* p, ddif_stream_t s);
+int ddif_dpm_single_f32(const ddif_dpm_single_t* p, ddif_stream_t s);
+int ddif_loss_f32(const ddif_loss_t* p, ddif_stream_t s);
+int ddif_metrics_f32(const ddif_metrics_t* p, ddif_stream_t s);
+int ddif_tile_f32(const ddif_tile_t* p, ddif_stream_t s);
+int ddif_wavelet_cond_f32(const ddif_wavelet_cond_t* p, ddif_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -35,11 +35,18 @@ def sam_ergas_psnr(gt_chw: torch.Tensor, out_chw: torch.Tensor, ratio: int = 4) 
     ergas = 100 * (1 / ratio) * ((summ / a.shape[2]) ** 0.5)
     rmse = torch.mean(torch.mean((a - b) ** 2, 0), 0) ** 0.5
     psnr = torch.mean(-20 * (torch.log(1 / rmse) / math.log(10)))
-    return {"SAM": float(sam), "ERGAS": float(ergas), "PSNR": float(psnr)}
+    # CC (:367-375, choices=5)
+    hw = a.shape[0] * a.shape[1]
+    ma, mb = torch.mean(torch.mean(a, 0), 0), torch.mean(torch.mean(b, 0), 0)
+    c1 = torch.sum(torch.sum(a * b, 0), 0) - hw * (ma * mb)
+    c2 = torch.sum(torch.sum(b ** 2, 0), 0) - hw * (mb ** 2)
+    c3 = torch.sum(torch.sum(a ** 2, 0), 0) - hw * (ma ** 2)
+    cc = torch.mean(c1 / ((c2 * c3) ** 0.5))
+    return {"SAM": float(sam), "ERGAS": float(ergas), "PSNR": float(psnr), "CC": float(cc)}
 
 
 def batch_metrics(gt: torch.Tensor, out: torch.Tensor, ratio: int = 4) -> Dict[str, float]:
-    acc = {"SAM": 0.0, "ERGAS": 0.0, "PSNR": 0.0}
+    acc = {"SAM": 0.0, "ERGAS": 0.0, "PSNR": 0.0, "CC": 0.0}
     for g, o in zip(gt, out):
         m = sam_ergas_psnr(g, o, ratio)
         for k in acc:

@@ -322,3 +322,199 @@ def dpmpp_multistep_sample(model, ns: VPSchedule, x, cond, steps=20, order=2, tr
         else:
             m_list = m_list[1:] + [m_list[-1]]
     return x
+
+
+# ----------------------------------------------------------------------------
+# DPM-Solver: both algorithm types, multistep and singlestep (dpm.py:435-450, 490-548, 555-912, 1179-1240)
+# ----------------------------------------------------------------------------
+def analytic_denoiser(x, t_in, cond=None, self_cond=None):
+    """Cheap smooth stand-in for the UNet (same call signature) used to pin the SOLVER arithmetic against the reference:
+    the reference's DPM_Solver is model-agnostic, so its golden trajectories do not need the 10 M parameter network."""
+    tt = t_in.reshape(-1, 1, 1, 1).to(x.dtype)
+    return 0.7 * x * torch.cos(0.002 * tt) + 0.1 * torch.sin(x) + (0.0 if cond is None else 0.05 * cond[:, : x.shape[1]])
+
+
+def inverse_lambda(ns: "VPSchedule", lamb: torch.Tensor) -> torch.Tensor:
+    """NoiseScheduleVP.inverse_lambda, discrete schedule (dpm.py:163-175)."""
+    log_alpha = -0.5 * torch.logaddexp(torch.zeros((1,)), -2.0 * lamb)
+    t = interp1d(log_alpha.reshape(-1, 1), torch.flip(ns.log_alpha_array, [1]), torch.flip(ns.t_array, [1]))
+    return t.reshape(-1)
+
+
+def _time_steps(ns, skip_type, t_T, t_0, N):
+    if skip_type == "logSNR":
+        lT, l0 = ns.lam(torch.tensor([t_T])), ns.lam(torch.tensor([t_0]))
+        return inverse_lambda(ns, torch.linspace(lT.item(), l0.item(), N + 1))
+    if skip_type == "time_uniform":
+        return torch.linspace(t_T, t_0, N + 1)
+    return torch.linspace(t_T ** 0.5, t_0 ** 0.5, N + 1).pow(2)
+
+
+def dpm_prediction(ns, model, x, t, cond, model_type, algorithm):
+    """model_wrapper + noise_prediction_fn / data_prediction_fn (dpm.py:279-303, 435-450)."""
+    tt = t.reshape(-1)[:1].expand(x.shape[0])
+    t_in = (tt - 1.0 / ns.total_N) * 1000.0
+    out = model(x, t_in, cond, None)
+    a, s = ns.alpha(tt).view(-1, 1, 1, 1), ns.std(tt).view(-1, 1, 1, 1)
+    if model_type == "noise":
+        noise = out
+    elif model_type == "x_start":
+        noise = (x - a * out) / s
+    else:  # v
+        noise = a * out + s * x
+    if algorithm == "dpmsolver":
+        return noise
+    a1, s1 = ns.alpha(t.reshape(-1)[:1]), ns.std(t.reshape(-1)[:1])
+    return (x - s1 * noise) / a1
+
+
+def dpm_sample(model, ns: "VPSchedule", x, cond=None, steps=20, order=2, skip_type="time_uniform", method="multistep",
+               algorithm="dpmsolver++", model_type="x_start", lower_order_final=True):
+    """DPM_Solver.sample for method in multistep / singlestep / singlestep_fixed, solver_type 'dpmsolver' (dpm.py:1055-1253)."""
+    pp = algorithm == "dpmsolver++"
+    t_0, t_T = 1.0 / ns.total_N, ns.T
+    pred = lambda xx, tt: dpm_prediction(ns, model, xx, tt, cond, model_type, algorithm)
+    la = ns.log_alpha
+
+    def first(x, s, t, m_s):
+        h = ns.lam(t) - ns.lam(s)
+        if pp:
+            return ns.std(t) / ns.std(s) * x - ns.alpha(t) * torch.expm1(-h) * m_s
+        return torch.exp(la(t) - la(s)) * x - (ns.std(t) * torch.expm1(h)) * m_s
+
+    def single2(x, s, t, r1):
+        r1 = 0.5 if r1 is None else r1
+        h = ns.lam(t) - ns.lam(s)
+        s1 = inverse_lambda(ns, ns.lam(s) + r1 * h)
+        m_s = pred(x, s)
+        if pp:
+            phi_11, phi_1 = torch.expm1(-r1 * h), torch.expm1(-h)
+            x_s1 = (ns.std(s1) / ns.std(s)) * x - (ns.alpha(s1) * phi_11) * m_s
+            m_s1 = pred(x_s1, s1)
+            return (ns.std(t) / ns.std(s)) * x - (ns.alpha(t) * phi_1) * m_s - (0.5 / r1) * (ns.alpha(t) * phi_1) * (m_s1 - m_s)
+        phi_11, phi_1 = torch.expm1(r1 * h), torch.expm1(h)
+        x_s1 = torch.exp(la(s1) - la(s)) * x - (ns.std(s1) * phi_11) * m_s
+        m_s1 = pred(x_s1, s1)
+        return torch.exp(la(t) - la(s)) * x - (ns.std(t) * phi_1) * m_s - (0.5 / r1) * (ns.std(t) * phi_1) * (m_s1 - m_s)
+
+    def single3(x, s, t, r1, r2):
+        r1 = 1.0 / 3.0 if r1 is None else r1
+        r2 = 2.0 / 3.0 if r2 is None else r2
+        h = ns.lam(t) - ns.lam(s)
+        s1, s2 = inverse_lambda(ns, ns.lam(s) + r1 * h), inverse_lambda(ns, ns.lam(s) + r2 * h)
+        m_s = pred(x, s)
+        if pp:
+            phi_11, phi_12, phi_1 = torch.expm1(-r1 * h), torch.expm1(-r2 * h), torch.expm1(-h)
+            phi_22 = torch.expm1(-r2 * h) / (r2 * h) + 1.0
+            phi_2 = phi_1 / h + 1.0
+            x_s1 = (ns.std(s1) / ns.std(s)) * x - (ns.alpha(s1) * phi_11) * m_s
+            m_s1 = pred(x_s1, s1)
+            x_s2 = (ns.std(s2) / ns.std(s)) * x - (ns.alpha(s2) * phi_12) * m_s + r2 / r1 * (ns.alpha(s2) * phi_22) * (m_s1 - m_s)
+            m_s2 = pred(x_s2, s2)
+            return (ns.std(t) / ns.std(s)) * x - (ns.alpha(t) * phi_1) * m_s + (1.0 / r2) * (ns.alpha(t) * phi_2) * (m_s2 - m_s)
+        phi_11, phi_12, phi_1 = torch.expm1(r1 * h), torch.expm1(r2 * h), torch.expm1(h)
+        phi_22 = torch.expm1(r2 * h) / (r2 * h) - 1.0
+        phi_2 = phi_1 / h - 1.0
+        x_s1 = torch.exp(la(s1) - la(s)) * x - (ns.std(s1) * phi_11) * m_s
+        m_s1 = pred(x_s1, s1)
+        x_s2 = torch.exp(la(s2) - la(s)) * x - (ns.std(s2) * phi_12) * m_s - r2 / r1 * (ns.std(s2) * phi_22) * (m_s1 - m_s)
+        m_s2 = pred(x_s2, s2)
+        return torch.exp(la(t) - la(s)) * x - (ns.std(t) * phi_1) * m_s - (1.0 / r2) * (ns.std(t) * phi_2) * (m_s2 - m_s)
+
+    def multi(x, m, tl, t, o):
+        if o == 1:
+            return first(x, tl[-1], t, m[-1])
+        l0, lt = ns.lam(tl[-1]), ns.lam(t)
+        h = lt - l0
+        r0 = (l0 - ns.lam(tl[-2])) / h
+        D10 = (1.0 / r0) * (m[-1] - m[-2])
+        lead = ns.std(t) / ns.std(tl[-1]) if pp else torch.exp(la(t) - la(tl[-1]))
+        amp = ns.alpha(t) if pp else ns.std(t)
+        phi_1 = torch.expm1(-h) if pp else torch.expm1(h)
+        if o == 2:
+            return lead * x - (amp * phi_1) * m[-1] - 0.5 * (amp * phi_1) * D10
+        r1 = (ns.lam(tl[-2]) - ns.lam(tl[-3])) / h
+        D11 = (1.0 / r1) * (m[-2] - m[-3])
+        D1 = D10 + (r0 / (r0 + r1)) * (D10 - D11)
+        D2 = (1.0 / (r0 + r1)) * (D10 - D11)
+        if pp:
+            phi_2 = phi_1 / h + 1.0
+            phi_3 = phi_2 / h - 0.5
+            return lead * x - (amp * phi_1) * m[-1] + (amp * phi_2) * D1 - (amp * phi_3) * D2
+        phi_2 = phi_1 / h - 1.0
+        phi_3 = phi_2 / h - 0.5
+        return lead * x - (amp * phi_1) * m[-1] - (amp * phi_2) * D1 - (amp * phi_3) * D2
+
+    if method == "multistep":
+        assert steps >= order
+        ts = _time_steps(ns, skip_type, t_T, t_0, steps)
+        tl, m = [ts[0:1]], [pred(x, ts[0:1])]
+        for step in range(1, order):
+            x = multi(x, m, tl, ts[step:step + 1], step)
+            tl.append(ts[step:step + 1])
+            m.append(pred(x, ts[step:step + 1]))
+        for step in range(order, steps + 1):
+            t = ts[step:step + 1]
+            so = min(order, steps + 1 - step) if (lower_order_final and steps < 10) else order
+            x = multi(x, m, tl, t, so)
+            tl = tl[1:] + [t]
+            m = m[1:] + [pred(x, t) if step < steps else m[-1]]
+        return x
+    if method == "singlestep":
+        if order == 3:
+            K = steps // 3 + 1
+            orders = [3] * (K - 2) + [2, 1] if steps % 3 == 0 else ([3] * (K - 1) + [1] if steps % 3 == 1 else [3] * (K - 1) + [2])
+        elif order == 2:
+            K = steps // 2 if steps % 2 == 0 else steps // 2 + 1
+            orders = [2] * K if steps % 2 == 0 else [2] * (K - 1) + [1]
+        else:
+            K, orders = 1, [1] * steps
+        if skip_type == "logSNR":
+            outer = _time_steps(ns, skip_type, t_T, t_0, K)
+        else:
+            outer = _time_steps(ns, skip_type, t_T, t_0, steps)[torch.cumsum(torch.tensor([0] + orders), 0)]
+    else:
+        K = steps // order
+        orders = [order] * K
+        outer = _time_steps(ns, skip_type, t_T, t_0, K)
+    for step, o in enumerate(orders):
+        s, t = outer[step:step + 1], outer[step + 1:step + 2]
+        inner = _time_steps(ns, skip_type, s.item(), t.item(), o)
+        lam_in = ns.lam(inner)
+        h = lam_in[-1] - lam_in[0]
+        r1 = None if o <= 1 else (lam_in[1] - lam_in[0]) / h
+        r2 = None if o <= 2 else (lam_in[2] - lam_in[0]) / h
+        if o == 1:
+            x = first(x, s, t, pred(x, s))
+        elif o == 2:
+            x = single2(x, s, t, r1)
+        else:
+            x = single3(x, s, t, r1, r2)
+    return x
+
+
+# ----------------------------------------------------------------------------
+# training objective, forward (diffusion_ddpm_pan.py:692-766)
+# ----------------------------------------------------------------------------
+def p_losses(sb, model, x_start, t, noise, cond, pred_mode="x_start", loss_type="l1", self_cond=False):
+    """`t`, `noise` and the self-conditioning coin are INPUTS here (the reference draws them: :694,697,702)."""
+    e = lambda k: _ex(sb[k], t)
+    x_noisy = e("sqrt_alphas_cumprod") * x_start + e("sqrt_one_minus_alphas_cumprod") * noise
+    x0_of = {
+        "noise": lambda out: e("sqrt_recip_alphas_cumprod") * x_noisy - e("sqrt_recipm1_alphas_cumprod") * out,
+        "x_start": lambda out: out,
+        "pred_v": lambda out: e("sqrt_alphas_cumprod") * x_noisy - e("sqrt_one_minus_alphas_cumprod") * out,
+    }[pred_mode]
+    sc = x0_of(model(x_noisy, t, cond, None)) if self_cond else None
+    pred = model(x_noisy, t, cond, sc)
+    if pred_mode == "noise":
+        target, recon = noise, x0_of(pred)
+    elif pred_mode == "x_start":
+        target, recon = x_start, pred
+    else:
+        target = e("sqrt_alphas_cumprod") * noise - e("sqrt_one_minus_alphas_cumprod") * x_start
+        recon = x0_of(target)
+    # nn.L1Loss() / nn.MSELoss() reduce to a SCALAR (:189-193) before the p2 weight is applied, so `extract(..., loss.shape)` is [B] and
+    # the objective is mean(l) * mean_b(p2_loss_weight[t_b]) (:759-762) -- not a per-sample weighting.
+    l = (target - pred).abs().mean() if loss_type == "l1" else ((target - pred) ** 2).mean()
+    return (l * sb["p2_loss_weight"].gather(-1, t)).mean(), recon

@@ -53,54 +53,83 @@ __device__ __forceinline__ float haar_coef(const float* __restrict__ pl, int w, 
   return DIV(MUL(v, 0.5f), dv);
 }
 
-__global__ void wavelet_cond_kernel(ddif_wavelet_cond_t p) {
-  const int c = (int)p.c, pp = (int)p.p, h = (int)p.h, w = (int)p.w, hh = h / 2, wh = w / 2;
+// grid (ceil(h * w/4 / 256), channels of cond, batch): one thread per 4 consecutive output pixels of one cond plane, 32-bit indexing.
+// A wavelet-channel thread needs coefficient columns 2q-1 .. 2q+2 of two coefficient rows for its 4 bilinear outputs: 8 Haar
+// coefficients (16 float2 loads) instead of 16 per 4 outputs, and it also emits the two raw coefficients of its 2x2 blocks.
+__global__ void __launch_bounds__(256) wavelet_cond_kernel(ddif_wavelet_cond_t p) {
+  const int c = (int)p.c, pp = (int)p.p, h = (int)p.h, w = (int)p.w, hh = h / 2, wh = w / 2, wq = w / 4;
   const int cw = c + 3 * pp, ct = c + pp + cw;
-  const int64_t hw = (int64_t)h * w;
-  const int64_t items = p.batch * ct * hw;
+  const int ch = blockIdx.y, b = blockIdx.z;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= h * wq) return;
+  const int oy = idx / wq, q = idx - oy * wq;
+  const size_t hw = (size_t)h * w;
   const float dv = (float)p.divisor;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t pix = i % hw;
-    const int ch = (int)((i / hw) % ct);
-    const int64_t b = i / (hw * ct);
-    float v;
-    if (ch < c) {
-      v = DIV(p.lms[(b * c + ch) * hw + pix], dv);
-    } else if (ch < c + pp) {
-      v = DIV(p.pan[(b * pp + (ch - c)) * hw + pix], dv);
-    } else {
-      const int k = ch - c - pp;  // wavelet channel: [LL(lms) x c | pan sub-band 0 x p | sub-band 1 x p | sub-band 2 x p]
-      const float* pl;
-      int coef;
-      if (k < c) {
-        pl = p.lms + (b * c + k) * hw;
-        coef = 0;
-      } else {
-        const int g = (k - c) / pp, j = (k - c) % pp;
-        pl = p.pan + (b * pp + j) * hw;
-        coef = p.order == 0 ? (g == 0 ? 1 : (g == 1 ? 3 : 2)) : g + 1;  // Pan: h, d, v;  HISR: h, v, d
-      }
-      const int oy = (int)(pix / w), ox = (int)(pix % w);
-      float sy = 0.5f * ((float)oy + 0.5f) - 0.5f, sx = 0.5f * ((float)ox + 0.5f) - 0.5f;
-      if (sy < 0.f) sy = 0.f;
-      if (sx < 0.f) sx = 0.f;
-      int y0 = (int)sy, x0 = (int)sx;
-      if (y0 > hh - 1) y0 = hh - 1;
-      if (x0 > wh - 1) x0 = wh - 1;
-      const int y1 = y0 + (y0 < hh - 1 ? 1 : 0), x1 = x0 + (x0 < wh - 1 ? 1 : 0);
-      const float ly1 = sy - (float)y0, ly0 = 1.f - ly1, lx1 = sx - (float)x0, lx0 = 1.f - lx1;
-      const float v00 = haar_coef(pl, w, y0, x0, coef, dv), v01 = haar_coef(pl, w, y0, x1, coef, dv);
-      const float v10 = haar_coef(pl, w, y1, x0, coef, dv), v11 = haar_coef(pl, w, y1, x1, coef, dv);
-      v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);  // same expression as cond_assemble_kernel
-      if (p.wav && !(oy & 1) && !(ox & 1))  // one thread per 2x2 block also emits the raw coefficient
-        p.wav[((b * cw + k) * hh + (oy >> 1)) * wh + (ox >> 1)] = haar_coef(pl, w, oy >> 1, ox >> 1, coef, dv);
-    }
-    p.cond[i] = v;
+  float4* dst = reinterpret_cast<float4*>(p.cond + ((size_t)b * ct + ch) * hw + (size_t)oy * w + 4 * q);
+  if (ch < c + pp) {
+    const float* src = ch < c ? p.lms + ((size_t)b * c + ch) * hw : p.pan + ((size_t)b * pp + (ch - c)) * hw;
+    const float4 v = *reinterpret_cast<const float4*>(src + (size_t)oy * w + 4 * q);
+    *dst = make_float4(DIV(v.x, dv), DIV(v.y, dv), DIV(v.z, dv), DIV(v.w, dv));
+    return;
+  }
+  const int k = ch - c - pp;  // wavelet channel: [LL(lms) x c | pan sub-band 0 x p | sub-band 1 x p | sub-band 2 x p]
+  const float* pl;
+  int coef;
+  if (k < c) {
+    pl = p.lms + ((size_t)b * c + k) * hw;
+    coef = 0;
+  } else {
+    const int g = (k - c) / pp, j = (k - c) % pp;
+    pl = p.pan + ((size_t)b * pp + j) * hw;
+    coef = p.order == 0 ? (g == 0 ? 1 : (g == 1 ? 3 : 2)) : g + 1;  // Pan: h, d, v;  HISR: h, v, d
+  }
+  float sy = 0.5f * ((float)oy + 0.5f) - 0.5f;
+  if (sy < 0.f) sy = 0.f;
+  int y0 = (int)sy;
+  if (y0 > hh - 1) y0 = hh - 1;
+  const int y1 = y0 + (y0 < hh - 1 ? 1 : 0);
+  const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+  float cf[2][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int bx = 2 * q - 1 + j;
+    bx = bx < 0 ? 0 : (bx > wh - 1 ? wh - 1 : bx);
+    cf[0][j] = haar_coef(pl, w, y0, bx, coef, dv);
+    cf[1][j] = y1 == y0 ? cf[0][j] : haar_coef(pl, w, y1, bx, coef, dv);
+  }
+  float o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int ox = 4 * q + e;
+    float sx = 0.5f * ((float)ox + 0.5f) - 0.5f;
+    if (sx < 0.f) sx = 0.f;
+    int x0 = (int)sx;
+    if (x0 > wh - 1) x0 = wh - 1;
+    const int x1 = x0 + (x0 < wh - 1 ? 1 : 0);
+    const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+    // cached column index of coefficient column x: x - (2q - 1), valid after the same clamping (edge columns repeat)
+    int j0 = x0 - (2 * q - 1), j1 = x1 - (2 * q - 1);
+    j0 = j0 < 0 ? 0 : (j0 > 3 ? 3 : j0);
+    j1 = j1 < 0 ? 0 : (j1 > 3 ? 3 : j1);
+    float v00, v01, v10, v11;
+    // compile-time indices after unrolling e: (e=0: cols 0,1) (e=1,2: cols 1,2) (e=3: cols 2,3), except at the clamped image edges
+    v00 = j0 == 0 ? cf[0][0] : (j0 == 1 ? cf[0][1] : (j0 == 2 ? cf[0][2] : cf[0][3]));
+    v01 = j1 == 0 ? cf[0][0] : (j1 == 1 ? cf[0][1] : (j1 == 2 ? cf[0][2] : cf[0][3]));
+    v10 = j0 == 0 ? cf[1][0] : (j0 == 1 ? cf[1][1] : (j0 == 2 ? cf[1][2] : cf[1][3]));
+    v11 = j1 == 0 ? cf[1][0] : (j1 == 1 ? cf[1][1] : (j1 == 2 ? cf[1][2] : cf[1][3]));
+    o[e] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);  // same expression as cond_assemble_kernel
+  }
+  *dst = make_float4(o[0], o[1], o[2], o[3]);
+  if (p.wav && !(oy & 1)) {  // raw coefficients of blocks (oy/2, 2q) and (oy/2, 2q+1): row oy/2 is y1 (y0 at the top edge)
+    const int r = (y1 == (oy >> 1)) ? 1 : 0;
+    *reinterpret_cast<float2*>(p.wav + (((size_t)b * cw + k) * hh + (oy >> 1)) * wh + 2 * q) = make_float2(cf[r][1], cf[r][2]);
   }
 }
 int launch_wavelet_cond(const ddif_wavelet_cond_t& p, cudaStream_t s) {
-  if (p.h % 2 || p.w % 2 || p.c < 1 || p.p < 1 || p.order < 0 || p.order > 1) return DDIF_ERR_SHAPE;
-  wavelet_cond_kernel<<<pgrid(p.batch * (2 * p.c + 4 * p.p) * p.h * p.w), 256, 0, s>>>(p);
+  if (p.h % 2 || p.w % 4 || p.c < 1 || p.p < 1 || p.order < 0 || p.order > 1 || p.batch > 65535 || p.h * p.w > (1 << 28)) return DDIF_ERR_SHAPE;
+  if (p.batch < 1) return DDIF_OK;
+  const dim3 grid((unsigned)ceil_div(p.h * (p.w / 4), 256), (unsigned)(2 * p.c + 4 * p.p), (unsigned)p.batch);
+  wavelet_cond_kernel<<<grid, 256, 0, s>>>(p);
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }
@@ -186,54 +215,68 @@ int launch_axpby(const ddif_axpby_t& p, cudaStream_t s) {
 }
 
 // ---- validation metrics: partial sums per image ---------------------------------------------------------------------------
-// grid (chunks, batch).  Pass 1 (blockIdx.z == 0): spectral angle per pixel; pass 2 (blockIdx.z = 1 + band): band sums.
-__global__ void metrics_kernel(ddif_metrics_t p) {
-  __shared__ double sh[8];
+// grid (1 + c, batch): block (0, b) sums the spectral angles of image b, block (1 + k, b) the six sums of band k; each block owns its
+// outputs (plain stores, no atomics), 32-bit pixel indexing, one shared-memory stage for all of a block's sums.
+template <int N>
+__device__ __forceinline__ void block_sums(double (&v)[N], double* sh /* [N][8] */, double* out) {
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0)
+#pragma unroll
+    for (int j = 0; j < N; ++j) sh[j * 8 + w] = v[j];
+  __syncthreads();
+  if (threadIdx.x < N) {
+    double r = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[threadIdx.x * 8 + i];
+    out[threadIdx.x] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256) metrics_kernel(ddif_metrics_t p) {
+  __shared__ double sh[6 * 8];
   const int b = blockIdx.y;
   const int c = (int)p.c, h = (int)p.h, w = (int)p.w;
   const int hc = h - 1, wc = w - 1;  // bounds cut [0:-1] on both axes
-  const int64_t npix = (int64_t)hc * wc, hw = (int64_t)h * w;
+  const int npix = hc * wc;
+  const size_t hw = (size_t)h * w;
   const float* ga = p.gt + (size_t)b * c * hw;
   const float* oa = p.out + (size_t)b * c * hw;
   double* out = p.sums + (size_t)b * (2 + 6 * c);
-  if (blockIdx.z == 0) {
-    double tot = 0.0, num = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t off = (i / wc) * w + (i % wc);
+  if (blockIdx.x == 0) {
+    double v[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+      const int y = i / wc, off = y * w + (i - y * wc);
       float s1 = 0.f, na = 0.f, nb = 0.f;  // fp32 like the reference's torch float32 reductions over the band axis
       for (int k = 0; k < c; ++k) {
         const float a = ga[k * hw + off], o = oa[k * hw + off];
         s1 += a * o; na += a * a; nb += o * o;
       }
       const float t = sqrtf(na * nb);
-      if (t > 0.f) num += 1.0;
+      if (t > 0.f) v[1] += 1.0;
       const float ang = acosf(s1 / t);
-      if (!isnan(ang)) tot += (double)ang;
+      if (!isnan(ang)) v[0] += (double)ang;
     }
-    const double t0 = block_sum(tot, sh);
-    const double t1 = block_sum(num, sh);
-    if (threadIdx.x == 0) { atomicAdd(out, t0); atomicAdd(out + 1, t1); }
+    block_sums<2>(v, sh, out);
   } else {
-    const int k = blockIdx.z - 1;
+    const int k = blockIdx.x - 1;
+    const float* gk = ga + k * hw;
+    const float* ok = oa + k * hw;
     double v[6] = {0, 0, 0, 0, 0, 0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t off = (i / wc) * w + (i % wc);
-      const float a = ga[k * hw + off], o = oa[k * hw + off];
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+      const int y = i / wc, off = y * w + (i - y * wc);
+      const float a = gk[off], o = ok[off];
       const float d = a - o;
       v[0] += (double)(d * d); v[1] += a; v[2] += o; v[3] += (double)a * a; v[4] += (double)o * o; v[5] += (double)a * o;
     }
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const double t = block_sum(v[j], sh);
-      if (threadIdx.x == 0) atomicAdd(out + 2 + 6 * k + j, t);
-    }
+    block_sums<6>(v, sh, out + 2 + 6 * k);
   }
 }
 int launch_metrics(const ddif_metrics_t& p, cudaStream_t s) {
-  if (p.h < 2 || p.w < 2 || p.c < 1 || p.c > 1024 || p.batch < 1 || p.batch > 65535) return DDIF_ERR_SHAPE;
-  int64_t chunks = ceil_div((p.h - 1) * (p.w - 1), 256 * 4);
-  if (chunks > 64) chunks = 64;
-  metrics_kernel<<<dim3((unsigned)chunks, (unsigned)p.batch, (unsigned)(1 + p.c)), 256, 0, s>>>(p);
+  if (p.h < 2 || p.w < 2 || p.c < 1 || p.c > 1024 || p.batch < 1 || p.batch > 65535 || p.h * p.w > (1 << 30)) return DDIF_ERR_SHAPE;
+  metrics_kernel<<<dim3((unsigned)(1 + p.c), (unsigned)p.batch), 256, 0, s>>>(p);
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }

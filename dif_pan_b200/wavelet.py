@@ -92,8 +92,8 @@ def make_cond(lms_dn: torch.Tensor, pan_dn: torch.Tensor, division: float = 1.0,
     lms_dn, pan_dn = lms_dn.to(torch.float32).contiguous(), pan_dn.to(torch.float32).contiguous()
     B, C, H, W = lms_dn.shape
     P = pan_dn.shape[1]
-    if pan_dn.shape[0] != B or tuple(pan_dn.shape[2:]) != (H, W) or H % 2 or W % 2:
-        raise ValueError(f"lms {tuple(lms_dn.shape)} and pan {tuple(pan_dn.shape)} must share batch and an even H x W")
+    if pan_dn.shape[0] != B or tuple(pan_dn.shape[2:]) != (H, W) or H % 2 or W % 4:
+        raise ValueError(f"lms {tuple(lms_dn.shape)} and pan {tuple(pan_dn.shape)} must share batch and H x W with even H and W % 4 == 0")
     cond = torch.empty(B, 2 * C + 4 * P, H, W, dtype=torch.float32, device=lms_dn.device)
     wav = torch.empty(B, C + 3 * P, H // 2, W // 2, dtype=torch.float32, device=lms_dn.device) if return_wavelets else None
     _lib.launch("ddif_wavelet_cond_t", _stream(lms_dn), lms=lms_dn.data_ptr(), pan=pan_dn.data_ptr(), cond=cond.data_ptr(),

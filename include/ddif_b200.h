@@ -191,7 +191,7 @@ typedef struct { const float* a; const float* b; const float* weight; double* ou
 /* out[b,i] = ca[b]*x[b,i] + cb[b]*y[b,i]  (ca, cb: float[batch] on the device) */
 typedef struct { const float* x; const float* y; const float* ca; const float* cb; float* out; int64_t batch, chw; } ddif_axpby_t;
 /* gt, out: [batch, c, h, w] fp32.  Only pixels y < h-1, x < w-1 enter (the reference's bounds cut `[0:-1]`, :300-302).
- * sums: double[batch][2 + 6*c], zeroed by the caller: {sum of spectral angles, pixels with |a||b| > 0,
+ * sums: double[batch][2 + 6*c] (every entry is written; no pre-zeroing needed): {sum of spectral angles, pixels with |a||b| > 0,
  * per band: sum (a-b)^2, sum a, sum b, sum a^2, sum b^2, sum a*b}  with a = gt, b = out. */
 typedef struct { const float* gt; const float* out; double* sums; int64_t batch, c, h, w; } ddif_metrics_t;
 /* dir 0: tiles[(b*ny + iy)*nx + ix, c, :, :] = scene[b, c, iy*sy : iy*sy+ph, ix*sx : ix*sx+pw]
@@ -200,7 +200,7 @@ typedef struct { float* scene; float* tiles; int64_t batch, c, h, w, ph, pw, sy,
 /* cond[b] = cat(lms/div, pan/div, up2(LL(lms)/div), up2(pan sub-bands / div))  in ONE pass from the raw arrays.
  * lms [batch, c, h, w], pan [batch, p, h, w] raw values; order 0 = Pan datasets (cH, cD, cV; pan_dataset.py:139-141),
  * 1 = HISR (cH, cV, cD; hisr.py:57-59); up2 = bilinear x2, align_corners=False (diffusion_engine.py:224-226).
- * wav (optional): [batch, c + 3p, h/2, w/2] also receives the wavelet stack the reference datasets return. */
+ * wav (optional): [batch, c + 3p, h/2, w/2] also receives the wavelet stack the reference datasets return.  h even, w % 4 == 0. */
 typedef struct { const float* lms; const float* pan; float* cond; float* wav; int64_t batch, c, p, h, w, order; double divisor; } ddif_wavelet_cond_t;
 /* x: [planes, h, w] fp32 (output for IDWT); 4 sub-bands each [planes, h/2, w/2] (LL, cH, cV, cD).
  * DWT: every coefficient is divided by `divisor` (the dataset "division", pan_dataset.py:127-134); IDWT ignores it. */

@@ -201,6 +201,28 @@ int launch_loss(const ddif_loss_t& p, cudaStream_t s) {
   return DDIF_OK;
 }
 
+// ---- adaptive DPM-Solver: per-sample error norm (dpm_solver.py:1003-1006), one block per sample ---------------------------------
+__global__ void __launch_bounds__(256) dpm_err_kernel(ddif_dpm_err_t p) {
+  __shared__ double sh[8];
+  const size_t base = (size_t)blockIdx.x * p.chw;
+  const float atol = (float)p.atol, rtol = (float)p.rtol;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < p.chw; i += blockDim.x) {
+    const float xl = p.x_lower[base + i];
+    const float delta = fmaxf(atol, MUL(rtol, fmaxf(fabsf(xl), fabsf(p.x_prev[base + i]))));
+    const float e = DIV(SUB(p.x_higher[base + i], xl), delta);
+    acc += (double)MUL(e, e);
+  }
+  const double t = block_sum(acc, sh);
+  if (threadIdx.x == 0) p.out[blockIdx.x] = t;
+}
+int launch_dpm_err(const ddif_dpm_err_t& p, cudaStream_t s) {
+  if (p.batch < 1 || p.batch > 0x7fffffff || !p.out) return DDIF_ERR_ARG;
+  dpm_err_kernel<<<(unsigned)p.batch, 256, 0, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
 __global__ void axpby_kernel(ddif_axpby_t p) {
   const int64_t n = p.batch * p.chw;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {

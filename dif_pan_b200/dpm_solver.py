@@ -11,8 +11,9 @@ Implemented: algorithm_type 'dpmsolver++' and 'dpmsolver'; method 'multistep' (o
 'singlestep' (the "DPM-Solver-fast" order schedule, dpm.py:490-548) and 'singlestep_fixed' (orders 1-3, one fused
 `ddif_dpm_single_f32` kernel per denoiser evaluation); skip types time_uniform / time_quadratic / logSNR; model types
 x_start / noise / v; guidance 'uncond' or 'classifier-free' with scale 1 (the wiring SURVEY.md §3.3 names).
-method='adaptive' (dpm.py:964-1018), solver_type='taylor', thresholding correctors and denoise_to_zero raise
-NotImplementedError (not used by any BASELINE config).
+method='adaptive' (dpm.py:964-1018; one error-norm reduction kernel + a host scalar decision per iteration) is implemented
+as well.  solver_type='taylor', thresholding correctors and denoise_to_zero raise NotImplementedError (not used by any
+BASELINE config).
 
 Reference quirk kept out: model_wrapper multiplies `[B]`-shaped alpha_t against `[B,C,H,W]` (dpm.py:299-300),
 which only broadcasts for B == 1 or B == W; all entries are equal, so a scalar multiply is the same arithmetic and
@@ -273,6 +274,87 @@ class DPM_Solver:
                 (s1, s2, 1, f(lead(s2)), f(amp(s2) * phi_12), sgn * f(c2_s2)),
                 (s2, None, 1, f(lead(t)), f(amp(t) * phi_1), sgn * f(c2_t))]
 
+    def dpm_solver_adaptive(self, x, order, t_T, t_0, h_init=0.05, atol=0.0078, rtol=0.05, theta=0.9, t_err=1e-5, solver_type="dpmsolver"):
+        """Adaptive step-size solver (dpm.py:964-1018): a lower-order and a higher-order singlestep update share their denoiser
+        evaluations; the per-sample error norm is ONE reduction kernel (`ddif_dpm_err_f32`) and the accept / step-size decision is a
+        host scalar per iteration, as in the reference (`E.max()`, `torch.all(E <= 1.)` synchronise there too)."""
+        if order not in (2, 3):
+            raise ValueError("For adaptive step size solver, order must be 2 or 3, got {}".format(order))
+        if solver_type != "dpmsolver":
+            raise NotImplementedError("solver_type='taylor' is not on the CUDA path")
+        if not x.is_cuda:
+            raise RuntimeError("dif_pan_b200 sampler kernels run on CUDA only (no CPU fallback)")
+        ns, wm = self.noise_schedule, self.wrapped
+        B, dev = x.shape[0], x.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        fast = isinstance(wm.model, UNetSR3) and wm.condition is not None and not wm.model_kwargs
+        predict = 0 if self.algorithm_type == "dpmsolver++" else 1
+        mt = MODEL_TYPES[wm.model_type]
+        s = t_T * torch.ones((1,))
+        lambda_s = ns.marginal_lambda(s)
+        lambda_0 = ns.marginal_lambda(t_0 * torch.ones_like(s))
+        h = h_init * torch.ones_like(s)
+        nfe = 0
+        with torch.no_grad():
+            if fast:
+                rt = wm.model.runtime(B, x.shape[2], x.shape[3])
+                rt.set_cond(wm.condition)
+                xe, tbuf = rt.x_buf, rt.t_buf
+            else:
+                xe, tbuf = torch.empty_like(x, dtype=torch.float32).contiguous(), None
+            xs = x.to(torch.float32).clone().contiguous()       # state at time s
+            x_prev = xs.clone()
+            x_lo, x_hi = torch.empty_like(xs), torch.empty_like(xs)
+            m_s, m_k = torch.empty_like(xs), torch.empty_like(xs)
+            err = torch.empty(B, dtype=torch.float64, device=dev)
+
+            def evaluate(t_ev):
+                if fast:
+                    tbuf.fill_(float(wm.input_time(t_ev)))
+                    rt.step()
+                    return rt.out_buf
+                return wm.raw(xe, t_ev.reshape(-1)[:1].to(dev).expand(B)).contiguous()
+
+            def stage(out, t_ev, mode, c0, c1, c2, m_cur, x_out):
+                _lib.launch("ddif_dpm_single_t", stream, x_base=xs.data_ptr(), x_eval=xe.data_ptr(), model_out=out.data_ptr(), m_cur=m_cur.data_ptr(),
+                            m_a=m_s.data_ptr() if mode == 1 else None, x_out=x_out.data_ptr(), time_out=None, n=xs.numel(), batch=B, model_type=mt,
+                            predict=predict, mode=mode, alpha_e=float(ns.marginal_alpha(t_ev)), sigma_e=float(ns.marginal_std(t_ev)), c0=c0, c1=c1,
+                            c2=c2, t_next_in=0.0)
+
+            while torch.abs((s - t_0)).mean() > t_err:
+                t = ns.inverse_lambda(lambda_s + h)
+                xe.copy_(xs)
+                out = evaluate(s)
+                if order == 2:
+                    (_, _, _, a0, a1, _), = self._single_coefficients(s, t, 1, None, None)
+                    hi = self._single_coefficients(s, t, 2, 0.5, None)
+                    stage(out, s, 0, a0, a1, 0.0, m_s, x_lo)                         # x_lower = DPM-Solver-1, model_s
+                    stage(out, s, 0, hi[0][3], hi[0][4], 0.0, m_s, xe)               # x_s1
+                    out = evaluate(hi[1][0])
+                    stage(out, hi[1][0], 1, hi[1][3], hi[1][4], hi[1][5], m_k, x_hi)  # x_higher = DPM-Solver-2
+                else:
+                    r1, r2 = 1.0 / 3.0, 2.0 / 3.0
+                    lo = self._single_coefficients(s, t, 2, r1, None)
+                    hi = self._single_coefficients(s, t, 3, r1, r2)
+                    stage(out, s, 0, lo[0][3], lo[0][4], 0.0, m_s, xe)               # x_s1 (shared by both orders), model_s
+                    out = evaluate(lo[1][0])
+                    stage(out, lo[1][0], 1, lo[1][3], lo[1][4], lo[1][5], m_k, x_lo)  # x_lower = DPM-Solver-2 with r1 = 1/3
+                    stage(out, hi[1][0], 1, hi[1][3], hi[1][4], hi[1][5], m_k, xe)    # x_s2 from model_s, model_s1
+                    out = evaluate(hi[2][0])
+                    stage(out, hi[2][0], 1, hi[2][3], hi[2][4], hi[2][5], m_k, x_hi)  # x_higher = DPM-Solver-3
+                _lib.launch("ddif_dpm_err_t", stream, x_higher=x_hi.data_ptr(), x_lower=x_lo.data_ptr(), x_prev=x_prev.data_ptr(), out=err.data_ptr(),
+                            batch=B, chw=xs[0].numel(), atol=float(atol), rtol=float(rtol))
+                E = torch.sqrt(err / float(xs[0].numel())).max().to(torch.float32).cpu()
+                if torch.all(E <= 1.0):
+                    xs, x_hi = x_hi, xs
+                    x_prev, x_lo = x_lo, x_prev
+                    s = t
+                    lambda_s = ns.marginal_lambda(s)
+                h = torch.min(theta * h * torch.float_power(E, -1.0 / order).float(), lambda_0 - lambda_s)
+                nfe += order
+            self.last_nfe = nfe
+            return xs.clone()
+
     def _sample_singlestep(self, x, steps, order, skip_type, method, t_T, t_0, return_intermediate):
         """dpm.py:1222-1240: every outer step s -> t evaluates the denoiser `order` times (at s, s1[, s2]); each evaluation is
         followed by ONE fused kernel (model_wrapper round trip + prediction + the stage's linear update)."""
@@ -336,10 +418,10 @@ class DPM_Solver:
         t_0 = 1.0 / ns.total_N if t_end is None else t_end
         t_T = ns.T if t_start is None else t_start
         assert t_0 > 0 and t_T > 0, "Time range needs to be greater than 0. For discrete-time DPMs, it needs to be in [1 / N, 1], where N is the length of betas array"
-        if method not in ("multistep", "singlestep", "singlestep_fixed"):
-            if method == "adaptive":
-                raise NotImplementedError("method='adaptive' (data-dependent step-size control, dpm.py:964-1018) is not on the CUDA path")
+        if method not in ("multistep", "singlestep", "singlestep_fixed", "adaptive"):
             raise ValueError("Got wrong method {}".format(method))
+        if return_intermediate:
+            assert method in ["multistep", "singlestep", "singlestep_fixed"], "Cannot use adaptive solver when saving intermediate values"
         if solver_type != "dpmsolver":
             if solver_type == "taylor":
                 raise NotImplementedError("solver_type='taylor' is not on the CUDA path")
@@ -350,6 +432,8 @@ class DPM_Solver:
             raise ValueError("Solver order must be 1 or 2 or 3, got {}".format(order))
         if not x.is_cuda:
             raise RuntimeError("dif_pan_b200 sampler kernels run on CUDA only (no CPU fallback)")
+        if method == "adaptive":
+            return self.dpm_solver_adaptive(x, order=order, t_T=t_T, t_0=t_0, atol=atol, rtol=rtol, solver_type=solver_type)
         if method != "multistep":
             return self._sample_singlestep(x, steps, order, skip_type, method, t_T, t_0, return_intermediate)
         assert steps >= order

@@ -58,6 +58,7 @@ enum ddif_op_kind {
   DDIF_OP_AXPBY = 25,        /* out = ca[b]*x + cb[b]*y per sample (predict_start_from_noise / _v)  diffusion_ddpm_pan.py:284-312 */
   DDIF_OP_METRICS = 26,      /* per-image partial sums of SAM / ERGAS / PSNR / CC                  utils/_metric_legacy.py:299-346 */
   DDIF_OP_TILE = 27,         /* scene -> patch batch (gather) and patch batch -> scene (overlap-averaged stitch) */
+  DDIF_OP_DPM_ERR = 29,      /* adaptive DPM-Solver error estimate per sample                      dpm_solver.py:1003-1006 */
   DDIF_OP_WAVELET_COND = 28  /* raw lms, pan -> cond in one pass: Haar DWT, /division, channel order, bilinear up, concat
                                 dataset/pan_dataset.py:73-142, dataset/hisr.py:48-59, diffusion_engine.py:221-228 */
 };
@@ -185,6 +186,9 @@ typedef struct {
   int64_t n, batch, model_type, predict, mode;
   double alpha_e, sigma_e, c0, c1, c2, t_next_in;
 } ddif_dpm_single_t;
+/* Adaptive step-size control (dpm_solver.py:1003-1006): out[b] = sum_i ((x_higher - x_lower) / max(atol, rtol*max(|x_lower|, |x_prev|)))^2 for
+ * sample b (every entry written); the host takes E = max_b sqrt(out[b] / chw). */
+typedef struct { const float* x_higher; const float* x_lower; const float* x_prev; double* out; int64_t batch, chw; double atol, rtol; } ddif_dpm_err_t;
 /* out[0] += sum_b weight[b] * sum_i l(a[b,i], b[b,i]); squared 0: |a-b| (l1), 1: (a-b)^2 (l2).  weight may be NULL (= 1).
  * `out` is a device double the caller zeroes; the mean is out[0] / (batch*chw). */
 typedef struct { const float* a; const float* b; const float* weight; double* out; int64_t batch, chw, squared; } ddif_loss_t;
@@ -249,6 +253,7 @@ int ddif_dpmpp_step_f32(const ddif_dpmpp_step_t* p, ddif_stream_t s);
 int ddif_q_sample_f32(const ddif_q_sample_t* p, ddif_stream_t s);
 int ddif_conv_igemm_bf16(const ddif_gemm_t* p, ddif_stream_t s);
 int ddif_dpm_single_f32(const ddif_dpm_single_t* p, ddif_stream_t s);
+int ddif_dpm_err_f32(const ddif_dpm_err_t* p, ddif_stream_t s);
 int ddif_loss_f32(const ddif_loss_t* p, ddif_stream_t s);
 int ddif_metrics_f32(const ddif_metrics_t* p, ddif_stream_t s);
 int ddif_tile_f32(const ddif_tile_t* p, ddif_stream_t s);

@@ -493,6 +493,67 @@ def dpm_sample(model, ns: "VPSchedule", x, cond=None, steps=20, order=2, skip_ty
     return x
 
 
+def dpm_adaptive(model, ns: "VPSchedule", x, cond=None, order=2, algorithm="dpmsolver++", model_type="x_start", h_init=0.05, atol=0.0078,
+                 rtol=0.05, theta=0.9, t_err=1e-5):
+    """dpm_solver_adaptive (dpm.py:964-1018), solver_type 'dpmsolver'.  Returns (x_0, nfe)."""
+    pp = algorithm == "dpmsolver++"
+    t_0, t_T = 1.0 / ns.total_N, ns.T
+    pred = lambda xx, tt: dpm_prediction(ns, model, xx, tt, cond, model_type, algorithm)
+    la = ns.log_alpha
+    lead = (lambda u, s: ns.std(u) / ns.std(s)) if pp else (lambda u, s: torch.exp(la(u) - la(s)))
+    amp = ns.alpha if pp else ns.std
+    em = (lambda v: torch.expm1(-v)) if pp else torch.expm1
+    sgn = 1.0 if pp else -1.0
+
+    def first(x, s, t):
+        m_s = pred(x, s)
+        return lead(t, s) * x - amp(t) * em(ns.lam(t) - ns.lam(s)) * m_s, m_s
+
+    def second(x, s, t, r1, m_s=None):
+        h = ns.lam(t) - ns.lam(s)
+        s1 = inverse_lambda(ns, ns.lam(s) + r1 * h)
+        m_s = pred(x, s) if m_s is None else m_s
+        x_s1 = lead(s1, s) * x - (amp(s1) * em(r1 * h)) * m_s
+        m_s1 = pred(x_s1, s1)
+        return lead(t, s) * x - (amp(t) * em(h)) * m_s - (0.5 / r1) * (amp(t) * em(h)) * (m_s1 - m_s), m_s, m_s1
+
+    def third(x, s, t, r1, r2, m_s, m_s1):
+        h = ns.lam(t) - ns.lam(s)
+        s2 = inverse_lambda(ns, ns.lam(s) + r2 * h)
+        phi_1 = em(h)
+        if pp:
+            phi_22 = torch.expm1(-r2 * h) / (r2 * h) + 1.0
+            phi_2 = phi_1 / h + 1.0
+        else:
+            phi_22 = torch.expm1(r2 * h) / (r2 * h) - 1.0
+            phi_2 = phi_1 / h - 1.0
+        x_s2 = lead(s2, s) * x - (amp(s2) * em(r2 * h)) * m_s + sgn * (r2 / r1 * (amp(s2) * phi_22)) * (m_s1 - m_s)
+        m_s2 = pred(x_s2, s2)
+        return lead(t, s) * x - (amp(t) * phi_1) * m_s + sgn * ((1.0 / r2) * (amp(t) * phi_2)) * (m_s2 - m_s)
+
+    s = t_T * torch.ones((1,))
+    lambda_s = ns.lam(s)
+    lambda_0 = ns.lam(t_0 * torch.ones_like(s))
+    h = h_init * torch.ones_like(s)
+    x_prev, nfe = x, 0
+    while torch.abs(s - t_0).mean() > t_err:
+        t = inverse_lambda(ns, lambda_s + h)
+        if order == 2:
+            x_lower, m_s = first(x, s, t)
+            x_higher, _, _ = second(x, s, t, 0.5, m_s)
+        else:
+            x_lower, m_s, m_s1 = second(x, s, t, 1.0 / 3.0)
+            x_higher = third(x, s, t, 1.0 / 3.0, 2.0 / 3.0, m_s, m_s1)
+        delta = torch.max(torch.ones_like(x) * atol, rtol * torch.max(torch.abs(x_lower), torch.abs(x_prev)))
+        E = torch.sqrt(torch.square(((x_higher - x_lower) / delta).reshape(x.shape[0], -1)).mean(dim=-1, keepdim=True)).max()
+        if torch.all(E <= 1.0):
+            x, s, x_prev = x_higher, t, x_lower
+            lambda_s = ns.lam(s)
+        h = torch.min(theta * h * torch.float_power(E, -1.0 / order).float(), lambda_0 - lambda_s)
+        nfe += order
+    return x, nfe
+
+
 # ----------------------------------------------------------------------------
 # training objective, forward (diffusion_ddpm_pan.py:692-766)
 # ----------------------------------------------------------------------------

@@ -232,3 +232,42 @@ def test_scene_driver_whole_and_tiled():
     assert torch.equal(out_t, (dp.stitch_tiles(manual, (128, 128)) * spec.division).clamp(0, spec.division))
     got = dmetrics.batch_metrics(d["hr"].to(DEV), out_t / spec.division)
     assert np.isfinite(list(got.values())).all()
+
+
+# ---- adaptive DPM-Solver ------------------------------------------------------------------------------------------------------------------
+from test_oracle_variants import ADAPTIVE_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("order,algo,mtype", ADAPTIVE_CASES)
+def test_dpm_adaptive_matches_reference_golden(order, algo, mtype):
+    """Step-size control (dpm_solver.py:964-1018): fused stage kernels + one error-norm reduction per iteration; the accept / reject
+    sequence must reproduce the reference's, so the final state agrees to the solver kernels' own tolerance."""
+    g = np.load(os.path.join(GOLDEN, "dpm_variants.npz"))
+    x_T, cond = dpm_inputs(int(g["seed"]))
+    betas = torch.as_tensor(so.make_beta_schedule("cosine", 500), dtype=torch.float32)
+    ns = dp.NoiseScheduleVP("discrete", betas=betas.to(DEV))
+    wm = dp.model_wrapper(so.analytic_denoiser, ns, model_type=mtype, guidance_type="classifier-free", condition=cond.to(DEV), guidance_scale=1.0)
+    sol = dp.DPM_Solver(wm, ns, algorithm_type=algo)
+    got = sol.sample(x_T.to(DEV), order=order, method="adaptive")
+    key = f"adaptive_{order}_{algo.replace('+', 'p')}_{mtype}"
+    e = rel_max(got.cpu().numpy(), g[key])
+    print(f"{key}: nfe {sol.last_nfe}, max err / max |ref| = {e:.3g}")
+    assert e <= 2e-3
+    with pytest.raises(ValueError):
+        sol.sample(x_T.to(DEV), order=1, method="adaptive")
+
+
+def test_dpm_adaptive_unet_fast_path():
+    net, kw = _net("gf2")
+    cond = synth.make_batch("gf2", 2, seed=5)["cond"].to(DEV)
+    betas = torch.as_tensor(so.make_beta_schedule("cosine", 500), dtype=torch.float32)
+    ns = dp.NoiseScheduleVP("discrete", betas=betas.to(DEV))
+    gen = torch.Generator().manual_seed(8)
+    x_T = torch.randn(2, 4, 64, 64, generator=gen).to(DEV)
+    outs = []
+    for model in (net, lambda x, t, c: net(x, t, c)):
+        wm = dp.model_wrapper(model, ns, model_type="x_start", guidance_type="classifier-free", condition=cond, guidance_scale=1.0)
+        sol = dp.DPM_Solver(wm, ns)
+        outs.append(sol.sample(x_T.clone(), order=2, method="adaptive", atol=0.05, rtol=0.1))
+        assert 0 < sol.last_nfe < 400
+    assert torch.isfinite(outs[0]).all() and _rel(outs[0], outs[1]) < 1e-3

@@ -89,3 +89,16 @@ def test_cc_oracle_matches_reference():
     for i in range(2):
         m = metrics_oracle.sam_ergas_psnr(d["hr"][i], out[i])
         np.testing.assert_allclose([m["SAM"], m["ERGAS"], m["PSNR"], m["CC"]], g["sam_ergas_psnr_cc"][i], rtol=1e-5)
+
+
+ADAPTIVE_CASES = [(2, "dpmsolver++", "x_start"), (3, "dpmsolver++", "x_start"), (2, "dpmsolver", "x_start")]
+
+
+@pytest.mark.parametrize("order,algo,mtype", ADAPTIVE_CASES)
+def test_dpm_adaptive_oracle_matches_reference(order, algo, mtype):
+    g = np.load(os.path.join(GOLDEN, "dpm_variants.npz"))
+    x_T, cond = dpm_inputs(int(g["seed"]))
+    ns = so.VPSchedule(torch.as_tensor(so.make_beta_schedule("cosine", 500), dtype=torch.float32))
+    out, nfe = so.dpm_adaptive(so.analytic_denoiser, ns, x_T.clone(), cond, order=order, algorithm=algo, model_type=mtype)
+    key = f"adaptive_{order}_{algo.replace('+', 'p')}_{mtype}"
+    assert nfe > 0 and rel_max(out.numpy(), g[key]) <= 2e-4, (nfe, rel_max(out.numpy(), g[key]))

@@ -60,7 +60,7 @@ KIND_OF_STRUCT = {
     "ddif_fwm_weff_t": "DDIF_OP_FWM_WEFF", "ddif_ddpm_step_t": "DDIF_OP_DDPM_STEP", "ddif_ddim_step_t": "DDIF_OP_DDIM_STEP",
     "ddif_dpmpp_step_t": "DDIF_OP_DPMPP_STEP", "ddif_q_sample_t": "DDIF_OP_Q_SAMPLE", "ddif_cond_assemble_t": "DDIF_OP_COND_ASSEMBLE",
     "ddif_randn_t": "DDIF_OP_RANDN", "ddif_axpby_clip_t": "DDIF_OP_AXPBY_CLIP", "ddif_dpm_single_t": "DDIF_OP_DPM_SINGLE",
-    "ddif_loss_t": "DDIF_OP_LOSS", "ddif_dpm_err_t": "DDIF_OP_DPM_ERR", "ddif_axpby_t": "DDIF_OP_AXPBY", "ddif_metrics_t": "DDIF_OP_METRICS", "ddif_tile_t": "DDIF_OP_TILE",
+    "ddif_loss_t": "DDIF_OP_LOSS", "ddif_dpm_err_t": "DDIF_OP_DPM_ERR", "ddif_attn_block_t": "DDIF_OP_ATTN_BLOCK", "ddif_axpby_t": "DDIF_OP_AXPBY", "ddif_metrics_t": "DDIF_OP_METRICS", "ddif_tile_t": "DDIF_OP_TILE",
     "ddif_wavelet_cond_t": "DDIF_OP_WAVELET_COND",
 }
 

@@ -39,6 +39,7 @@ union OpParams {
   ddif_dpm_single_t dpm_single;
   ddif_loss_t loss;
   ddif_dpm_err_t dpm_err;
+  ddif_attn_block_t attn_block;
   ddif_axpby_t axpby;
   ddif_metrics_t metrics;
   ddif_tile_t tile;
@@ -72,6 +73,7 @@ static size_t params_size(int kind) {
     case DDIF_OP_DPM_SINGLE: return sizeof(ddif_dpm_single_t);
     case DDIF_OP_LOSS: return sizeof(ddif_loss_t);
     case DDIF_OP_DPM_ERR: return sizeof(ddif_dpm_err_t);
+    case DDIF_OP_ATTN_BLOCK: return sizeof(ddif_attn_block_t);
     case DDIF_OP_AXPBY: return sizeof(ddif_axpby_t);
     case DDIF_OP_METRICS: return sizeof(ddif_metrics_t);
     case DDIF_OP_TILE: return sizeof(ddif_tile_t);
@@ -116,6 +118,7 @@ static int dispatch(const Op& op, cudaStream_t s) {
     case DDIF_OP_DPM_SINGLE: return launch_dpm_single(op.p.dpm_single, s);
     case DDIF_OP_LOSS: return launch_loss(op.p.loss, s);
     case DDIF_OP_DPM_ERR: return launch_dpm_err(op.p.dpm_err, s);
+    case DDIF_OP_ATTN_BLOCK: return launch_attn_block(op.p.attn_block, s);
     case DDIF_OP_AXPBY: return launch_axpby(op.p.axpby, s);
     case DDIF_OP_METRICS: return launch_metrics(op.p.metrics, s);
     case DDIF_OP_TILE: return launch_tile(op.p.tile, s);

@@ -266,6 +266,12 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], net: "UNetSR3") -> Dict[str, to
         P[p + ".qkv.w"] = _pack_conv(sd[p + ".qkv.weight"])
         P[p + ".out.w"] = _pack_conv(sd[p + ".out.weight"])
         P[p + ".out.b"] = f32(sd[p + ".out.bias"])
+        C = sd[p + ".out.weight"].shape[1]
+        if C == 128:  # fused attention block (csrc/attn_block.cu): out weight with its K axis permuted for 64-byte fragment loads
+            pos = torch.arange(C, device=sd[p + ".out.weight"].device)
+            t_, ks, h_, e_ = pos // 32, (pos % 32) // 4, (pos % 4) // 2, pos % 2
+            src = 16 * ks + 8 * h_ + 2 * t_ + e_
+            P[p + ".out.wp"] = sd[p + ".out.weight"].to(torch.float32)[:, :, 0, 0][:, src].to(torch.bfloat16).contiguous()
 
     cin = net.in_channel + (net.out_channel if net.self_condition else 0)
     P["downs.0.w"] = _pack_conv(sd["downs.0.weight"], _ceil(cin, 16))
@@ -367,6 +373,7 @@ class Schedule:
         self.first_body_op = 0
         self.use_qconv = os.environ.get("DDIF_NO_QCONV") is None  # A/B switch for profiling only
         self.use_dwq = os.environ.get("DDIF_NO_DWQ") is None      # A/B switch: in-kernel depthwise q path vs composed dense 3x3
+        self.use_attn_block = os.environ.get("DDIF_NO_ATTN_BLOCK") is None  # A/B switch: fused attention block vs 4 launches
 
     @staticmethod
     def _levels(net) -> int:
@@ -464,11 +471,19 @@ class Schedule:
     def _attention(self, x: Act, p: str) -> Act:
         A, pb = self.addr, self.fwd
         C = x.C
+        ntok = x.H * x.W
+        if self.use_attn_block and ntok == 64 and C == 128 and self.net.N_HEADS == 8 and (p + ".out.wp") in A and x.stats is not None:
+            # GN + qkv + 64-token attention + out + residual + statistics in ONE kernel, one CTA per sample (csrc/attn_block.cu)
+            out = self._act(pb, p + ".out", x.B, x.H, x.W, C, stats=True)
+            pb.add("ddif_attn_block_t", label=p + ".block", flops=2.0 * x.B * ntok * C * (3 * C + C) + 4.0 * x.B * ntok * ntok * C,
+                   traffic=x.B * ntok * C * 4, x=x.buf, stats_in=x.stats, gamma=A[p + ".gamma"], beta=A[p + ".beta"], wqkv=A[p + ".qkv.w"],
+                   wout=A[p + ".out.wp"], bout=A[p + ".out.b"], out=out.buf, stats_out=out.stats, batch=x.B, ntok=ntok, c=C,
+                   heads=self.net.N_HEADS, scale=1.0 / math.sqrt(C), eps=1e-5)
+            return out
         n, _ = self._gn(pb, p + ".norm", x, A[p + ".gamma"], A[p + ".beta"], 0, name=p + ".n")
         qkv = self._act(pb, p + ".qkv", x.B, x.H, x.W, 3 * C)
         self._gemm(pb, p + ".qkv", [n], [A[p + ".qkv.w"]], 3 * C, qkv, taps=[1])
         a = self._act(pb, p + ".a", x.B, x.H, x.W, C)
-        ntok = x.H * x.W
         pb.add("ddif_attn_t", label=p + ".core", flops=4.0 * x.B * ntok * ntok * C, traffic=x.B * ntok * C * 8,
                qkv=qkv.buf, out=a.buf, batch=x.B, ntok=ntok, c=C, heads=self.net.N_HEADS, scale=1.0 / math.sqrt(C))
         out = self._act(pb, p + ".out", x.B, x.H, x.W, C, stats=True)

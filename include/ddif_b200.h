@@ -58,6 +58,7 @@ enum ddif_op_kind {
   DDIF_OP_AXPBY = 25,        /* out = ca[b]*x + cb[b]*y per sample (predict_start_from_noise / _v)  diffusion_ddpm_pan.py:284-312 */
   DDIF_OP_METRICS = 26,      /* per-image partial sums of SAM / ERGAS / PSNR / CC                  utils/_metric_legacy.py:299-346 */
   DDIF_OP_TILE = 27,         /* scene -> patch batch (gather) and patch batch -> scene (overlap-averaged stitch) */
+  DDIF_OP_ATTN_BLOCK = 30,   /* whole SelfAttention block at 64 tokens: GN + qkv + attention + out + residual   sr3_dwt.py:330-360 */
   DDIF_OP_DPM_ERR = 29,      /* adaptive DPM-Solver error estimate per sample                      dpm_solver.py:1003-1006 */
   DDIF_OP_WAVELET_COND = 28  /* raw lms, pan -> cond in one pass: Haar DWT, /division, channel order, bilinear up, concat
                                 dataset/pan_dataset.py:73-142, dataset/hisr.py:48-59, diffusion_engine.py:221-228 */
@@ -121,6 +122,14 @@ typedef struct {
 typedef struct { const void* in; void* out; int64_t batch, h, w, c; double scale; int64_t in_ld; } ddif_softmax_h_t;
 /* qkv: [B, ntok, 3*C] with per-head channel blocks [q(hd) k(hd) v(hd)]; out: [B, ntok, C] */
 typedef struct { const void* qkv; void* out; int64_t batch, ntok, c, heads; double scale; } ddif_attn_t;
+/* Fused SelfAttention block (sr3_dwt.py:330-360) for ntok = 64, c = 128, heads = 8 (what the UNet attends at): x [B, 64, c] bf16 is the block
+ * input AND the residual; stats_in = its per-sample (sum, sumsq) in fp64; wqkv = the packed qkv 1x1 weight [3c][c] bf16; wout = the out 1x1
+ * weight [c][c] bf16 with its K axis permuted for 64-byte fragment loads (position 32t + 4ks + 2h + e holds input channel 16ks + 8h + 2t + e,
+ * t < 4, ks < 8, h < 2, e < 2; csrc/attn_block.cu); out [B, 64, c] bf16; stats_out (optional) += (sum, sumsq) of out per sample. */
+typedef struct {
+  const void* x; const double* stats_in; const float* gamma; const float* beta; const void* wqkv; const void* wout; const float* bout;
+  void* out; double* stats_out; int64_t batch, ntok, c, heads; double scale, eps;
+} ddif_attn_block_t;
 typedef struct { const void* in; void* out; int64_t batch, h, w, c; } ddif_upsample2x_t;
 typedef struct {
   const void* in; int64_t in_ld, cin, in_h, in_w; const void* w; int64_t w_k, taps, stride;

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-from gpu_util import DEV, nhwc_bf16, rel_err, stream, to_nchw_f32  # noqa: E402
+from gpu_util import DEV, nhwc_bf16, pack_w, rel_err, stream, to_nchw_f32  # noqa: E402
 import dif_pan_b200 as dp  # noqa: E402
 from dif_pan_b200 import _lib, synth  # noqa: E402
 from oracle import sampler_oracle as so, wavelet_oracle as wo  # noqa: E402
@@ -310,3 +310,46 @@ def test_device_randn_is_standard_normal():
     assert abs(float(z.mean())) < 3e-3 and abs(float(z.std()) - 1) < 3e-3
     assert abs(float((z ** 4).mean()) - 3.0) < 0.05 and torch.isfinite(z).all()
     assert abs(float((z[:-1] * z[1:]).mean())) < 3e-3
+
+
+def test_fused_attention_block_matches_torch():
+    """ddif_attn_block_f32 path (GN + qkv + 64-token 8-head attention + out + residual + statistics in one kernel) against an fp32
+    torch restatement of SelfAttention.forward (sr3_dwt.py:330-360) on the same bf16 inputs / weights."""
+    import math
+    B, C, heads, hd = 5, 128, 8, 16
+    g = torch.Generator().manual_seed(17)
+    x = (torch.randn(B, C, 8, 8, generator=g) * 1.5 + 0.3)
+    xa = nhwc_bf16(x.to(DEV))                                   # [B, 8, 8, C] bf16
+    xf = to_nchw_f32(xa)                                          # the bf16-rounded input as fp32 NCHW
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).to(DEV), (torch.randn(C, generator=g) * 0.2).to(DEV)
+    wqkv = (torch.randn(3 * C, C, 1, 1, generator=g) / math.sqrt(C)).to(DEV)
+    wout = (torch.randn(C, C, 1, 1, generator=g) / math.sqrt(C)).to(DEV)
+    bout = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    stats_in = torch.stack([xf.double().sum(dim=(1, 2, 3)), (xf.double() ** 2).sum(dim=(1, 2, 3))], dim=1).contiguous()
+    wq_p = pack_w(wqkv)                                           # [1][384][128] bf16
+    pos = torch.arange(C, device=DEV)
+    src = 16 * ((pos % 32) // 4) + 8 * ((pos % 4) // 2) + 2 * (pos // 32) + pos % 2
+    wo_p = wout[:, :, 0, 0][:, src].to(torch.bfloat16).contiguous()
+    out = torch.zeros(B, 8, 8, C, dtype=torch.bfloat16, device=DEV)
+    stats_out = torch.zeros(B, 2, dtype=torch.float64, device=DEV)
+    _lib.launch("ddif_attn_block_t", stream(), x=xa.data_ptr(), stats_in=stats_in.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
+                wqkv=wq_p.data_ptr(), wout=wo_p.data_ptr(), bout=bout.data_ptr(), out=out.data_ptr(), stats_out=stats_out.data_ptr(), batch=B,
+                ntok=64, c=C, heads=heads, scale=1.0 / math.sqrt(C), eps=1e-5)
+    torch.cuda.synchronize()
+    # fp32 reference with the same roundings of the stored operands (bf16 weights)
+    n = F.group_norm(xf, 1, gamma, beta, eps=1e-5)
+    qkv = F.conv2d(n, wqkv.to(torch.bfloat16).float()).view(B, heads, 3 * hd, 64)
+    q, k, v = qkv.chunk(3, dim=2)
+    att = torch.softmax(torch.einsum("bhdq,bhdk->bhqk", q, k) / math.sqrt(C), dim=-1)
+    o = torch.einsum("bhqk,bhdk->bhdq", att, v).reshape(B, C, 8, 8)
+    ref = F.conv2d(o, wout.to(torch.bfloat16).float(), bout) + xf
+    got = to_nchw_f32(out)
+    e = rel_err(got, ref)
+    print("fused attention block rel err", e)
+    assert e < 6e-3
+    assert float((stats_out[:, 0] - ref.double().sum(dim=(1, 2, 3))).abs().max()) < 2e-2 * 64 * C ** 0.5
+    assert float((stats_out[:, 1] / (ref.double() ** 2).sum(dim=(1, 2, 3)) - 1).abs().max()) < 1e-2
+    with pytest.raises(RuntimeError):
+        _lib.launch("ddif_attn_block_t", stream(), x=xa.data_ptr(), stats_in=stats_in.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
+                    wqkv=wq_p.data_ptr(), wout=wo_p.data_ptr(), bout=bout.data_ptr(), out=out.data_ptr(), stats_out=None, batch=B, ntok=128,
+                    c=C, heads=heads, scale=1.0, eps=1e-5)

@@ -13,9 +13,15 @@
 // A tcgen05 version needs four TMEM->register->shared-memory->descriptor hand-offs per sample for the same arithmetic.
 //
 // K ordering trick: an MMA sums over its k slots, so A and B may enumerate the channels in ANY common order.  Thread t of a quad
-// takes the 32 contiguous channels [32t, 32t+32) for all 8 k-steps (slot (ks, half, e) <-> channel 32t + 4ks + 2half + e): every
-// operand row is then fetched with four 16-byte loads per thread instead of sixteen 4-byte ones.  The out projection's A operand
-// comes from registers in the natural order, so its weight is stored with that permutation applied on the host (unet.py).
+// takes the four 16-byte chunks c = 4j + t (j < 4) of every 256-byte operand row for all 8 k-steps (slot (ks, half, e) <-> channel
+// 32(ks>>1) + 8t + 4(ks&1) + 2half + e): every operand row is fetched with four 16-byte accesses per thread instead of sixteen 4-byte
+// ones, and with the chunk position XOR-ed by 4*(row & 1) the shared-memory reads of a quarter warp (two rows x four t) hit eight
+// distinct 16-byte bank groups.  The out projection's A operand comes from registers in the natural order, so its weight is stored
+// with that permutation applied on the host (unet.py).
+//
+// Weights go through shared memory: the 12 KB qkv slice of head h+1 and the whole 32 KB out weight are fetched with cp.async while
+// head h computes (ncu on the first version, which read weight fragments straight from global memory: every HMMA stalled on
+// long_scoreboard, 25 us per CTA; profiles/r01s5_ncu_attn_block_*.txt).
 #include "common.cuh"
 #include "ddif_internal.h"
 
@@ -41,17 +47,48 @@ __device__ __forceinline__ float2 unpack_bf2(uint32_t w) {
 // word index (0..15) inside a thread's 64-byte operand slice of slot (ks, half)
 __device__ __forceinline__ constexpr int ab_word(int ks, int half) { return (ks >> 1) * 4 + (ks & 1) * 2 + half; }
 
+static constexpr int kAbW1Rows = 48, kAbRowB = kAbC * 2;  // weight rows of one head's [q|k|v] slice; bytes per weight row
+static constexpr int kAbSmemK = 0, kAbSmemVt = kAbSmemK + kAbTok * kAbKsLd * 2, kAbSmemW1 = kAbSmemVt + kAbC * kAbVtLd * 2,
+                     kAbSmemW3 = kAbSmemW1 + 2 * kAbW1Rows * kAbRowB, kAbSmemRed = kAbSmemW3 + kAbC * kAbRowB, kAbSmemBytes = kAbSmemRed + 32;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// `rows` weight rows of 256 bytes -> shared memory, 16-byte chunk c of row r stored at chunk position c ^ (4 * (r & 1))
+__device__ __forceinline__ void ab_fill(uint32_t dst, const bf16* src, int rows, int tid) {
+  for (int q = tid; q < rows * 16; q += 128) {
+    const int r = q >> 4, c = q & 15;
+    cp_async16(dst + (uint32_t)(r * kAbRowB + ((c ^ ((r & 1) << 2)) << 4)), src + (size_t)r * kAbC + 8 * c);
+  }
+}
+// the 16 operand words of thread t for weight row r (chunks 4j + t, j < 4)
+__device__ __forceinline__ void ab_row(uint32_t base, int r, int t, uint32_t (&w)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t a = base + (uint32_t)(r * kAbRowB + (((4 * j + t) ^ ((r & 1) << 2)) << 4));
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * j]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3]) : "r"(a));
+  }
+}
+
 __global__ void __launch_bounds__(128) attn_block64_kernel(ddif_attn_block_t p) {
-  __shared__ __align__(16) bf16 s_k[kAbTok * kAbKsLd];
-  __shared__ __align__(16) bf16 s_vt[kAbC * kAbVtLd];
-  __shared__ float s_red[8];
-  pdl_wait();
+  extern __shared__ __align__(16) uint8_t ab_smem[];
+  bf16* s_k = reinterpret_cast<bf16*>(ab_smem + kAbSmemK);
+  bf16* s_vt = reinterpret_cast<bf16*>(ab_smem + kAbSmemVt);
+  float* s_red = reinterpret_cast<float*>(ab_smem + kAbSmemRed);
+  const uint32_t s_w1 = smem_u32(ab_smem + kAbSmemW1), s_w3 = smem_u32(ab_smem + kAbSmemW3);
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int r0 = warp * 16 + g, r1 = r0 + 8;
   const bf16* x = reinterpret_cast<const bf16*>(p.x) + (size_t)b * kAbTok * kAbC;
   const bf16* wqkv = reinterpret_cast<const bf16*>(p.wqkv);
   const bf16* wout = reinterpret_cast<const bf16*>(p.wout);
+  // static weights: requested before the dependency wait (they overlap the previous kernel's tail)
+  ab_fill(s_w3, wout, kAbC, threadIdx.x);
+  ab_fill(s_w1, wqkv, kAbW1Rows, threadIdx.x);
+  cp_async_commit();
+  pdl_wait();
 
   // ---- GroupNorm(1 group) statistics of the sample (fp64 sums from the producer's epilogue) ----
   const double cnt = (double)kAbTok * kAbC;
@@ -60,26 +97,30 @@ __global__ void __launch_bounds__(128) attn_block64_kernel(ddif_attn_block_t p) 
   if (var_d < 0) var_d = 0;
   const float mean = (float)mean_d, rstd = rsqrtf((float)var_d + (float)p.eps);
 
-  // ---- A fragments of the normalised rows r0, r1: channels [32t, 32t+32) ----
+  // ---- A fragments of the normalised rows r0, r1: chunks 4j + t, i.e. channels 32j + 8t .. + 7 ----
   uint32_t af[8][4];
   {
     uint32_t xr[2][16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint4 v0 = *reinterpret_cast<const uint4*>(x + (size_t)r0 * kAbC + 32 * t + 8 * j);
-      const uint4 v1 = *reinterpret_cast<const uint4*>(x + (size_t)r1 * kAbC + 32 * t + 8 * j);
+      const uint4 v0 = *reinterpret_cast<const uint4*>(x + (size_t)r0 * kAbC + 32 * j + 8 * t);
+      const uint4 v1 = *reinterpret_cast<const uint4*>(x + (size_t)r1 * kAbC + 32 * j + 8 * t);
       xr[0][4 * j] = v0.x; xr[0][4 * j + 1] = v0.y; xr[0][4 * j + 2] = v0.z; xr[0][4 * j + 3] = v0.w;
       xr[1][4 * j] = v1.x; xr[1][4 * j + 1] = v1.y; xr[1][4 * j + 2] = v1.z; xr[1][4 * j + 3] = v1.w;
     }
 #pragma unroll
-    for (int w = 0; w < 16; ++w) {  // word w = channels 32t + 2w, 32t + 2w + 1
-      const float2 gm = __ldg(reinterpret_cast<const float2*>(p.gamma + 32 * t + 2 * w));
-      const float2 bt = __ldg(reinterpret_cast<const float2*>(p.beta + 32 * t + 2 * w));
-      const float a0 = rstd * gm.x, a1 = rstd * gm.y;
-      const float d0 = bt.x - mean * a0, d1 = bt.y - mean * a1;
-      const float2 u0 = unpack_bf2(xr[0][w]), u1 = unpack_bf2(xr[1][w]);
-      xr[0][w] = pack_bf2(fmaf(u0.x, a0, d0), fmaf(u0.y, a1, d1));
-      xr[1][w] = pack_bf2(fmaf(u1.x, a0, d0), fmaf(u1.y, a1, d1));
+    for (int j = 0; j < 4; ++j) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + 32 * j + 8 * t)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + 32 * j + 8 * t + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + 32 * j + 8 * t)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + 32 * j + 8 * t + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float a0 = rstd * gm[2 * w], a1 = rstd * gm[2 * w + 1];
+        const float d0 = bt[2 * w] - mean * a0, d1 = bt[2 * w + 1] - mean * a1;
+        const float2 u0 = unpack_bf2(xr[0][4 * j + w]), u1 = unpack_bf2(xr[1][4 * j + w]);
+        xr[0][4 * j + w] = pack_bf2(fmaf(u0.x, a0, d0), fmaf(u0.y, a1, d1));
+        xr[1][4 * j + w] = pack_bf2(fmaf(u1.x, a0, d0), fmaf(u1.y, a1, d1));
+      }
     }
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
@@ -94,26 +135,28 @@ __global__ void __launch_bounds__(128) attn_block64_kernel(ddif_attn_block_t p) 
   uint32_t qf[kAbHeads][4];
 #pragma unroll
   for (int h = 0; h < kAbHeads; ++h) {
-    // all 24 weight loads of the head are issued before the first MMA: one exposed L2 round trip per head instead of one per n-tile
-    uint32_t bw[6][16];
-#pragma unroll
-    for (int nt = 0; nt < 6; ++nt) {
-      const bf16* wr = wqkv + (size_t)(48 * h + 8 * nt + g) * kAbC + 32 * t;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(wr + 8 * j));
-        bw[nt][4 * j] = v.x; bw[nt][4 * j + 1] = v.y; bw[nt][4 * j + 2] = v.z; bw[nt][4 * j + 3] = v.w;
-      }
+    cp_async_wait_all();   // this head's weight slice (and, the first time, the out weight) has landed for this thread's copies ...
+    __syncthreads();       // ... and for everybody's; all warps are also done reading the buffer the next fill overwrites
+    if (h + 1 < kAbHeads) {
+      ab_fill(s_w1 + (uint32_t)(((h + 1) & 1) * kAbW1Rows * kAbRowB), wqkv + (size_t)(h + 1) * kAbW1Rows * kAbC, kAbW1Rows, threadIdx.x);
+      cp_async_commit();
     }
+    const uint32_t wb = s_w1 + (uint32_t)((h & 1) * kAbW1Rows * kAbRowB);
     float acc[6][4];
 #pragma unroll
     for (int nt = 0; nt < 6; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks)  // k-step outer: six independent accumulator chains in flight (an MMA's result latency is ~30+ cycles)
+    for (int half6 = 0; half6 < 2; ++half6) {  // three n-tiles at a time: 48 operand registers, three independent accumulator chains
+      uint32_t bw[3][16];
 #pragma unroll
-      for (int nt = 0; nt < 6; ++nt) mma16816(acc[nt], af[ks], bw[nt][ab_word(ks, 0)], bw[nt][ab_word(ks, 1)]);
+      for (int u = 0; u < 3; ++u) ab_row(wb, 8 * (3 * half6 + u) + g, t, bw[u]);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+        for (int u = 0; u < 3; ++u) mma16816(acc[3 * half6 + u], af[ks], bw[u][ab_word(ks, 0)], bw[u][ab_word(ks, 1)]);
+    }
     qf[h][0] = pack_bf2(acc[0][0], acc[0][1]);
     qf[h][1] = pack_bf2(acc[0][2], acc[0][3]);
     qf[h][2] = pack_bf2(acc[1][0], acc[1][1]);
@@ -197,20 +240,13 @@ __global__ void __launch_bounds__(128) attn_block64_kernel(ddif_attn_block_t p) 
     of[h][3] = pack_bf2(o[1][2] * i1, o[1][3] * i1);
   }
 
-  // ---- y = O Wout^T + bias + x, n-tile by n-tile (K-permuted weight rows: four 16-byte loads per thread and n-tile) ----
+  // ---- y = O Wout^T + bias + x, four n-tiles at a time (K-permuted weight rows from shared memory) ----
   bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)b * kAbTok * kAbC;
   float s1 = 0.f, s2 = 0.f;
-  for (int ng = 0; ng < 4; ++ng) {  // 4 n-tiles per group, their 16 weight loads issued together
+  for (int ng = 0; ng < 4; ++ng) {
     uint32_t bw[4][16];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bf16* wr = wout + (size_t)(8 * (4 * ng + u) + g) * kAbC + 32 * t;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(wr + 8 * j));
-        bw[u][4 * j] = v.x; bw[u][4 * j + 1] = v.y; bw[u][4 * j + 2] = v.z; bw[u][4 * j + 3] = v.w;
-      }
-    }
+    for (int u = 0; u < 4; ++u) ab_row(s_w3, 8 * (4 * ng + u) + g, t, bw[u]);
     float yy[4][4];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -256,7 +292,12 @@ bool attn_block_applicable(const ddif_attn_block_t& p) { return p.ntok == kAbTok
 int launch_attn_block(const ddif_attn_block_t& p, cudaStream_t s) {
   if (!attn_block_applicable(p)) return DDIF_ERR_SHAPE;
   if (!p.x || !p.stats_in || !p.gamma || !p.beta || !p.wqkv || !p.wout || !p.out || p.batch < 1) return DDIF_ERR_ARG;
-  DDIF_CUDA_CHECK(launch_pdl(attn_block64_kernel, dim3((unsigned)p.batch), dim3(128), (size_t)0, s, p));
+  static bool attr_done = false;
+  if (!attr_done) {
+    DDIF_CUDA_CHECK(cudaFuncSetAttribute(attn_block64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes));
+    attr_done = true;
+  }
+  DDIF_CUDA_CHECK(launch_pdl(attn_block64_kernel, dim3((unsigned)p.batch), dim3(128), (size_t)kAbSmemBytes, s, p));
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }

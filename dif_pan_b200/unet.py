@@ -269,8 +269,8 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], net: "UNetSR3") -> Dict[str, to
         C = sd[p + ".out.weight"].shape[1]
         if C == 128:  # fused attention block (csrc/attn_block.cu): out weight with its K axis permuted for 64-byte fragment loads
             pos = torch.arange(C, device=sd[p + ".out.weight"].device)
-            t_, ks, h_, e_ = pos // 32, (pos % 32) // 4, (pos % 4) // 2, pos % 2
-            src = 16 * ks + 8 * h_ + 2 * t_ + e_
+            j_, t_, w_, e_ = pos // 32, (pos % 32) // 8, (pos % 8) // 2, pos % 2   # chunk 4j + t of the row, word w of the chunk
+            src = 16 * (2 * j_ + w_ // 2) + 8 * (w_ % 2) + 2 * t_ + e_
             P[p + ".out.wp"] = sd[p + ".out.weight"].to(torch.float32)[:, :, 0, 0][:, src].to(torch.bfloat16).contiguous()
 
     cin = net.in_channel + (net.out_channel if net.self_condition else 0)

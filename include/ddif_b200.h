@@ -124,8 +124,8 @@ typedef struct { const void* in; void* out; int64_t batch, h, w, c; double scale
 typedef struct { const void* qkv; void* out; int64_t batch, ntok, c, heads; double scale; } ddif_attn_t;
 /* Fused SelfAttention block (sr3_dwt.py:330-360) for ntok = 64, c = 128, heads = 8 (what the UNet attends at): x [B, 64, c] bf16 is the block
  * input AND the residual; stats_in = its per-sample (sum, sumsq) in fp64; wqkv = the packed qkv 1x1 weight [3c][c] bf16; wout = the out 1x1
- * weight [c][c] bf16 with its K axis permuted for 64-byte fragment loads (position 32t + 4ks + 2h + e holds input channel 16ks + 8h + 2t + e,
- * t < 4, ks < 8, h < 2, e < 2; csrc/attn_block.cu); out [B, 64, c] bf16; stats_out (optional) += (sum, sumsq) of out per sample. */
+ * weight [c][c] bf16 with its K axis permuted for 16-byte fragment chunks (position 32(ks>>1) + 8t + 4(ks&1) + 2h + e holds input channel
+ * 16ks + 8h + 2t + e, t < 4, ks < 8, h < 2, e < 2; csrc/attn_block.cu); out [B, 64, c] bf16; stats_out (optional) += (sum, sumsq) of out per sample. */
 typedef struct {
   const void* x; const double* stats_in; const float* gamma; const float* beta; const void* wqkv; const void* wout; const float* bout;
   void* out; double* stats_out; int64_t batch, ntok, c, heads; double scale, eps;

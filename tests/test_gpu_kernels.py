@@ -328,7 +328,7 @@ def test_fused_attention_block_matches_torch():
     stats_in = torch.stack([xf.double().sum(dim=(1, 2, 3)), (xf.double() ** 2).sum(dim=(1, 2, 3))], dim=1).contiguous()
     wq_p = pack_w(wqkv)                                           # [1][384][128] bf16
     pos = torch.arange(C, device=DEV)
-    src = 16 * ((pos % 32) // 4) + 8 * ((pos % 4) // 2) + 2 * (pos // 32) + pos % 2
+    src = 16 * (2 * (pos // 32) + ((pos % 8) // 2) // 2) + 8 * (((pos % 8) // 2) % 2) + 2 * ((pos % 32) // 8) + pos % 2
     wo_p = wout[:, :, 0, 0][:, src].to(torch.bfloat16).contiguous()
     out = torch.zeros(B, 8, 8, C, dtype=torch.bfloat16, device=DEV)
     stats_out = torch.zeros(B, 2, dtype=torch.float64, device=DEV)

@@ -13,3 +13,8 @@ tail -2 gpurun_out/ncu_halo32.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3x3_halo -s 4 -c 1 -f -o gpurun_out/prof_halo64 \
   python tools/layer_bench.py 256 32 32 64 64 1 1 1 0 9 6 > gpurun_out/ncu_halo64.log 2>&1
 tail -2 gpurun_out/ncu_halo64.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_block64 -s 3 -c 1 -f -o gpurun_out/prof_attn_block \
+  python tools/run_attn_block.py 256 3 > gpurun_out/ncu_attn_block.log 2>&1
+tail -2 gpurun_out/ncu_attn_block.log
+timeout 600 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err; tail -2 gpurun_out/configs.err
+python tools/profile_step.py --batch 256 > gpurun_out/step_profile.txt 2>&1; head -3 gpurun_out/step_profile.txt

@@ -21,7 +21,7 @@
 //
 // Weights go through shared memory: the 12 KB qkv slice of head h+1 and the whole 32 KB out weight are fetched with cp.async while
 // head h computes (ncu on the first version, which read weight fragments straight from global memory: every HMMA stalled on
-// long_scoreboard, 25 us per CTA; profiles/r01s5_ncu_attn_block_*.txt).
+// long_scoreboard, 25 us per CTA; profiles/r01s5_ncu_prof_attn_block_v1_global_weights_stalls.txt).
 #include "common.cuh"
 #include "ddif_internal.h"
 

@@ -619,7 +619,10 @@ class Schedule:
                 # prenorm_x -> [DW3x3 -> Conv1x1 | attn_res] as ONE tensor-core 3x3 conv over the virtual concat (x, skip) with
                 # the GroupNorm fused into its loader: channels [0, dim) = q, [dim, dim + o) = r = attn_res(x_hat)
                 qr = self._act(pb, q + ".qr", B, x.H, x.W, dim + o)
-                if self.use_dwq:  # depthwise 3x3 inside the kernel, one tensor-core tap (q from dw(x_hat), r from x_hat)
+                # depthwise 3x3 inside the kernel + ONE tensor-core tap (q from dw(x_hat), r from x_hat) when the composed dense 3x3 would
+                # waste 9x the 1x1 FLOPs on K = 9*dim >= 864; at dim = 64 the composed conv is the cheaper one (measured per layer at
+                # B = 256: dim 64 @64^2 104 vs 143 us; dim 96 @64^2 238 vs 219; dim 128 @32^2 147 vs 77; dim 128 @16^2 49 vs 31)
+                if self.use_dwq and dim >= 96:
                     self._gemm(pb, q + ".qconv", [x, skip], [A[q + ".q1r.w"], A[q + ".q1r.w"] + 2 * x.C], dim + o, qr, taps=[9, 9], w_s=[1, 1],
                                bias=A[q + ".qcr.b"], gn=(A[q + ".gamma"], A[q + ".beta"], 0), w_k=[dim, dim], dw=(A[q + ".q0"], dim),
                                ref_flops=2.0 * B * x.H * x.W * dim * (9 + dim + o))

@@ -111,9 +111,10 @@ def test_executed_flops_match_reference_count():
     _, _, s = _schedule("wv3", 1, 64, 64)
     step = sum(op.flops for op in s.fwd.ops)
     cond = sum(op.flops for op in s.cnd.ops)
-    # executed == reference-equivalent work within a few percent: the FWM q path runs its depthwise 3x3 inside the conv kernel
-    # (CUDA cores) and ONE tensor-core tap; only the dim-192 block at the 16-pixel level still uses the composed dense 3x3
-    assert 7.2e9 < step < 7.9e9
+    # executed vs reference-equivalent work: the FWM q path runs its depthwise 3x3 inside the conv kernel (CUDA cores) and ONE
+    # tensor-core tap where dim >= 96; the dim-64 blocks at 64x64 (and the dim-192 block at 16x16) use the composed dense 3x3, which
+    # executes 9x the 1x1's FLOPs (+1.0 GFLOP per patch-forward) but is the faster kernel there (unet.py)
+    assert 8.2e9 < step < 8.9e9
     ref = sum(op.ref_flops for op in s.fwd.ops)
     assert 7.0e9 < ref < 7.6e9
 

@@ -374,6 +374,9 @@ class Schedule:
         self.use_qconv = os.environ.get("DDIF_NO_QCONV") is None  # A/B switch for profiling only
         self.use_dwq = os.environ.get("DDIF_NO_DWQ") is None      # A/B switch: in-kernel depthwise q path vs composed dense 3x3
         self.use_attn_block = os.environ.get("DDIF_NO_ATTN_BLOCK") is None  # A/B switch: fused attention block vs 4 launches
+        # nearest x2 inside the conv's loader (csrc/conv3x3_tc.cu, the LDG-fed kernel) vs upsample kernel + halo conv: the two launches are
+        # faster at every level (B = 256: 45 -> 41, 59 -> 45, 176 -> 127 us), so the fused loader is opt-in (DDIF_UPFUSE=1)
+        self.use_upfuse = os.environ.get("DDIF_UPFUSE") is not None
 
     @staticmethod
     def _levels(net) -> int:
@@ -599,7 +602,7 @@ class Schedule:
             p = f"ups.{i}"
             if kind == "up":
                 y = self._act(pb, p, B, x.H * 2, x.W * 2, x.C, stats=True)
-                if x.W * 2 >= 16 and x.C <= 256:  # nearest x2 folded into the conv's loader
+                if x.W * 2 >= 16 and x.C <= 256 and self.use_upfuse:  # nearest x2 folded into the conv's loader
                     self._gemm(pb, p + ".up+conv", [x], [A[p + ".w"]], x.C, y, taps=[9], bias=A[p + ".b"], a_up=1)
                 else:
                     up = self._act(pb, p + ".up", B, x.H * 2, x.W * 2, x.C)

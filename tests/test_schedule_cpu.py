@@ -81,7 +81,7 @@ def test_schedule_structure(dataset, B, H, W):
     assert kinds.count("ddif_gn_apply_t") == (0 if fused_attn else 8) + 5
     merged = [op for op in s.fwd.ops if op.label.endswith(".qconv") and op.fields["n_valid"] > op.fields["w_k"][0]]
     assert len(merged) == 11
-    assert kinds.count("ddif_upsample2x_t") == 0  # nearest x2 folded into the following conv
+    assert kinds.count("ddif_upsample2x_t") == 3  # nearest x2 as its own kernel + halo conv (faster than the fused LDG loader)
     fused = [op for op in s.fwd.ops if op.struct == "ddif_gemm_t" and op.fields.get("gn_stats") is not None]
     # 30 resblocks x 2 + final conv, + the FWM q path (prenorm -> DW3x3 -> 1x1 composed into one 3x3 conv with the
     # GroupNorm in its loader) of every decoder block with H >= 16, W >= 8, dim <= 192

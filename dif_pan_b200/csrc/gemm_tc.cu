@@ -244,7 +244,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
     const int sub = (warp - 2) >> 2;
     if constexpr ((F & kLean) != 0) {
       constexpr bool kMod = (F & kLeanMod) != 0, kRes = (F & kLeanRes) != 0, kStats = (F & kLeanStats) != 0;
-      const int cg = sub;                      // this thread's 16-channel chunk
+      // N <= 32 needs only 1-2 of the 4 column groups: the others form further TILE groups (group g drains accumulator g for the
+      // CTA's tiles g, g + groups, ...), so two (four) tiles' wait -> tcgen05.ld -> math -> store chains overlap instead of running
+      // back to back (a single group left the 64x64-level 1x1 convs latency-bound at ~3400 cycles per 128 x 32 tile).
+      const int ncg = 4 / p.groups;            // column groups per tile group
+      const int cg = sub % ncg;                // this thread's 16-channel chunk
+      const int grp = sub / ncg;               // this thread's tile group
       const int row = q * 32 + lane;
       const int px_per_img = p.tw * p.th;
       const int tn_i = row / px_per_img;
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
       float bv[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) bv[j] = (active && p.bias) ? __ldg(p.bias + ng + j) : 0.f;
-      const int step = (int)gridDim.x;
+      const int step = (int)gridDim.x * p.groups;
       LeanOperands<F> nxt;
       bool nxt_ok = false;
       size_t nxt_pix = 0;
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
           ldg256(m + p.n_valid, o.sh);
         }
       };
-      int m_tile = (int)blockIdx.x;
+      int m_tile = (int)blockIdx.x + grp * (int)gridDim.x;
       if (m_tile < p.num_m_tiles) {
         nxt_ok = locate(m_tile, nxt_pix, nxt_b);
         fetch(nxt, nxt_pix, nxt_ok);
@@ -300,8 +305,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
             fv[j] = t.x; fv[j + 1] = t.y; fv[j + 2] = t.z; fv[j + 3] = t.w;
           }
         }
-        const uint32_t acc = tcount & 1u;
-        mbar_wait(&tmem_full_bar[acc], (tcount >> 1) & 1u);
+        // one group: two accumulators alternate per tile; several groups: group g owns accumulator g
+        const uint32_t acc = p.groups == 1 ? (tcount & 1u) : (uint32_t)grp;
+        mbar_wait(&tmem_full_bar[acc], (p.groups == 1 ? (tcount >> 1) : tcount) & 1u);
         tc_fence_after();
         uint32_t r[16];
         if (active) {
@@ -519,8 +525,9 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   const bool lean = bn <= 64 && g.n_pad == bn && g.n_valid % 16 == 0 && g.out && !g.out_nchw && g.out_ld % 16 == 0 &&
                     (!g.residual || g.res_ld % 16 == 0) && (!g.film || g.film_ld % 4 == 0) && !(g.mod && g.residual);
   p.lean = lean ? (kLean | (g.mod ? kLeanMod : 0) | (g.residual ? kLeanRes : 0) | (g.stats ? kLeanStats : 0)) : 0;
-  p.groups = lean ? 1 : (4 * bn <= 512 ? 4 : 2);
-  p.naccs = lean ? 2 : p.groups;
+  // lean: N = 64 (48) -> all 16 warps on one tile, two alternating accumulators; N = 32 -> 2 tile groups; N = 16 -> 4 tile groups
+  p.groups = lean ? (bn <= 16 ? 4 : (bn <= 32 ? 2 : 1)) : (4 * bn <= 512 ? 4 : 2);
+  p.naccs = lean ? (p.groups == 1 ? 2 : p.groups) : p.groups;
   uint32_t cols = 32;
   while ((int)cols < p.naccs * bn) cols <<= 1;
   p.tmem_cols = cols;

@@ -1042,7 +1042,9 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
       const bool can_ost = !no_ostore && g.out && !g.out_nchw && bn % 32 == 0 && g.n_valid == g.n_pad && g.out_ld % 8 == 0 && g.out_w % 8 == 0;
       if (pass == 0 && !can_ost) continue;
       const int o_bytes = pass == 0 ? 128 * bn * 2 : 0;
+      static const int kslab_cap = getenv("DDIF_HALO_KSLAB_MAX") ? atoi(getenv("DDIF_HALO_KSLAB_MAX")) : 64;  // tuning switch (tools/)
       for (int kslab = gcd; kslab >= 16; kslab >>= 1) {
+        if (kslab > kslab_cap && kslab > 16) continue;
         const int span = kslab * 2;
         const int stage_bytes = (kHPx * span + 1023) & ~1023;
         const int b_total = h.ntap_w * cin * bn * 2;  // independent of the slab size

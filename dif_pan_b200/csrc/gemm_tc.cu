@@ -547,7 +547,8 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
     stages = budget / (a_stage + b_slot);
     p.b_slots = stages;
   }
-  if (stages > 8) stages = 8;
+  static const int max_stages = getenv("DDIF_GEMM_MAX_STAGES") ? atoi(getenv("DDIF_GEMM_MAX_STAGES")) : 8;  // tuning switch (tools/)
+  if (stages > max_stages) stages = max_stages;
   if (stages < 2) return DDIF_ERR_SHAPE;
   if (!p.resident_b) p.b_slots = stages;
   p.stages = stages;

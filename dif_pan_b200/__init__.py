@@ -13,8 +13,8 @@ from .diffusion import GaussianDiffusion, make_beta_schedule, fuse_output, devic
 from .dpm_solver import NoiseScheduleVP, model_wrapper, DPM_Solver, interpolate_fn  # noqa: F401
 from .wavelet import haar_dwt2, haar_idwt2, wavelet_channels, assemble_cond, make_cond  # noqa: F401
 from .scene import tile_scene, stitch_tiles, sample_cond, fuse_scene  # noqa: F401
-from . import metrics  # noqa: F401
+from . import metrics, optim  # noqa: F401
 
 __all__ = ["UNetSR3", "GaussianDiffusion", "make_beta_schedule", "fuse_output", "device_randn", "NoiseScheduleVP",
            "model_wrapper", "DPM_Solver", "interpolate_fn", "haar_dwt2", "haar_idwt2", "wavelet_channels", "assemble_cond", "make_cond",
-           "tile_scene", "stitch_tiles", "sample_cond", "fuse_scene", "metrics"]
+           "tile_scene", "stitch_tiles", "sample_cond", "fuse_scene", "metrics", "optim"]

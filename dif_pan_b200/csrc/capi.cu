@@ -40,6 +40,7 @@ union OpParams {
   ddif_loss_t loss;
   ddif_dpm_err_t dpm_err;
   ddif_attn_block_t attn_block;
+  ddif_multi_tensor_t multi_tensor;
   ddif_axpby_t axpby;
   ddif_metrics_t metrics;
   ddif_tile_t tile;
@@ -74,6 +75,7 @@ static size_t params_size(int kind) {
     case DDIF_OP_LOSS: return sizeof(ddif_loss_t);
     case DDIF_OP_DPM_ERR: return sizeof(ddif_dpm_err_t);
     case DDIF_OP_ATTN_BLOCK: return sizeof(ddif_attn_block_t);
+    case DDIF_OP_MULTI_TENSOR: return sizeof(ddif_multi_tensor_t);
     case DDIF_OP_AXPBY: return sizeof(ddif_axpby_t);
     case DDIF_OP_METRICS: return sizeof(ddif_metrics_t);
     case DDIF_OP_TILE: return sizeof(ddif_tile_t);
@@ -119,6 +121,7 @@ static int dispatch(const Op& op, cudaStream_t s) {
     case DDIF_OP_LOSS: return launch_loss(op.p.loss, s);
     case DDIF_OP_DPM_ERR: return launch_dpm_err(op.p.dpm_err, s);
     case DDIF_OP_ATTN_BLOCK: return launch_attn_block(op.p.attn_block, s);
+    case DDIF_OP_MULTI_TENSOR: return launch_multi_tensor(op.p.multi_tensor, s);
     case DDIF_OP_AXPBY: return launch_axpby(op.p.axpby, s);
     case DDIF_OP_METRICS: return launch_metrics(op.p.metrics, s);
     case DDIF_OP_TILE: return launch_tile(op.p.tile, s);
@@ -282,6 +285,7 @@ int ddif_dpmpp_step_f32(const ddif_dpmpp_step_t* p, ddif_stream_t s) { return dd
 int ddif_dpm_single_f32(const ddif_dpm_single_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_DPM_SINGLE, p, s); }
 int ddif_loss_f32(const ddif_loss_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_LOSS, p, s); }
 int ddif_dpm_err_f32(const ddif_dpm_err_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_DPM_ERR, p, s); }
+int ddif_multi_tensor_f32(const ddif_multi_tensor_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_MULTI_TENSOR, p, s); }
 int ddif_metrics_f32(const ddif_metrics_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_METRICS, p, s); }
 int ddif_tile_f32(const ddif_tile_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_TILE, p, s); }
 int ddif_wavelet_cond_f32(const ddif_wavelet_cond_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_WAVELET_COND, p, s); }

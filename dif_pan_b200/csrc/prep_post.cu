@@ -303,4 +303,57 @@ int launch_metrics(const ddif_metrics_t& p, cudaStream_t s) {
   return DDIF_OK;
 }
 
+// ---- multi-tensor apply (training-loop surround: EMA, grad clip, AdamW) ---------------------------------------------------------
+// One block per chunk of one tensor; element-wise, fp32, explicit operation order (no FMA contraction) so that results match the
+// eager torch expressions the reference executes tensor by tensor.
+__global__ void __launch_bounds__(256) multi_tensor_kernel(ddif_multi_tensor_t p) {
+  __shared__ double sh[8];
+  const int64_t ti = p.chunks[2 * blockIdx.x], start = p.chunks[2 * blockIdx.x + 1];
+  int64_t n = p.sizes[ti] - start;
+  if (n > p.chunk) n = p.chunk;
+  float* p0 = reinterpret_cast<float*>(p.ptrs[4 * ti]) + start;
+  const float* p1 = reinterpret_cast<const float*>(p.ptrs[4 * ti + 1]) + start;
+  float* p2 = reinterpret_cast<float*>(p.ptrs[4 * ti + 2]) + start;
+  float* p3 = reinterpret_cast<float*>(p.ptrs[4 * ti + 3]) + start;
+  const float s0 = (float)p.s0, s1 = (float)p.s1;
+  if (p.op == 0) {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) p0[i] = ADD(MUL(p0[i], s0), MUL(p1[i], s1));
+  } else if (p.op == 1) {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) p0[i] = p1[i];
+  } else if (p.op == 2) {
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += (double)p0[i] * (double)p0[i];
+    const double t = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(p.out, t);
+  } else if (p.op == 3) {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) p0[i] = MUL(p0[i], s0);
+  } else if (p.op == 4) {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) p0[i] = fminf(fmaxf(p0[i], -s0), s0);
+  } else {
+    // torch.optim.AdamW, single-tensor expression order (torch/optim/adamw.py): decoupled decay, lerp first moment, mul/addcmul
+    // second moment, denom = sqrt(v) / sqrt(bc2) + eps, param -= (lr / bc1) * m / denom
+    const float lr = s0, b1 = s1, b2 = (float)p.s2, eps = (float)p.s3, wd = (float)p.s4;
+    const float decay = (float)(1.0 - p.s0 * p.s4), w1 = (float)(1.0 - p.s1), w2 = (float)(1.0 - p.s2);
+    const float step_size = (float)(p.s0 / p.s5), bc2s = (float)sqrt(p.s6);
+    (void)lr; (void)b1; (void)wd;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const float g = p1[i];
+      const float w = MUL(p0[i], decay);
+      const float m = ADD(p2[i], MUL(w1, SUB(g, p2[i])));
+      const float v = ADD(MUL(p3[i], b2), MUL(MUL(g, g), w2));
+      const float denom = ADD(DIV(sqrtf(v), bc2s), eps);
+      p2[i] = m;
+      p3[i] = v;
+      p0[i] = SUB(w, MUL(step_size, DIV(m, denom)));
+    }
+  }
+}
+int launch_multi_tensor(const ddif_multi_tensor_t& p, cudaStream_t s) {
+  if (p.op < 0 || p.op > 5 || p.chunk < 1 || !p.ptrs || !p.sizes || !p.chunks || (p.op == 2 && !p.out)) return DDIF_ERR_ARG;
+  if (p.nchunks < 1) return DDIF_OK;
+  multi_tensor_kernel<<<(unsigned)p.nchunks, 256, 0, s>>>(p);
+  DDIF_LAUNCH_CHECK();
+  return DDIF_OK;
+}
+
 }  // namespace ddif

@@ -59,6 +59,7 @@ enum ddif_op_kind {
   DDIF_OP_METRICS = 26,      /* per-image partial sums of SAM / ERGAS / PSNR / CC                  utils/_metric_legacy.py:299-346 */
   DDIF_OP_TILE = 27,         /* scene -> patch batch (gather) and patch batch -> scene (overlap-averaged stitch) */
   DDIF_OP_ATTN_BLOCK = 30,   /* whole SelfAttention block at 64 tokens: GN + qkv + attention + out + residual   sr3_dwt.py:330-360 */
+  DDIF_OP_MULTI_TENSOR = 31, /* one launch over a LIST of tensors: EMA, copy, sum of squares, scale, clamp, AdamW   utils/optim_utils.py:24-58, utils/misc.py:25-36 */
   DDIF_OP_DPM_ERR = 29,      /* adaptive DPM-Solver error estimate per sample                      dpm_solver.py:1003-1006 */
   DDIF_OP_WAVELET_COND = 28  /* raw lms, pan -> cond in one pass: Haar DWT, /division, channel order, bilinear up, concat
                                 dataset/pan_dataset.py:73-142, dataset/hisr.py:48-59, diffusion_engine.py:221-228 */
@@ -195,6 +196,17 @@ typedef struct {
   int64_t n, batch, model_type, predict, mode;
   double alpha_e, sigma_e, c0, c1, c2, t_next_in;
 } ddif_dpm_single_t;
+/* Multi-tensor apply (the training loop's EMA / grad-clip / optimizer update touch ~350 small parameter tensors; the
+ * reference issues 3-10 ATen kernels per tensor).  ptrs: device int64[ntensors][4] (addresses of up to four fp32 tensors per entry), sizes:
+ * device int64[ntensors], chunks: device int64[nchunks][2] = (tensor index, first element); every chunk covers <= `chunk` elements.
+ *   op 0 EMA    p0 = s0*p0 + s1*p1                       EmaUpdater.update, utils/optim_utils.py:44-52 (s0 = decay, s1 = 1 - decay)
+ *   op 1 COPY   p0 = p1                                   :53-58
+ *   op 2 SUMSQ  out[0] += sum p0^2                        clip_grad_norm_, utils/misc.py:33-34
+ *   op 3 SCALE  p0 *= s0
+ *   op 4 CLAMP  p0 = min(max(p0, -s0), s0)                clip_grad_value_, utils/misc.py:35-36
+ *   op 5 ADAMW  torch.optim.AdamW step (p0 param, p1 grad, p2 exp_avg, p3 exp_avg_sq; s0 lr, s1 beta1, s2 beta2, s3 eps, s4 weight_decay,
+ *               s5 = 1 - beta1^step, s6 = 1 - beta2^step), diffusion_engine.py:202-241 */
+typedef struct { const int64_t* ptrs; const int64_t* sizes; const int64_t* chunks; double* out; int64_t nchunks, chunk, op; double s0, s1, s2, s3, s4, s5, s6; } ddif_multi_tensor_t;
 /* Adaptive step-size control (dpm_solver.py:1003-1006): out[b] = sum_i ((x_higher - x_lower) / max(atol, rtol*max(|x_lower|, |x_prev|)))^2 for
  * sample b (every entry written); the host takes E = max_b sqrt(out[b] / chw). */
 typedef struct { const float* x_higher; const float* x_lower; const float* x_prev; double* out; int64_t batch, chw; double atol, rtol; } ddif_dpm_err_t;
@@ -263,6 +275,7 @@ int ddif_q_sample_f32(const ddif_q_sample_t* p, ddif_stream_t s);
 int ddif_conv_igemm_bf16(const ddif_gemm_t* p, ddif_stream_t s);
 int ddif_dpm_single_f32(const ddif_dpm_single_t* p, ddif_stream_t s);
 int ddif_dpm_err_f32(const ddif_dpm_err_t* p, ddif_stream_t s);
+int ddif_multi_tensor_f32(const ddif_multi_tensor_t* p, ddif_stream_t s);
 int ddif_loss_f32(const ddif_loss_t* p, ddif_stream_t s);
 int ddif_metrics_f32(const ddif_metrics_t* p, ddif_stream_t s);
 int ddif_tile_f32(const ddif_tile_t* p, ddif_stream_t s);

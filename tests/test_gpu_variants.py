@@ -271,3 +271,72 @@ def test_dpm_adaptive_unet_fast_path():
         outs.append(sol.sample(x_T.clone(), order=2, method="adaptive", atol=0.05, rtol=0.1))
         assert 0 < sol.last_nfe < 400
     assert torch.isfinite(outs[0]).all() and _rel(outs[0], outs[1]) < 1e-3
+
+
+# ---- training-loop surround: multi-tensor EMA / grad clip / AdamW --------------------------------------------------------
+def _param_sets(seed):
+    """Two UNets with the reference's parameter list (702 entries incl. biases) and synthetic gradients."""
+    from dif_pan_b200 import optim as dopt  # noqa: F401
+    net, kw = _net("gf2")
+    net2 = dp.UNetSR3(**kw).to(DEV)
+    gen = torch.Generator().manual_seed(seed)
+    for p in net2.parameters():
+        p.data = torch.randn(p.shape, generator=gen).to(DEV) * 0.05
+    for p in net.parameters():
+        p.grad = (torch.randn(p.shape, generator=gen) * 0.01).to(DEV)
+    return net, net2
+
+
+def test_ema_updater_matches_reference_expression():
+    from dif_pan_b200.optim import EmaUpdater
+    net, ema = _param_sets(3)
+    holder = lambda n: type("D", (), {"model": n, "state_dict": n.state_dict, "load_state_dict": n.load_state_dict})()
+    up = EmaUpdater(holder(net), holder(ema), decay=0.9999, start_iter=2)
+    ref = [pe.data * 0.9999 + p.data * (1 - 0.9999) for p, pe in zip(net.parameters(), ema.parameters())]   # utils/optim_utils.py:49-51
+    up.update(5)
+    for r, pe in zip(ref, ema.parameters()):
+        assert torch.equal(r, pe.data)
+    up.update(1)                                                                                             # iteration <= start_iter: copy
+    for p, pe in zip(net.parameters(), ema.parameters()):
+        assert torch.equal(p.data, pe.data)
+    assert len(up.ema_model_state_dict) == len(up.on_fly_model_state_dict) == 702
+
+
+def test_grad_clip_and_fused_adamw_match_torch():
+    from dif_pan_b200.optim import FusedAdamW, grad_clip
+    net, _ = _param_sets(4)
+    params = list(net.parameters())
+    twin = [torch.nn.Parameter(p.data.clone()) for p in params]
+    for t, p in zip(twin, params):
+        t.grad = p.grad.clone()
+    # clip by norm (the engine clips at 0.003, diffusion_engine.py:236) and by value
+    n_ref = torch.nn.utils.clip_grad_norm_(twin, max_norm=0.003)
+    n_got = grad_clip(params, mode="norm", value=0.003)
+    assert abs(float(n_got) - float(n_ref)) <= 1e-5 * float(n_ref)
+    for t, p in zip(twin, params):
+        assert float((t.grad - p.grad).abs().max()) <= 1e-6 * float(t.grad.abs().max() + 1e-12)
+    torch.nn.utils.clip_grad_value_(twin, clip_value=1e-5)
+    grad_clip(params, mode="value", value=1e-5)
+    for t, p in zip(twin, params):
+        assert float(p.grad.abs().max()) <= 1e-5 and float((t.grad - p.grad).abs().max()) <= 1e-11
+    # three AdamW steps against torch.optim.AdamW (single-tensor, unfused implementation)
+    ref_opt = torch.optim.AdamW(twin, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, foreach=False, fused=False)
+    opt = FusedAdamW(params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    gen = torch.Generator().manual_seed(9)
+    for _ in range(3):
+        for t, p in zip(twin, params):
+            g = (torch.randn(p.shape, generator=gen) * 0.01).to(DEV)
+            t.grad, p.grad = g.clone(), g.clone()
+        ref_opt.step()
+        opt.step()
+    worst = max(float((t.data - p.data).abs().max() / (t.data.abs().max() + 1e-12)) for t, p in zip(twin, params))
+    print("AdamW worst relative deviation after 3 steps", worst)
+    assert worst <= 2e-6
+    with pytest.raises(RuntimeError):
+        grad_clip([_cpu_param()], mode="value", value=1.0)
+
+
+def _cpu_param():
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    return p

@@ -356,8 +356,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
             const __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
             w[j] = *reinterpret_cast<const uint32_t*>(&t);
           }
+#ifndef DDIF_VAR_G_NO_STG
           stg256(p.out + pix * (size_t)p.out_ld + ng, w);
+#endif
         }
+#ifndef DDIF_VAR_G_NO_STATRED
         if (kStats && active) {  // all rows of one warp belong to one sample
           s1 = warp_sum(s1);
           s2 = warp_sum(s2);
@@ -368,6 +371,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
             atomicAdd(p.stats + 2 * (size_t)stat_sample + 1, (double)s2);
           }
         }
+#else
+        if (kStats && s1 + s2 == 1.2345f) atomicAdd(p.stats, 1.0);
+#endif
       }
       tc_fence_before();
     } else {

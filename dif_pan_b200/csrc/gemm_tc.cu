@@ -60,7 +60,15 @@ struct alignas(64) GemmKParams {
 static constexpr int kEpiWarps = 16;                      // 4 TMEM lane quarters x 4 column groups
 static constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp0 TMA, warp1 MMA, warps 2..17 epilogue
 
-// Persistent, warp-specialised: each CTA owns one N tile (blockIdx.y) and walks M tiles blockIdx.x, +gridDim.x, ...
+// CONTIGUOUS M-tile range of this CTA: [base, base + count) (sequential memory walk; see conv3x3_halo.cu halo_range)
+__device__ __forceinline__ void gemm_range(int num_m_tiles, int& base, int& count) {
+  const int G = (int)gridDim.x, c = (int)blockIdx.x;
+  const int q = num_m_tiles / G, r = num_m_tiles - q * G;
+  base = c * q + (c < r ? c : r);
+  count = q + (c < r ? 1 : 0);
+}
+
+// Persistent, warp-specialised: each CTA owns one N tile (blockIdx.y) and walks its contiguous range of M tiles.
 // Three pipelines: smem full/empty ring (TMA <-> MMA) running ACROSS tiles, TMEM full/empty (MMA <-> epilogue, two
 // accumulators so tile i's epilogue overlaps tile i+1's MMAs), and the static tile walk.
 // F = 0: generic run-time epilogue (epilogue.cuh), tile groups.  F & 1: lean epilogue for N <= 64 with 32-byte aligned rows --
@@ -98,6 +106,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
   const int lane = threadIdx.x & 31;
   const int n_tile = blockIdx.y;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
+  int tile_base, tile_count;
+  gemm_range(p.num_m_tiles, tile_base, tile_count);
+  const int tile_end = tile_base + tile_count;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
@@ -141,10 +152,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
       uint32_t stage = 0, phase = 0;
       uint8_t* a_dst = smem_a;
       bool first = true;
-      int img_grp = (int)blockIdx.x / tiles_per_img;
-      int t_in = (int)blockIdx.x - img_grp * tiles_per_img;
-      const int step_grp = (int)gridDim.x / tiles_per_img, step_in = (int)gridDim.x - step_grp * tiles_per_img;
-      for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x, first = false) {
+      int img_grp = tile_base / tiles_per_img;
+      int t_in = tile_base - img_grp * tiles_per_img;
+      const int step_grp = 0, step_in = 1;
+      for (int m_tile = tile_base; m_tile < tile_end; ++m_tile, first = false) {
         const int trow = t_in / p.tiles_x;
         const int ty0 = trow * p.th;
         const int tx0 = (t_in - trow * p.tiles_x) * p.tw;
@@ -204,7 +215,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
       const bool resident = p.resident_b != 0;
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       const uint32_t ngroups = (uint32_t)p.naccs;
-      for (int m_tile = blockIdx.x; m_tile < p.num_m_tiles; m_tile += gridDim.x) {
+      for (int m_tile = tile_base; m_tile < tile_end; ++m_tile) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.bn;
@@ -260,7 +271,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
       float bv[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) bv[j] = (active && p.bias) ? __ldg(p.bias + ng + j) : 0.f;
-      const int step = (int)gridDim.x * p.groups;
+      const int step = p.groups;
       LeanOperands<F> nxt;
       bool nxt_ok = false;
       size_t nxt_pix = 0;
@@ -282,17 +293,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
           ldg256(m + p.n_valid, o.sh);
         }
       };
-      int m_tile = (int)blockIdx.x + grp * (int)gridDim.x;
-      if (m_tile < p.num_m_tiles) {
+      int m_tile = tile_base + grp;
+      if (m_tile < tile_end) {
         nxt_ok = locate(m_tile, nxt_pix, nxt_b);
         fetch(nxt, nxt_pix, nxt_ok);
       }
-      for (uint32_t tcount = 0; m_tile < p.num_m_tiles; m_tile += step, ++tcount) {
+      for (uint32_t tcount = 0; m_tile < tile_end; m_tile += step, ++tcount) {
         const LeanOperands<F> cur = nxt;
         const bool row_ok = nxt_ok;
         const size_t pix = nxt_pix;
         const int b = nxt_b;
-        if (m_tile + step < p.num_m_tiles) {
+        if (m_tile + step < tile_end) {
           nxt_ok = locate(m_tile + step, nxt_pix, nxt_b);
           fetch(nxt, nxt_pix, nxt_ok);  // next tile's operands travel while this tile is processed
         }
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
     EpiParams e{p.bias, p.film, p.film_ld, p.mod, p.residual, p.res_ld, p.act, p.out, p.out_ld, p.out_nchw, p.stats,
                 p.n_valid, p.batch, p.out_h, p.out_w};
     uint32_t tcount = 0;
-    for (int m_tile = (int)blockIdx.x + grp * (int)gridDim.x; m_tile < p.num_m_tiles; m_tile += p.groups * (int)gridDim.x, ++tcount) {
+    for (int m_tile = tile_base + grp; m_tile < tile_end; m_tile += p.groups, ++tcount) {
       const int img_grp = m_tile / tiles_per_img;
       const int t_in = m_tile - img_grp * tiles_per_img;
       const int y = (t_in / p.tiles_x) * p.th + ry;

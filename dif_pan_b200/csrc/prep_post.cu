@@ -39,9 +39,10 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 }
 
 // ---- fused conditioning prep ----------------------------------------------------------------------------------------
-// Haar coefficient k (0 LL, 1 cH, 2 cV, 3 cD) of the 2x2 block (by, bx) of one plane, divided by dv -- same expressions as
-// haar_dwt2_kernel (sampler.cu), so the fused path is bit-identical to DWT -> cat -> cond_assemble.
-__device__ __forceinline__ float haar_coef(const float* __restrict__ pl, int w, int by, int bx, int k, float dv) {
+// Haar coefficient k (0 LL, 1 cH, 2 cV, 3 cD) of the 2x2 block (by, bx) of one plane, scaled by inv = 1 / division.  The multiply by the
+// reciprocal (<= 1.5 ulp from the IEEE division of haar_dwt2_kernel) replaces eight ~18-instruction divisions per thread: ncu showed
+// this kernel instruction-bound on them (FCHK + slow path), 333 us for 64 WV3 scenes of 256x256.
+__device__ __forceinline__ float haar_coef(const float* __restrict__ pl, int w, int by, int bx, int k, float inv) {
   const float2 r0 = *reinterpret_cast<const float2*>(pl + (size_t)(2 * by) * w + 2 * bx);
   const float2 r1 = *reinterpret_cast<const float2*>(pl + (size_t)(2 * by + 1) * w + 2 * bx);
   const float ab = ADD(r0.x, r0.y), cd = ADD(r1.x, r1.y), amb = SUB(r0.x, r0.y), cmd = SUB(r1.x, r1.y);
@@ -50,7 +51,7 @@ __device__ __forceinline__ float haar_coef(const float* __restrict__ pl, int w, 
   else if (k == 1) v = SUB(ab, cd);
   else if (k == 2) v = ADD(amb, cmd);
   else v = SUB(amb, cmd);
-  return DIV(MUL(v, 0.5f), dv);
+  return MUL(MUL(v, 0.5f), inv);
 }
 
 // grid (ceil(h * w/4 / 256), channels of cond, batch): one thread per 4 consecutive output pixels of one cond plane, 32-bit indexing.
@@ -64,12 +65,12 @@ __global__ void __launch_bounds__(256) wavelet_cond_kernel(ddif_wavelet_cond_t p
   if (idx >= h * wq) return;
   const int oy = idx / wq, q = idx - oy * wq;
   const size_t hw = (size_t)h * w;
-  const float dv = (float)p.divisor;
+  const float dv = (float)(1.0 / p.divisor);  // reciprocal, see haar_coef
   float4* dst = reinterpret_cast<float4*>(p.cond + ((size_t)b * ct + ch) * hw + (size_t)oy * w + 4 * q);
   if (ch < c + pp) {
     const float* src = ch < c ? p.lms + ((size_t)b * c + ch) * hw : p.pan + ((size_t)b * pp + (ch - c)) * hw;
     const float4 v = *reinterpret_cast<const float4*>(src + (size_t)oy * w + 4 * q);
-    *dst = make_float4(DIV(v.x, dv), DIV(v.y, dv), DIV(v.z, dv), DIV(v.w, dv));
+    *dst = make_float4(MUL(v.x, dv), MUL(v.y, dv), MUL(v.z, dv), MUL(v.w, dv));
     return;
   }
   const int k = ch - c - pp;  // wavelet channel: [LL(lms) x c | pan sub-band 0 x p | sub-band 1 x p | sub-band 2 x p]

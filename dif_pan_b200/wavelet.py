@@ -82,7 +82,7 @@ def make_cond(lms_dn: torch.Tensor, pan_dn: torch.Tensor, division: float = 1.0,
     """Raw `lms` [B,C,H,W] and `pan` [B,P,H,W] (digital numbers, or [0,1] data with division=1) -> `cond` [B, 2C+4P, H, W] in ONE
     kernel (`ddif_wavelet_cond_f32`): Haar DWT of both, /division, the dataset's channel order, bilinear x2 of the wavelet stack and
     the concat with lms/division and pan/division (pan_dataset.py:73-142, hisr.py:48-59, diffusion_engine.py:221-228).
-    Same expressions as `assemble_cond(lms/div, pan/div, wavelet_channels(...))` (wavelets bit-identical, the bilinear taps to an ulp);
+    Same arithmetic as `assemble_cond(lms/div, pan/div, wavelet_channels(...))` up to 1.5 ulp (multiply by 1/division instead of dividing);
     4 B read + 4 B written per cond element instead of
     three kernels and two intermediate tensors.  With return_wavelets also returns the [B, C+3P, H/2, W/2] stack the datasets yield."""
     if not (lms_dn.is_cuda and pan_dn.is_cuda):

@@ -166,8 +166,8 @@ def test_make_cond_fused(ds):
     cond, wav = dp.make_cond(lms_dn, pan_dn, spec.division, spec.wavelet_order, return_wavelets=True)
     wav3 = dp.wavelet_channels(lms_dn, pan_dn, spec.division, spec.wavelet_order)
     cond3 = dp.assemble_cond(lms_dn / spec.division, pan_dn / spec.division, wav3)
-    assert torch.equal(wav, wav3)                                        # same expressions as the stand-alone DWT kernel: bit-identical
-    assert float((cond - cond3).abs().max()) <= 5e-7                     # bilinear taps: FMA contraction may differ by an ulp
+    assert float((wav - wav3).abs().max()) <= 2.5e-7                     # reciprocal multiply vs the DWT kernel's IEEE division: <= 1.5 ulp
+    assert float((cond - cond3).abs().max()) <= 5e-7                     # + bilinear taps: FMA contraction may differ by an ulp
     assert float((cond.cpu() - d["cond"]).abs().max()) <= 2e-6           # and equal to the float64 dataset pipeline
     assert float((wav.cpu() - d["wavelets"]).abs().max()) <= 1e-6
     big = dp.make_cond(torch.rand(1, 4, 512, 512, device=DEV) * 1023, torch.rand(1, 1, 512, 512, device=DEV) * 1023, 1023.0)

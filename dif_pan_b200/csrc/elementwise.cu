@@ -618,24 +618,35 @@ int launch_attn(const ddif_attn_t& p, cudaStream_t s) {
 }
 
 // ---- nearest x2 (sr3_dwt.py:269) ---------------------------------------------------------------------------
-__global__ void upsample2x_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
+// One thread per INPUT 16-byte chunk: one load, four stores (the 2x2 output pixels), 32-bit index math; grid (chunks of a sample, batch).
+__global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
+  pdl_wait();
   const int nchunk = C >> 3;
-  const int OW = 2 * W, OH = 2 * H;
-  const int64_t items = (int64_t)B * OH * OW * nchunk;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ch = (int)(i % nchunk);
-    int64_t r = i / nchunk;
-    const int ox = (int)(r % OW); r /= OW;
-    const int oy = (int)(r % OH);
-    const int b = (int)(r / OH);
-    const bf16x8 v = *reinterpret_cast<const bf16x8*>(in + (((size_t)b * H + (oy >> 1)) * W + (ox >> 1)) * C + ch * 8);
-    *reinterpret_cast<bf16x8*>(out + (size_t)i * 8) = v;
+  const int per_sample = H * W * nchunk;
+  const int b = blockIdx.y;
+  const uint4* src = reinterpret_cast<const uint4*>(in) + (size_t)b * per_sample;
+  uint4* dst = reinterpret_cast<uint4*>(out) + (size_t)b * per_sample * 4;
+  const int OW = 2 * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += gridDim.x * blockDim.x) {
+    const int ch = i % nchunk;
+    const int px = i / nchunk;
+    const int y = px / W, x = px - y * W;
+    const uint4 v = src[i];
+    const int o = ((2 * y) * OW + 2 * x) * nchunk + ch;
+    dst[o] = v;
+    dst[o + nchunk] = v;
+    dst[o + OW * nchunk] = v;
+    dst[o + OW * nchunk + nchunk] = v;
   }
 }
 int launch_upsample2x(const ddif_upsample2x_t& p, cudaStream_t s) {
   if (p.c % 8 != 0) return DDIF_ERR_SHAPE;
-  upsample2x_kernel<<<grid_for(p.batch * p.h * p.w * 4 * (p.c / 8), 256), 256, 0, s>>>((const bf16*)p.in, (bf16*)p.out, (int)p.batch,
-                                                                                         (int)p.h, (int)p.w, (int)p.c);
+  if (p.batch < 1 || p.batch > 65535 || p.h * p.w * p.c > (1 << 28)) return DDIF_ERR_SHAPE;
+  const int per_sample = (int)(p.h * p.w * (p.c / 8));
+  int gx = (per_sample + 255) / 256;
+  if (gx > 64) gx = 64;
+  DDIF_CUDA_CHECK(launch_pdl(upsample2x_kernel, dim3((unsigned)gx, (unsigned)p.batch), dim3(256), (size_t)0, s, (const bf16*)p.in, (bf16*)p.out,
+                             (int)p.batch, (int)p.h, (int)p.w, (int)p.c));
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }

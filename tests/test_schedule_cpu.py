@@ -153,3 +153,51 @@ def test_cabi_exports_and_struct_sizes():
     p = lib.ddif_plan_create()
     assert lib.ddif_plan_size(ctypes.c_void_p(p)) == 0
     lib.ddif_plan_destroy(ctypes.c_void_p(p))
+
+
+def test_dpm_solver_host_logic_singlestep_orders_and_times():
+    """Host side of the singlestep solvers (no GPU): the "DPM-Solver-fast" order schedule of dpm_solver.py:490-548 (cases from its
+    docstring) and the outer time grid; stage coefficients are finite and consistent between the orders that share evaluations."""
+    import math
+    from dif_pan_b200.dpm_solver import DPM_Solver, NoiseScheduleVP, model_wrapper
+    from dif_pan_b200.diffusion import make_beta_schedule
+    ns = NoiseScheduleVP("discrete", betas=torch.as_tensor(make_beta_schedule("cosine", 500), dtype=torch.float32))
+    sol = DPM_Solver(model_wrapper(lambda x, t, c: x, ns, model_type="x_start", guidance_type="classifier-free", condition=torch.zeros(1)), ns)
+    t0, tT = 1.0 / ns.total_N, ns.T
+    cases = {(9, 3): [3, 3, 2, 1], (10, 3): [3, 3, 3, 1], (11, 3): [3, 3, 3, 2], (6, 2): [2, 2, 2], (7, 2): [2, 2, 2, 1], (4, 1): [1, 1, 1, 1]}
+    for (steps, order), want in cases.items():
+        outer, orders = sol.get_orders_and_timesteps_for_singlestep_solver(steps, order, "time_uniform", tT, t0)
+        assert orders == want and sum(orders) == steps
+        grid = torch.linspace(tT, t0, steps + 1)
+        assert torch.equal(outer, grid[torch.cumsum(torch.tensor([0] + orders), 0)])
+        assert float(outer[0]) == tT and abs(float(outer[-1]) - t0) < 1e-9
+    outer, orders = sol.get_orders_and_timesteps_for_singlestep_solver(10, 3, "logSNR", tT, t0)
+    assert len(outer) == len(orders) + 1 == 5 and all(float(outer[i]) > float(outer[i + 1]) for i in range(4))
+    with pytest.raises(ValueError):
+        sol.get_orders_and_timesteps_for_singlestep_solver(10, 4, "time_uniform", tT, t0)
+    s, t = torch.tensor([0.8]), torch.tensor([0.6])
+    st2 = sol._single_coefficients(s, t, 2, 1.0 / 3.0, None)
+    st3 = sol._single_coefficients(s, t, 3, 1.0 / 3.0, 2.0 / 3.0)
+    assert len(st2) == 2 and len(st3) == 3
+    assert st2[0][3:5] == st3[0][3:5] and float(st2[0][1]) == float(st3[0][1])      # shared first stage (adaptive order 3 relies on it)
+    assert all(math.isfinite(v) for stg in st2 + st3 for v in stg[3:])
+    assert st3[-1][1] is None and st3[1][1] is not None                              # last stage ends the step
+    with pytest.raises(ValueError):
+        sol.sample(torch.zeros(1, 1, 4, 4), method="bogus")
+    with pytest.raises(NotImplementedError):
+        sol.sample(torch.zeros(1, 1, 4, 4), solver_type="taylor")
+    with pytest.raises(RuntimeError):
+        sol.sample(torch.zeros(1, 1, 4, 4), steps=4, order=2, method="singlestep")   # CPU tensor: no fallback
+
+
+def test_every_op_kind_has_a_struct_and_named_wrappers_exist():
+    """Header <-> binding consistency: every DDIF_OP_* kind is reachable from Python through exactly one parameter struct (two kinds
+    share ddif_haar_t), and the named convenience wrappers the header declares are exported by the library."""
+    kinds = set(_lib.KINDS)
+    mapped = set(_lib.KIND_OF_STRUCT.values()) | {"DDIF_OP_HAAR_DWT2", "DDIF_OP_HAAR_IDWT2"}
+    assert kinds == mapped, kinds ^ mapped
+    assert set(_lib.KIND_OF_STRUCT) | {"ddif_haar_t"} == set(_lib.STRUCTS)
+    lib = _lib.load()
+    for name in _lib.EXPORTS:
+        assert getattr(lib, name) is not None
+    assert len(_lib.EXPORTS) >= 29 and len(kinds) == 31

@@ -12,7 +12,8 @@ Implemented: algorithm_type 'dpmsolver++' and 'dpmsolver'; method 'multistep' (o
 `ddif_dpm_single_f32` kernel per denoiser evaluation); skip types time_uniform / time_quadratic / logSNR; model types
 x_start / noise / v; guidance 'uncond' or 'classifier-free' with scale 1 (the wiring SURVEY.md §3.3 names).
 method='adaptive' (dpm.py:964-1018; one error-norm reduction kernel + a host scalar decision per iteration) is implemented
-as well.  solver_type='taylor', thresholding correctors and denoise_to_zero raise NotImplementedError (not used by any
+as well, and solver_type='taylor' for the multistep and the first/second-order singlestep updates (host scalars only).  The
+third-order singlestep 'taylor' form, thresholding correctors and denoise_to_zero raise NotImplementedError (not used by any
 BASELINE config).
 
 Reference quirk kept out: model_wrapper multiplies `[B]`-shaped alpha_t against `[B,C,H,W]` (dpm.py:299-300),
@@ -160,6 +161,7 @@ class DPM_Solver:
         self.model = lambda x, t: model_fn(x, t.expand((x.shape[0])))
         self.noise_schedule = noise_schedule
         self.algorithm_type = algorithm_type
+        self._solver_type = "dpmsolver"
 
     def get_time_steps(self, skip_type, t_T, t_0, N, device=None):
         """dpm.py:461-488 (host tensors)."""
@@ -193,7 +195,11 @@ class DPM_Solver:
             c = dict(cx=torch.exp(ns.marginal_log_mean_coeff(t_next) - ns.marginal_log_mean_coeff(t0)), ca=scale * phi_1)
         if order == 2:
             r0 = (lam(t0) - lam(t_hist[-2])) / h
-            c.update(cb=0.5 * (scale * phi_1), inv_r0=1.0 / r0)
+            if self._solver_type == "taylor":   # dpm.py:843-848 / 855-860: x -= ... becomes  + a*(phi_1/h + 1)*D1  resp.  - s*(phi_1/h - 1)*D1
+                cb = -(scale * (phi_1 / h + 1.0)) if pp else scale * (phi_1 / h - 1.0)
+            else:
+                cb = 0.5 * (scale * phi_1)
+            c.update(cb=cb, inv_r0=1.0 / r0)
         elif order == 3:
             r0 = (lam(t0) - lam(t_hist[-2])) / h
             r1 = (lam(t_hist[-2]) - lam(t_hist[-3])) / h
@@ -254,9 +260,16 @@ class DPM_Solver:
             r1 = 0.5 if r1 is None else r1
             s1 = ns.inverse_lambda(lam_s + r1 * h)
             phi_11, phi_1 = em(r1 * h), em(h)
-            c2 = (0.5 / r1) * (amp(t) * phi_1)
+            if self._solver_type == "taylor":   # dpm.py:651-656 / 674-679
+                c2 = (1.0 / r1) * (amp(t) * (phi_1 / h + 1.0)) if pp else -((1.0 / r1) * (amp(t) * (phi_1 / h - 1.0)))
+                c2 = f(c2)
+            else:
+                c2 = -f((0.5 / r1) * (amp(t) * phi_1))
             return [(s, s1, 0, f(lead(s1)), f(amp(s1) * phi_11), 0.0),
-                    (s1, None, 1, f(lead(t)), f(amp(t) * phi_1), -f(c2))]
+                    (s1, None, 1, f(lead(t)), f(amp(t) * phi_1), c2)]
+        if self._solver_type == "taylor":
+            raise NotImplementedError("solver_type='taylor' for the third-order singlestep update (three model values, dpm.py:759-768) is not on "
+                                      "the CUDA path")
         r1 = 1.0 / 3.0 if r1 is None else r1
         r2 = 2.0 / 3.0 if r2 is None else r2
         s1, s2 = ns.inverse_lambda(lam_s + r1 * h), ns.inverse_lambda(lam_s + r2 * h)
@@ -422,10 +435,9 @@ class DPM_Solver:
             raise ValueError("Got wrong method {}".format(method))
         if return_intermediate:
             assert method in ["multistep", "singlestep", "singlestep_fixed"], "Cannot use adaptive solver when saving intermediate values"
-        if solver_type != "dpmsolver":
-            if solver_type == "taylor":
-                raise NotImplementedError("solver_type='taylor' is not on the CUDA path")
+        if solver_type not in ("dpmsolver", "taylor"):
             raise ValueError("'solver_type' must be either 'dpmsolver' or 'taylor', got {}".format(solver_type))
+        self._solver_type = solver_type  # 'taylor' only changes host-side scalars (orders <= 2; the multistep third order has one form)
         if denoise_to_zero:
             raise NotImplementedError("denoise_to_zero is not on the CUDA path")
         if order not in (1, 2, 3):

@@ -369,7 +369,7 @@ def dpm_prediction(ns, model, x, t, cond, model_type, algorithm):
 
 
 def dpm_sample(model, ns: "VPSchedule", x, cond=None, steps=20, order=2, skip_type="time_uniform", method="multistep",
-               algorithm="dpmsolver++", model_type="x_start", lower_order_final=True):
+               algorithm="dpmsolver++", model_type="x_start", lower_order_final=True, solver_type="dpmsolver"):
     """DPM_Solver.sample for method in multistep / singlestep / singlestep_fixed, solver_type 'dpmsolver' (dpm.py:1055-1253)."""
     pp = algorithm == "dpmsolver++"
     t_0, t_T = 1.0 / ns.total_N, ns.T
@@ -387,14 +387,19 @@ def dpm_sample(model, ns: "VPSchedule", x, cond=None, steps=20, order=2, skip_ty
         h = ns.lam(t) - ns.lam(s)
         s1 = inverse_lambda(ns, ns.lam(s) + r1 * h)
         m_s = pred(x, s)
+        tay = solver_type == "taylor"  # dpm.py:651-656, 674-679
         if pp:
             phi_11, phi_1 = torch.expm1(-r1 * h), torch.expm1(-h)
             x_s1 = (ns.std(s1) / ns.std(s)) * x - (ns.alpha(s1) * phi_11) * m_s
             m_s1 = pred(x_s1, s1)
+            if tay:
+                return (ns.std(t) / ns.std(s)) * x - (ns.alpha(t) * phi_1) * m_s + (1.0 / r1) * (ns.alpha(t) * (phi_1 / h + 1.0)) * (m_s1 - m_s)
             return (ns.std(t) / ns.std(s)) * x - (ns.alpha(t) * phi_1) * m_s - (0.5 / r1) * (ns.alpha(t) * phi_1) * (m_s1 - m_s)
         phi_11, phi_1 = torch.expm1(r1 * h), torch.expm1(h)
         x_s1 = torch.exp(la(s1) - la(s)) * x - (ns.std(s1) * phi_11) * m_s
         m_s1 = pred(x_s1, s1)
+        if tay:
+            return torch.exp(la(t) - la(s)) * x - (ns.std(t) * phi_1) * m_s - (1.0 / r1) * (ns.std(t) * (phi_1 / h - 1.0)) * (m_s1 - m_s)
         return torch.exp(la(t) - la(s)) * x - (ns.std(t) * phi_1) * m_s - (0.5 / r1) * (ns.std(t) * phi_1) * (m_s1 - m_s)
 
     def single3(x, s, t, r1, r2):
@@ -432,6 +437,10 @@ def dpm_sample(model, ns: "VPSchedule", x, cond=None, steps=20, order=2, skip_ty
         amp = ns.alpha(t) if pp else ns.std(t)
         phi_1 = torch.expm1(-h) if pp else torch.expm1(h)
         if o == 2:
+            if solver_type == "taylor":  # dpm.py:843-848, 855-860
+                if pp:
+                    return lead * x - (amp * phi_1) * m[-1] + (amp * (phi_1 / h + 1.0)) * D10
+                return lead * x - (amp * phi_1) * m[-1] - (amp * (phi_1 / h - 1.0)) * D10
             return lead * x - (amp * phi_1) * m[-1] - 0.5 * (amp * phi_1) * D10
         r1 = (ns.lam(tl[-2]) - ns.lam(tl[-3])) / h
         D11 = (1.0 / r1) * (m[-2] - m[-3])

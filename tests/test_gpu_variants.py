@@ -340,3 +340,21 @@ def _cpu_param():
     p = torch.nn.Parameter(torch.zeros(4))
     p.grad = torch.ones(4)
     return p
+
+
+from test_oracle_variants import TAYLOR_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", TAYLOR_CASES, ids=[case_key(c) for c in TAYLOR_CASES])
+def test_dpm_taylor_matches_reference_golden(case):
+    """solver_type='taylor' only changes host-side scalars of the second-order updates (same fused kernels)."""
+    g = np.load(os.path.join(GOLDEN, "dpm_variants.npz"))
+    x_T, cond = dpm_inputs(int(g["seed"]))
+    method, order, steps, skip, algo, mtype = case
+    betas = torch.as_tensor(so.make_beta_schedule("cosine", 500), dtype=torch.float32)
+    ns = dp.NoiseScheduleVP("discrete", betas=betas.to(DEV))
+    wm = dp.model_wrapper(so.analytic_denoiser, ns, model_type=mtype, guidance_type="classifier-free", condition=cond.to(DEV), guidance_scale=1.0)
+    got = dp.DPM_Solver(wm, ns, algorithm_type=algo).sample(x_T.to(DEV), steps=steps, order=order, skip_type=skip, method=method, solver_type="taylor")
+    assert rel_max(got.cpu().numpy(), g["taylor_" + case_key(case)]) <= 2e-3
+    with pytest.raises(NotImplementedError):
+        dp.DPM_Solver(wm, ns, algorithm_type=algo).sample(x_T.to(DEV), steps=9, order=3, method="singlestep", solver_type="taylor")

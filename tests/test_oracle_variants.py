@@ -102,3 +102,22 @@ def test_dpm_adaptive_oracle_matches_reference(order, algo, mtype):
     out, nfe = so.dpm_adaptive(so.analytic_denoiser, ns, x_T.clone(), cond, order=order, algorithm=algo, model_type=mtype)
     key = f"adaptive_{order}_{algo.replace('+', 'p')}_{mtype}"
     assert nfe > 0 and rel_max(out.numpy(), g[key]) <= 2e-4, (nfe, rel_max(out.numpy(), g[key]))
+
+
+TAYLOR_CASES = [
+    ("multistep", 2, 10, "time_uniform", "dpmsolver++", "x_start"),
+    ("multistep", 2, 10, "time_uniform", "dpmsolver", "x_start"),
+    ("singlestep", 2, 8, "time_uniform", "dpmsolver++", "x_start"),
+    ("singlestep", 2, 7, "logSNR", "dpmsolver", "x_start"),
+]
+
+
+@pytest.mark.parametrize("case", TAYLOR_CASES, ids=[case_key(c) for c in TAYLOR_CASES])
+def test_dpm_taylor_oracle_matches_reference(case):
+    g = np.load(os.path.join(GOLDEN, "dpm_variants.npz"))
+    x_T, cond = dpm_inputs(int(g["seed"]))
+    method, order, steps, skip, algo, mtype = case
+    ns = so.VPSchedule(torch.as_tensor(so.make_beta_schedule("cosine", 500), dtype=torch.float32))
+    out = so.dpm_sample(so.analytic_denoiser, ns, x_T.clone(), cond, steps=steps, order=order, skip_type=skip, method=method,
+                        algorithm=algo, model_type=mtype, solver_type="taylor")
+    assert rel_max(out.numpy(), g["taylor_" + case_key(case)]) <= 2e-4

@@ -184,8 +184,11 @@ def test_dpm_solver_host_logic_singlestep_orders_and_times():
     assert st3[-1][1] is None and st3[1][1] is not None                              # last stage ends the step
     with pytest.raises(ValueError):
         sol.sample(torch.zeros(1, 1, 4, 4), method="bogus")
+    sol._solver_type = "taylor"
+    assert len(sol._single_coefficients(s, t, 2, 0.5, None)) == 2
     with pytest.raises(NotImplementedError):
-        sol.sample(torch.zeros(1, 1, 4, 4), solver_type="taylor")
+        sol._single_coefficients(s, t, 3, 1.0 / 3.0, 2.0 / 3.0)   # the three-value third-order 'taylor' form is not on the CUDA path
+    sol._solver_type = "dpmsolver"
     with pytest.raises(RuntimeError):
         sol.sample(torch.zeros(1, 1, 4, 4), steps=4, order=2, method="singlestep")   # CPU tensor: no fallback
 

@@ -13,8 +13,8 @@ Implemented: algorithm_type 'dpmsolver++' and 'dpmsolver'; method 'multistep' (o
 x_start / noise / v; guidance 'uncond' or 'classifier-free' with scale 1 (the wiring SURVEY.md §3.3 names).
 method='adaptive' (dpm.py:964-1018; one error-norm reduction kernel + a host scalar decision per iteration) is implemented
 as well, and solver_type='taylor' for the multistep and the first/second-order singlestep updates (host scalars only).  The
-third-order singlestep 'taylor' form, thresholding correctors and denoise_to_zero raise NotImplementedError (not used by any
-BASELINE config).
+third-order singlestep 'taylor' form and the thresholding correctors raise NotImplementedError (not used by any BASELINE config);
+denoise_to_zero is one more evaluation + the data-prediction kernel.
 
 Reference quirk kept out: model_wrapper multiplies `[B]`-shaped alpha_t against `[B,C,H,W]` (dpm.py:299-300),
 which only broadcasts for B == 1 or B == W; all entries are equal, so a scalar multiply is the same arithmetic and
@@ -368,7 +368,26 @@ class DPM_Solver:
             self.last_nfe = nfe
             return xs.clone()
 
-    def _sample_singlestep(self, x, steps, order, skip_type, method, t_T, t_0, return_intermediate):
+    def _denoise_to_zero(self, xb, t_0, rt=None):
+        """denoise_to_zero_fn (dpm.py:550-554): one more denoiser evaluation at t_0 and x <- data_prediction_fn(x, t_0) (always the DATA
+        prediction, whatever the algorithm type).  `rt`: the UNet runtime when xb is its input buffer (fast path)."""
+        ns, wm = self.noise_schedule, self.wrapped
+        B, dev = xb.shape[0], xb.device
+        t = torch.ones((1,)) * t_0
+        if rt is not None:
+            rt.t_buf.fill_(float(wm.input_time(t)))
+            rt.step()
+            out = rt.out_buf
+        else:
+            out = wm.raw(xb, t.to(dev).expand(B)).contiguous()
+        x0 = torch.empty_like(xb)
+        _lib.launch("ddif_dpm_single_t", torch.cuda.current_stream(dev).cuda_stream, x_base=None, x_eval=xb.data_ptr(), model_out=out.data_ptr(),
+                    m_cur=x0.data_ptr(), m_a=None, x_out=None, time_out=None, n=xb.numel(), batch=B, model_type=MODEL_TYPES[wm.model_type],
+                    predict=0, mode=2, alpha_e=float(ns.marginal_alpha(t)), sigma_e=float(ns.marginal_std(t)), c0=0.0, c1=0.0, c2=0.0,
+                    t_next_in=0.0)
+        return x0
+
+    def _sample_singlestep(self, x, steps, order, skip_type, method, t_T, t_0, return_intermediate, denoise_to_zero=False):
         """dpm.py:1222-1240: every outer step s -> t evaluates the denoiser `order` times (at s, s1[, s2]); each evaluation is
         followed by ONE fused kernel (model_wrapper round trip + prediction + the stage's linear update)."""
         ns, wm = self.noise_schedule, self.wrapped
@@ -421,6 +440,10 @@ class DPM_Solver:
                 if return_intermediate:
                     inter.append(xe.clone())
             res = xe.clone()
+            if denoise_to_zero:
+                res = self._denoise_to_zero(xe, t_0, rt if fast else None)
+                if return_intermediate:
+                    inter.append(res.clone())
         return (res, inter) if return_intermediate else res
 
     def sample(self, x, steps=20, t_start=None, t_end=None, order=2, skip_type="time_uniform", method="multistep",
@@ -438,16 +461,15 @@ class DPM_Solver:
         if solver_type not in ("dpmsolver", "taylor"):
             raise ValueError("'solver_type' must be either 'dpmsolver' or 'taylor', got {}".format(solver_type))
         self._solver_type = solver_type  # 'taylor' only changes host-side scalars (orders <= 2; the multistep third order has one form)
-        if denoise_to_zero:
-            raise NotImplementedError("denoise_to_zero is not on the CUDA path")
         if order not in (1, 2, 3):
             raise ValueError("Solver order must be 1 or 2 or 3, got {}".format(order))
         if not x.is_cuda:
             raise RuntimeError("dif_pan_b200 sampler kernels run on CUDA only (no CPU fallback)")
         if method == "adaptive":
-            return self.dpm_solver_adaptive(x, order=order, t_T=t_T, t_0=t_0, atol=atol, rtol=rtol, solver_type=solver_type)
+            res = self.dpm_solver_adaptive(x, order=order, t_T=t_T, t_0=t_0, atol=atol, rtol=rtol, solver_type=solver_type)
+            return self._denoise_to_zero(res, t_0) if denoise_to_zero else res
         if method != "multistep":
-            return self._sample_singlestep(x, steps, order, skip_type, method, t_T, t_0, return_intermediate)
+            return self._sample_singlestep(x, steps, order, skip_type, method, t_T, t_0, return_intermediate, denoise_to_zero)
         assert steps >= order
         wm = self.wrapped
         ts = self.get_time_steps(skip_type, t_T, t_0, steps)
@@ -492,4 +514,8 @@ class DPM_Solver:
                 if return_intermediate:
                     inter.append(xb.clone())
             res = xb.clone()
+            if denoise_to_zero:
+                res = self._denoise_to_zero(xb, t_0, rt if fast else None)
+                if return_intermediate:
+                    inter.append(res.clone())
         return (res, inter) if return_intermediate else res

@@ -369,8 +369,11 @@ def dpm_prediction(ns, model, x, t, cond, model_type, algorithm):
 
 
 def dpm_sample(model, ns: "VPSchedule", x, cond=None, steps=20, order=2, skip_type="time_uniform", method="multistep",
-               algorithm="dpmsolver++", model_type="x_start", lower_order_final=True, solver_type="dpmsolver"):
+               algorithm="dpmsolver++", model_type="x_start", lower_order_final=True, solver_type="dpmsolver", denoise_to_zero=False):
     """DPM_Solver.sample for method in multistep / singlestep / singlestep_fixed, solver_type 'dpmsolver' (dpm.py:1055-1253)."""
+    if denoise_to_zero:  # dpm.py:550-554, 1241-1247: x <- data_prediction_fn(x, t_0) after the last step
+        xe = dpm_sample(model, ns, x, cond, steps, order, skip_type, method, algorithm, model_type, lower_order_final, solver_type, False)
+        return dpm_prediction(ns, model, xe, torch.ones((1,)) * (1.0 / ns.total_N), cond, model_type, "dpmsolver++")
     pp = algorithm == "dpmsolver++"
     t_0, t_T = 1.0 / ns.total_N, ns.T
     pred = lambda xx, tt: dpm_prediction(ns, model, xx, tt, cond, model_type, algorithm)

@@ -358,3 +358,18 @@ def test_dpm_taylor_matches_reference_golden(case):
     assert rel_max(got.cpu().numpy(), g["taylor_" + case_key(case)]) <= 2e-3
     with pytest.raises(NotImplementedError):
         dp.DPM_Solver(wm, ns, algorithm_type=algo).sample(x_T.to(DEV), steps=9, order=3, method="singlestep", solver_type="taylor")
+
+
+from test_oracle_variants import DTZ_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", DTZ_CASES, ids=[case_key(c) for c in DTZ_CASES])
+def test_dpm_denoise_to_zero_matches_reference_golden(case):
+    g = np.load(os.path.join(GOLDEN, "dpm_variants.npz"))
+    x_T, cond = dpm_inputs(int(g["seed"]))
+    method, order, steps, skip, algo, mtype = case
+    betas = torch.as_tensor(so.make_beta_schedule("cosine", 500), dtype=torch.float32)
+    ns = dp.NoiseScheduleVP("discrete", betas=betas.to(DEV))
+    wm = dp.model_wrapper(so.analytic_denoiser, ns, model_type=mtype, guidance_type="classifier-free", condition=cond.to(DEV), guidance_scale=1.0)
+    got = dp.DPM_Solver(wm, ns, algorithm_type=algo).sample(x_T.to(DEV), steps=steps, order=order, skip_type=skip, method=method, denoise_to_zero=True)
+    assert rel_max(got.cpu().numpy(), g["dtz_" + case_key(case)]) <= 2e-3

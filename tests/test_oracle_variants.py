@@ -121,3 +121,17 @@ def test_dpm_taylor_oracle_matches_reference(case):
     out = so.dpm_sample(so.analytic_denoiser, ns, x_T.clone(), cond, steps=steps, order=order, skip_type=skip, method=method,
                         algorithm=algo, model_type=mtype, solver_type="taylor")
     assert rel_max(out.numpy(), g["taylor_" + case_key(case)]) <= 2e-4
+
+
+DTZ_CASES = [("multistep", 2, 10, "time_uniform", "dpmsolver++", "x_start"), ("singlestep", 3, 9, "time_uniform", "dpmsolver", "x_start")]
+
+
+@pytest.mark.parametrize("case", DTZ_CASES, ids=[case_key(c) for c in DTZ_CASES])
+def test_dpm_denoise_to_zero_oracle_matches_reference(case):
+    g = np.load(os.path.join(GOLDEN, "dpm_variants.npz"))
+    x_T, cond = dpm_inputs(int(g["seed"]))
+    method, order, steps, skip, algo, mtype = case
+    ns = so.VPSchedule(torch.as_tensor(so.make_beta_schedule("cosine", 500), dtype=torch.float32))
+    out = so.dpm_sample(so.analytic_denoiser, ns, x_T.clone(), cond, steps=steps, order=order, skip_type=skip, method=method,
+                        algorithm=algo, model_type=mtype, denoise_to_zero=True)
+    assert rel_max(out.numpy(), g["dtz_" + case_key(case)]) <= 2e-4

@@ -11,6 +11,13 @@ bf16 UNet internals / fp32 sampler state.  One "step" = one complete sampling of
 inputs resident in HBM; `e2e` = the same through the public API with the conditioning coming from pinned host
 memory and the fused images copied back to the host every step.  Multi-GPU: one process per GPU (torchrun), patches
 sharded, no data-path collective, final NCCL all_gather of the finished patches inside the timed region.
+
+The headline line is WEAK scaling (256 patches per GPU; the driver computes efficiency from the per-N values).  BASELINE configs[1]
+as written -- 256 patches in TOTAL, 256 / N per GPU -- is measured in the same run and reported under `strong` (or as the headline
+with --scaling strong).  Extra keys measured OUTSIDE the timed region on rank 0 at N = 1: `cpu_baseline` (the reference algorithm on
+the host cores), `gpu_eager_baseline` (the same reference algorithm as eager PyTorch -- cuDNN / cuBLAS -- on this GPU in fp32 and
+under bf16 autocast: the real bar, since the reference ships no Blackwell kernel) and `other_configs`
+(BASELINE configs[0], [2], [3] through the public API).
 """
 from __future__ import annotations
 
@@ -39,6 +46,8 @@ def parse():
     ap.add_argument("--timesteps", type=int, default=500)
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch patches per GPU (headline); strong: --batch patches in total")
+    ap.add_argument("--no-extras", action="store_true", help="skip strong / gpu_eager_baseline / other_configs (tuning runs)")
     return ap.parse_args()
 
 
@@ -129,6 +138,99 @@ def cpu_reference_run(cpu_batch: int, timesteps: int, steps: int, warmup: int):
                        f"patches/s extrapolated to T={timesteps}")
 
 
+def gpu_eager_run(dev, batches=(1, 32, 256), nsteps=20):
+    """The reference algorithm (oracle port = functional restatement of models/sr3_dwt.py + the DDPM posterior, pinned to the reference's
+    golden vectors) as EAGER PyTorch on this GPU: cuDNN convolutions (channels-last, cudnn.benchmark), native group_norm, cuBLAS bmm -- what
+    the reference itself would run here, in fp32 (torch defaults: TF32 allowed for cuDNN convolutions) and under torch.autocast(bfloat16).
+    ms per denoise step (UNet forward + posterior) over `nsteps` steps after 3 warm-up steps, CUDA events."""
+    import torch
+    from dif_pan_b200 import synth
+    from oracle import sampler_oracle as so, unet_oracle as uo
+
+    torch.backends.cudnn.benchmark = True
+    kw = synth.unet_kwargs("wv3")
+    cl = lambda v: v.to(dev).contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v.to(dev)
+    sd = {k: cl(v) for k, v in synth.make_state_dict(0, **kw).items()}
+    kw2 = dict(kw)
+    kw2.pop("dropout")
+    cfg = uo.UNetCfg(**kw2)
+    sb = {k: v.to(dev) for k, v in so.schedule_buffers(so.make_beta_schedule("cosine", 500)).items()}
+    rows = {}
+    for B in batches:
+        base = synth.make_batch("wv3", min(B, 16), seed=1)["cond"]
+        cond = cl(base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B])
+        g = torch.Generator(device=dev).manual_seed(0)
+        for mode in ("fp32", "bf16_autocast"):
+            x = cl(torch.randn(B, 8, 64, 64, generator=g, device=dev))
+            nz = torch.randn(B, 8, 64, 64, generator=g, device=dev)
+
+            def step(i, x):
+                t = torch.full((B,), 499 - i, dtype=torch.long, device=dev)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode != "fp32"):
+                    out = uo.unet_forward(sd, cfg, x, t, cond, x)
+                return so.ddpm_step(sb, x, t, out.float(), cond[:, :8], nz)
+
+            for i in range(3):
+                x = step(i, x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(nsteps):
+                x = step(3 + i, x)
+            e1.record()
+            torch.cuda.synchronize()
+            rows[f"B{B}_{mode}_ms_per_step"] = e0.elapsed_time(e1) / nsteps
+        del cond
+        torch.cuda.empty_cache()
+    return rows
+
+
+def other_configs_run(dev):
+    """BASELINE configs[0], [2], [3] through the public API (parity cases, not bench lines): ms per sampling, best of 3 after a warm-up."""
+    import torch
+    import dif_pan_b200 as dp
+    from dif_pan_b200 import synth
+
+    def timed(fn, warm=1, reps=3):
+        for _ in range(warm):
+            fn()
+        best = 1e30
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    def net_for(ds):
+        kw = synth.unet_kwargs(ds)
+        net = dp.UNetSR3(**kw)
+        net.load_state_dict(synth.make_state_dict(0, **kw))
+        return net.to(dev).eval()
+
+    out = {}
+    net = net_for("wv3")
+    cond = synth.make_batch("wv3", 1, seed=1)["cond"].to(dev)
+    x_T = torch.randn(1, 8, 64, 64, device=dev)
+    ms = timed(lambda: dp.sample_cond(net, cond, 8, "dpm20", x_T=x_T), warm=2)
+    out["configs[0] WV3 B=1 DPM-Solver++ 2M-20"] = dict(ms_per_sampling=ms, patches_per_s=1e3 / ms, ms_per_denoise_step=ms / 20)
+    del net
+    net = net_for("gf2")
+    d = synth.make_batch("gf2", 1, size=512, seed=2)
+    lms, pan = d["lms_dn"].float().to(dev), d["pan_dn"].float().to(dev)
+    ms = timed(lambda: dp.fuse_scene(net, lms, pan, synth.DATASETS["gf2"].division, sampler="dpm25", patch=64, tile_batch=64))
+    out["configs[2] GF2 512x512 scene -> 64 tiles, DPM-Solver++ 2M-25, stitched"] = dict(ms_per_scene=ms, patches_per_s=64e3 / ms, ms_per_denoise_step=ms / 25)
+    del net
+    net = net_for("cave")
+    cond = synth.make_batch("cave", 8, seed=3)["cond"].repeat(16, 1, 1, 1).contiguous().to(dev)
+    ms = timed(lambda: dp.sample_cond(net, cond, 31, "ddim25"))
+    out["configs[3] CAVE B=128 DDIM-25"] = dict(ms_per_sampling=ms, patches_per_s=128e3 / ms, ms_per_denoise_step=ms / 25)
+    del net, cond
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -156,14 +258,14 @@ def main():
 
     import dif_pan_b200 as dp
     from dif_pan_b200 import synth
-    from dif_pan_b200.sharding import gather_patches
+    from dif_pan_b200.sharding import gather_patches, shard_range
 
     torch.set_grad_enabled(False)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, T = a.batch, a.timesteps
+    T = a.timesteps
     kw = synth.unet_kwargs("wv3")
     net = dp.UNetSR3(**kw)
     net.load_state_dict(synth.make_state_dict(0, **kw))
@@ -171,53 +273,74 @@ def main():
     dif = dp.GaussianDiffusion(net, image_size=64, channels=8, pred_mode="x_start", loss_type="l1", device=dev, clamp_range=(0, 1))
     dif.set_new_noise_schedule(betas=dp.make_beta_schedule("cosine", T), device=dev)
     dif = dif.to(dev)
-    # synthetic conditioning: 16 distinct image-like samples tiled to the batch (rank-dependent seed), pinned on the host
-    base = synth.make_batch("wv3", min(B, 16), seed=1000 + rank)["cond"]
-    cond_host = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous().pin_memory()
-    out_host = torch.empty(B, 8, 64, 64, dtype=torch.float32).pin_memory()
-    cond_dev = cond_host.to(dev)
-    rt = net.runtime(B, 64, 64)
 
-    def one_sampling(e2e: bool, seed: int):
-        dif.seed = seed
-        if e2e:
-            c = cond_host.to(dev, non_blocking=True)  # fresh device tensor -> cond cache rebuilt, like a new batch
-        else:
-            c = cond_dev
-            rt.cond_key = None  # force the cond-cache build: it is part of every sampling
-        s = dif(c, mode="ddpm_sample")
-        sr = dp.fuse_output(s, c)
-        if world > 1:
-            sr = gather_patches(sr, B * world)[rank * B:(rank + 1) * B]  # final NCCL all_gather of the finished patches
-        if e2e:
-            out_host.copy_(sr, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return sr
+    class Workload:
+        """`total` patches over all ranks, this rank's contiguous shard [lo, hi) of them (sharding.shard_range)."""
 
-    def timed(e2e: bool, k: int):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(k):
-            one_sampling(e2e, 100 + i)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            dist.barrier()
-        return float(ms)
+        def __init__(self, total):
+            self.total = total
+            self.lo, self.hi = shard_range(total, rank, world)
+            self.B = B = self.hi - self.lo
+            # synthetic conditioning: 16 distinct image-like samples tiled to the shard (rank-dependent seed), pinned on the host
+            base = synth.make_batch("wv3", min(B, 16), seed=1000 + rank)["cond"]
+            self.cond_host = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous().pin_memory()
+            self.out_host = torch.empty(B, 8, 64, 64, dtype=torch.float32).pin_memory()
+            self.cond_dev = self.cond_host.to(dev)
+            self.rt = net.runtime(B, 64, 64)
 
+        def one_sampling(self, e2e: bool, seed: int):
+            dif.seed = seed
+            dif.noise_shard = (self.lo, self.total)  # in-kernel Philox noise indexed by the GLOBAL patch index: independent per patch on every rank
+            if e2e:
+                c = self.cond_host.to(dev, non_blocking=True)  # fresh device tensor -> cond cache rebuilt, like a new batch
+            else:
+                c = self.cond_dev
+                self.rt.cond_key = None  # force the cond-cache build: it is part of every sampling
+            s = dif(c, mode="ddpm_sample")
+            sr = dp.fuse_output(s, c)
+            if world > 1:
+                sr = gather_patches(sr, self.total)[self.lo:self.hi]  # final NCCL all_gather of the finished patches
+            if e2e:
+                self.out_host.copy_(sr, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            return sr
+
+        def timed(self, e2e: bool, k: int):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(k):
+                self.one_sampling(e2e, 100 + i)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                dist.barrier()
+            return float(ms)
+
+        def measure(self, steps, warmup):
+            for i in range(warmup):
+                self.one_sampling(i % 2 == 1, i)
+            torch.cuda.synchronize()
+            return self.timed(False, steps), self.timed(True, steps)
+
+    strong_head = a.scaling == "strong"
+    if strong_head and a.batch % world:
+        raise SystemExit("--scaling strong needs --batch divisible by the number of GPUs")
+    wl = Workload(a.batch if strong_head else a.batch * world)
+    B = wl.B
+    rt = wl.rt
     for i in range(a.warmup):
-        one_sampling(i % 2 == 1, i)
+        wl.one_sampling(i % 2 == 1, i)
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(False, a.steps)
-    ms_e2e = timed(True, a.steps)
+    ms_dev = wl.timed(False, a.steps)
+    ms_e2e = wl.timed(True, a.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     # roofline of the dominant kernel (conv3x3_halo_tc_kernel: every 3x3 stride-1 conv of the UNet): CUDA events around each
@@ -230,7 +353,7 @@ def main():
         var = rt.sch.fwd.variants()
         ops = rt.sch.fwd.ops
         tot_ms = sum(r[2] for r in rows)
-        names = {0: "conv_igemm_tc_kernel", 1: "conv3x3_fused_tc_kernel", 2: "conv3x3_halo_tc_kernel"}
+        names = {0: "conv_igemm_tc_kernel", 2: "conv3x3_halo_tc_kernel"}
         per = {}
         for i, r in enumerate(rows):
             if var[i] >= 0:
@@ -244,8 +367,15 @@ def main():
             traffic = json.load(open(tp)).get(dom + "_dram_bytes_per_launch")
         ach = d["ref_flops"] / (d["ms"] * 1e-3) / 1e12
         gemm_ms = sum(v["ms"] for v in per.values())
+        step_graph_ms = ms_dev / a.steps / T                      # one denoise step inside the sampling loop (CUDA graph + sampler kernel)
+        in_graph = d["ms"] * step_graph_ms / tot_ms               # the kernel's share of the step applied to the in-graph step time
+        ref_step = 8.378e9 * B
         roof = dict(bound="tensor", kernel=dom, achieved=ach, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
                     frac=ach / pk["bf16_tflops_sustained"], traffic=traffic, peak_source=pk["source"] + ":bf16_tflops_sustained",
+                    timing="eager replay of the step plan, one CUDA-event pair per launch (serialised: no overlap between launches)",
+                    in_graph=dict(avg_launch_ms=in_graph / d["launches"], achieved=d["ref_flops"] / (in_graph * 1e-3) / 1e12,
+                                  frac=d["ref_flops"] / (in_graph * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                                  how="share of the eager per-launch events x measured in-graph step time"),
                     launches_per_denoise_step=d["launches"], avg_launch_ms=d["ms"] / d["launches"], share_of_step=d["ms"] / tot_ms,
                     algorithmic_flops_per_launch=d["ref_flops"] / d["launches"], executed_flops_per_launch=d["executed_flops"] / d["launches"],
                     algorithmic_bytes_per_launch=d["bytes"] / d["launches"],
@@ -253,27 +383,61 @@ def main():
                              frac=d["bytes"] / (d["ms"] * 1e-3) / 1e9 / pk["hbm_gbs"]),
                     all_conv_kernels=dict(share_of_step=gemm_ms / tot_ms, launches=sum(v["launches"] for v in per.values()),
                                           achieved=sum(v["ref_flops"] for v in per.values()) / (gemm_ms * 1e-3) / 1e12),
-                    whole_step=dict(reference_flops=8.378e9 * B, ms_graph=ms_dev / a.steps / T,
-                                    achieved=8.378e9 * B / (ms_dev / a.steps / T * 1e-3) / 1e12,
-                                    frac=8.378e9 * B / (ms_dev / a.steps / T * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]),
-                    unet_step_ms_events=tot_ms)
-    cpu = None
+                    whole_step=dict(reference_flops=ref_step, ms_graph=step_graph_ms, achieved=ref_step / (step_graph_ms * 1e-3) / 1e12,
+                                    frac=ref_step / (step_graph_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]),
+                    unet_step_ms_events=tot_ms, launches_per_unet_forward=len(rows))
+    launches_fwd, launches_cnd = rt.launches_per_step(), len(rt.sch.cnd)
+
+    # BASELINE configs[1] as written: 256 patches in TOTAL, sharded 256 / N per GPU (strong scaling).  At N = 1 it IS the headline run.
+    strong = None
+    if not a.no_extras and not strong_head:
+        if world == 1:
+            strong = dict(patches_total=a.batch, patches_per_gpu=a.batch, value=a.batch * a.steps / (ms_dev * 1e-3), unit=UNIT,
+                          e2e=a.batch * a.steps / (ms_e2e * 1e-3), ms_per_denoise_step=ms_dev / a.steps / T, note="N = 1: identical to the headline run")
+        elif a.batch % world == 0:
+            n1_value = a.batch * a.steps / (ms_dev * 1e-3)   # one GPU sampling 256 patches = this run's per-GPU (weak) figure
+            ws = Workload(a.batch)
+            sd_ms, se_ms = ws.measure(a.steps, a.warmup)
+            if rank == 0:
+                v = a.batch * a.steps / (sd_ms * 1e-3)
+                strong = dict(patches_total=a.batch, patches_per_gpu=ws.B, value=v, unit=UNIT, e2e=a.batch * a.steps / (se_ms * 1e-3),
+                              ms_per_denoise_step=sd_ms / a.steps / T, speedup_vs_n1=v / n1_value, efficiency_vs_n1=v / n1_value / world,
+                              n1_value=n1_value, n1_how="per-GPU throughput of the weak run above (one GPU sampling %d patches)" % a.batch,
+                              launches_per_denoise_step=ws.rt.launches_per_step() + 1)
+    cpu = eager = others = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        r = cpu_reference_run(a.cpu_batch, T, 3, 1)
-        cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
+        r = cpu_reference_run(a.cpu_batch, T, 10, 2)
+        cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"], ms_per_denoise_step=r["ms_per_denoise_step"])
+    if rank == 0 and world == 1 and not a.no_extras:
+        step_ms = ms_dev / a.steps / T
+        try:
+            eager = gpu_eager_run(dev)
+            eager["what"] = ("reference algorithm (oracle port) as eager PyTorch on this GPU: cuDNN / cuBLAS, channels-last, cudnn.benchmark; "
+                             "fp32 (torch default TF32 policy) and torch.autocast(bfloat16); ms per denoise step (UNet forward + DDPM posterior), 20 steps")
+            eager["speedup_vs_eager_bf16_B%d" % a.batch] = eager.get("B%d_bf16_autocast_ms_per_step" % a.batch, float("nan")) / step_ms
+            eager["speedup_vs_eager_fp32_B%d" % a.batch] = eager.get("B%d_fp32_ms_per_step" % a.batch, float("nan")) / step_ms
+        except Exception as e:  # the bench line must survive a failure of the side measurement
+            eager = dict(error=repr(e)[:300])
+        torch.cuda.empty_cache()
+        try:
+            others = other_configs_run(dev)
+        except Exception as e:
+            others = dict(error=repr(e)[:300])
     if rank == 0:
-        total = B * world * a.steps
-        launches = a.steps * (T * (rt.launches_per_step() + 1) + len(rt.sch.cnd) + 2)
+        total = wl.total * a.steps
+        launches = a.steps * (T * (launches_fwd + 1) + launches_cnd + 2)
         line = dict(metric=METRIC, value=total / (ms_dev * 1e-3), unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
-                    ms_per_step=ms_dev / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    ms_per_step=ms_dev / a.steps, higher_is_better=True, scaling=a.scaling, vs_baseline=None, dtype="bf16", data="synthetic",
                     config=dict(workload="BASELINE configs[1]: WV3 64x64x8 patches, batch %d per GPU, full DDPM loop cosine T=%d, clip (0,1), "
-                                         "x_start, self-cond" % (B, T), batch_per_gpu=B, timesteps=T, patches_total=B * world,
+                                         "x_start, self-cond" % (B, T), batch_per_gpu=B, timesteps=T, patches_total=wl.total,
                                 l2_policy="inputs larger than L2 (per-step activation working set ~GBs >> 126 MB)",
-                                noise="in-kernel Philox4x32-10"),
+                                noise="in-kernel Philox4x32-10, counter = (seed, step, global patch element)",
+                                parity_note="Haar DWT oracle is pinned only by the two PyWavelets documentation known answers (pywt absent)"),
                     unet_ms_per_denoise_step=ms_dev / a.steps / T,
-                    e2e=dict(value=total / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=cond_host.numel() * 4, d2h_bytes_per_step=out_host.numel() * 4,
+                    e2e=dict(value=total / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=wl.cond_host.numel() * 4, d2h_bytes_per_step=wl.out_host.numel() * 4,
                              ms_per_step=ms_e2e / a.steps),
-                    gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu)
+                    gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu, strong=strong, gpu_eager_baseline=eager,
+                    other_configs=others)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

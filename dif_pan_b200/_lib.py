@@ -67,6 +67,46 @@ KIND_OF_STRUCT = {
 _lib = None
 
 
+class Stream(int):
+    """A cudaStream_t handle that remembers its device: every launch through this module makes that device current for the
+    call (kernel launches, cudaFuncSetAttribute and graph capture act on the CUDA *current* device, which need not be the device
+    of the tensors when the caller passes device='cuda:N' like the reference does)."""
+
+    def __new__(cls, handle: int, device=None):
+        obj = int.__new__(cls, handle)
+        obj.device = device
+        return obj
+
+
+def stream_of(device) -> "Stream":
+    """Current torch stream of `device` as a device-carrying handle."""
+    import torch
+    device = torch.device(device)
+    return Stream(torch.cuda.current_stream(device).cuda_stream, device)
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NOGUARD = _NoGuard()
+
+
+def guard(stream):
+    """Context manager making the stream's device current (no-op for plain ints and when it already is)."""
+    dev = getattr(stream, "device", None)
+    if dev is None:
+        return _NOGUARD
+    import torch
+    if dev.index is None or torch.cuda.current_device() == dev.index:
+        return _NOGUARD
+    return torch.cuda.device(dev)
+
+
 def load() -> ctypes.CDLL:
     """Load the CUDA library; raise loudly if it has not been built (no fallback path exists)."""
     global _lib
@@ -127,8 +167,10 @@ def launch(struct_name: str, stream: int, kind: str = None, **fields) -> None:
     """Launch one op immediately on the given CUDA stream handle (`kind` only for structs shared by two ops)."""
     st = make(struct_name, **fields)
     k = KINDS[kind or KIND_OF_STRUCT[struct_name]]
-    check(load().ddif_launch(k, ctypes.byref(st), ctypes.c_void_p(stream)), struct_name)
+    with guard(stream):
+        check(load().ddif_launch(k, ctypes.byref(st), ctypes.c_void_p(stream)), struct_name)
 
 
 def launch_kind(kind_name: str, st, stream: int) -> None:
-    check(load().ddif_launch(KINDS[kind_name], ctypes.byref(st), ctypes.c_void_p(stream)), kind_name)
+    with guard(stream):
+        check(load().ddif_launch(KINDS[kind_name], ctypes.byref(st), ctypes.c_void_p(stream)), kind_name)

@@ -1,7 +1,5 @@
 // extern "C" surface of libddif_b200.so: immediate launches, the recorded op list ("plan") that replays one
 // UNet forward per call, CUDA-graph capture of a plan, and per-op event profiling.  See include/ddif_b200.h.
-#include <stdlib.h>
-
 #include <vector>
 
 #include "common.cuh"
@@ -10,8 +8,11 @@
 namespace ddif {
 
 bool ddif_pdl_enabled() {
-  static const bool on = getenv("DDIF_NO_PDL") == nullptr;
-  return on;
+#ifdef DDIF_VAR_NO_PDL  // tuning build (tools/): launches without the programmatic-stream-serialization attribute
+  return false;
+#else
+  return true;
+#endif
 }
 
 union OpParams {
@@ -272,8 +273,7 @@ int ddif_plan_profile(ddif_plan_t* plan, ddif_stream_t stream, float* ms, int* k
 }
 
 int ddif_debug_set_timestamps(void* device_ptr) {
-  const int rc = ddif::conv3_set_debug_ts((long long*)device_ptr);
-  return rc ? rc : ddif::conv3_halo_set_debug_ts((long long*)device_ptr);
+  return ddif::conv3_halo_set_debug_ts((long long*)device_ptr);
 }
 
 int ddif_haar_dwt2_f32(const ddif_haar_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_HAAR_DWT2, p, s); }

@@ -19,8 +19,6 @@
 //
 // Measured floors (profiles/r01_microbench_*.txt): one M128xNxK16 MMA = max(44.8, N/2) cycles, so a 32->32 tile
 // (18 MMAs) needs >= 810 cycles; the TMA halo feed needs 420 (C=32) / 750 (C=64) cycles per tile.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "ddif_internal.h"
 #include "epilogue.cuh"
@@ -34,26 +32,19 @@ static constexpr int kHThreads = kHxfThreads + 64 + 32 * kHEpiWarps + 32;  // + 
 static constexpr int kHW = 10, kHH = 18, kHPx = kHW * kHH;  // halo of an 8 x 16 tile
 static constexpr int kHMaxStages = 8;
 static constexpr int kHMaxStat = 1024;
-// The TMA-store epilogue is compiled in only with -DDDIF_OSTORE_BUILD (tools/ experiments): even disabled at run time its extra
-// live values cost the epilogue registers (spills at the 96-register cap) and 10 % on the GN+conv layers.
-#ifdef DDIF_OSTORE_BUILD
-static constexpr bool kOstoreBuild = true;
-#else
-static constexpr bool kOstoreBuild = false;
-#endif
+// (A TMA-store epilogue -- tile staged in shared memory, stored with cp.async.bulk.tensor -- was built and measured in round 1:
+// correct but slower for N >= 64 and +4 % for N = 32, because the staging traffic competes with the tcgen05 operand fetch for
+// shared-memory bandwidth; removed)
 
 struct alignas(64) HaloKParams {
   CUtensorMap tmA[2];  // activations of K segment 0 / 1 (virtual channel concat: torch.cat((x, skip), 1), sr3_dwt.py:212)
   CUtensorMap tmB[2];  // weights of segment 0 / 1
   CUtensorMap tmR;     // residual tile box (L2 prefetch only)
   CUtensorMap tmRA;    // residual-as-operand mode: halo box of the residual tensor (kslab_r x 10 x 18 x 1), see `nslab_r`
-  CUtensorMap tmO[2];  // output tile boxes for the TMA store: [0] 64-channel slabs (SWIZZLE_128B), [1] 32-channel remainder (SWIZZLE_64B)
   const float* dw_w;   // depthwise mode (see ddif_gemm_t.dw_w): [9][cin] fp32
   int dw_n;            // leading output channels fed by the depthwise result; the rest read the normalised input itself
   int ntap_w;          // weight taps resident per K slab: 9, or 1 in depthwise mode
   uint32_t idesc_q, idesc_r, dw_bytes;  // depthwise mode: instruction descriptors (N = dw_n / bn - dw_n), bytes of one A buffer
-  int ostore;          // 1: epilogue stages the bf16 tile in shared memory and stores it with TMA (full 128-byte lines)
-  uint32_t o_bytes;    // bytes of one staging buffer (128 rows x bn channels); 4 buffers (2 per epilogue group)
   int has_res_map;
   int cin, kslab, nslab, span;
   int nslab0;          // slabs that come from segment 0
@@ -192,11 +183,8 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
   int cur_b = -1, cur_slab = -1, tcount = 0;
   f32x2 a2[4], d2[4];
   for (; it.remaining > 0; it.next()) {
-    if (it.slab >= p.nslab) {  // residual slab (identity-weight K segment): TMA -> MMA untouched, this group only relays the barrier
-      mbar_wait(&a_tma[stage], phase);
-      __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(&a_ready[stage]);
-      if (++stage == nst) { stage = 0; phase ^= 1u; }
+    if (it.slab >= p.nslab) {  // residual slab (identity-weight K segment): TMA -> MMA directly (the MMA warp waits on a_tma itself);
+      if (++stage == nst) { stage = 0; phase ^= 1u; }  // this group only keeps its ring position in step
       continue;
     }
     if (it.b != cur_b || it.slab != cur_slab) {
@@ -272,9 +260,9 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
 // tile) to the tensor pipe's critical path; with two, one warp waits for its next stage / accumulator while the other's
 // MMAs execute.
 template <int KSTEPS>
-__device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_base, uint32_t b_base, uint64_t* a_full, uint64_t* a_empty,
-                                              uint64_t* b_full, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int my_tiles,
-                                              int w, long long* dts) {
+__device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_base, uint32_t b_base, uint64_t* a_tma, uint64_t* a_ready,
+                                              uint64_t* a_empty, uint64_t* b_full, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
+                                              int my_tiles, int w, long long* dts) {
   const uint32_t span = (uint32_t)p.span;
   const uint64_t desc_b0 = make_smem_desc(b_base, 8u * span, p.layout_type);
   const uint32_t stage16 = p.stage_bytes >> 4, b16 = p.b_slot_bytes >> 4;
@@ -282,8 +270,12 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((uint32_t)((tap / 3) * kHW + (tap % 3)) * span) >> 4;
   const uint32_t nst = (uint32_t)p.stages >> 1;  // stages of this warp's ring
-  a_full += (uint32_t)w * nst; a_empty += (uint32_t)w * nst;
+  a_tma += (uint32_t)w * nst; a_empty += (uint32_t)w * nst;
+  if (a_ready) a_ready += (uint32_t)w * nst;  // nullptr without the GroupNorm prologue: the TMA barrier feeds the MMAs directly
   a_base += (uint32_t)w * nst * p.stage_bytes;
+  // a_tma[stage] completes one phase per ring wrap (every slab lands there); a_ready[stage] only when a CONV slab used the stage (residual
+  // slabs bypass the transform warps), so its parity is tracked per stage: bit s of rdy_par
+  uint32_t rdy_par = 0u;
   const uint64_t desc_a0 = make_smem_desc(a_base, (uint32_t)kHW * span, p.layout_type);  // SBO = one halo line (10 rows)
   // residual-as-operand: centre tap (one line + one pixel into the halo) of a stage holding rows of span_r bytes; identity weights
   // sit behind the conv weights
@@ -304,7 +296,12 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
     if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 1);
     uint64_t db = desc_b0;
     for (int slab = 0; slab < p.nslab; ++slab) {
-      mbar_wait(&a_full[stage], phase);
+      if (a_ready) {
+        mbar_wait(&a_ready[stage], (rdy_par >> stage) & 1u);
+        rdy_par ^= 1u << stage;
+      } else {
+        mbar_wait(&a_tma[stage], phase);
+      }
       tc_fence_after();
       if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 2);
       const uint64_t da = desc_a0 + (uint64_t)(stage * stage16);
@@ -319,7 +316,7 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
       if (++stage == nst) { stage = 0; phase ^= 1u; }
     }
     for (int rs = 0; rs < p.nslab_r; ++rs) {  // + residual: centre tap of the residual's halo stage x identity weights
-      mbar_wait(&a_full[stage], phase);
+      mbar_wait(&a_tma[stage], phase);
       tc_fence_after();
       const uint64_t da = desc_r0 + (uint64_t)(stage * stage16);
       const uint64_t dbr = desc_br0 + (uint64_t)((uint32_t)rs * (p.r_slot_bytes >> 4));
@@ -534,7 +531,7 @@ enum : int { kEpiRes = 1, kEpiAct = 2, kEpiStats = 4, kEpiNchw = 8 };
 
 template <int F>
 __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int warp,
-                                                   int lane, int my_tiles, long long* dts, float* s_add, uint8_t* smem_o) {
+                                                   int lane, int my_tiles, long long* dts, float* s_add, double2* s_run) {
   constexpr bool kRes = (F & kEpiRes) != 0, kAct = (F & kEpiAct) != 0, kStats = (F & kEpiStats) != 0, kNchw = (F & kEpiNchw) != 0;
   const int q = warp & 3;
   const int grp = (warp - 10) >> 2;
@@ -556,15 +553,6 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
   const size_t hw = (size_t)out_h * out_w;
   const uint32_t tm_lane0 = tmem_base + ((uint32_t)(q * 32) << 16);
   const bool four = p.nacc == 4;
-  // TMA-store path: per-thread 32-byte stores at a pixel pitch >= 128 B reach ~55 % of the HBM rate of full-line writes
-  // (profiles/r01_microbench_gran_copy.txt), so the tile is staged in shared memory in the swizzled box layout and one
-  // elected thread of the group stores it with cp.async.bulk.tensor (two staging buffers per group).
-  const bool ost = kOstoreBuild && !kNchw && p.ostore != 0;
-  const uint32_t so_base = smem_u32(smem_o) + (uint32_t)(grp * 2) * p.o_bytes;
-  const uint32_t so_row128 = (uint32_t)row * 128u, so_sw128 = (uint32_t)(row & 7);
-  const uint32_t so_row64 = (uint32_t)row * 64u, so_sw64 = (uint32_t)((row >> 1) & 3);
-  const int full_slabs = p.bn >> 6;  // 64-channel slabs; a 32-channel remainder slab follows when bn % 64 == 32
-  const bool issuer = (warp - 10) == grp * 4 && lane == 0;
   // per-warp additive vector (bias, or FiLM row of the tile's sample [+ bias]) in shared memory: with ~200 KB of dynamic
   // smem the L1 is a few KB, so per-tile __ldg of these vectors paid an L2 round trip per 16-channel chunk
   float* addv = s_add + (warp - 10) * 256;
@@ -591,24 +579,40 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
     r = g2 - sb * tpi;
     sy = r / tiles_x; sx = r - sy * tiles_x;
   }
-  // Statistics are reduced per TILE (two warp reductions + two fp64 atomics): the per-tile partials are the same values whatever the
-  // tile -> CTA assignment, so results do not depend on the batch size.  Carrying per-thread sums across a sample's tiles was tried:
-  // plain fp32 running sums are 10 % faster on the 32 -> 32 layers but make the statistics batch-size dependent at the 1e-5 level
-  // (= the bf16 noise level of the network output); compensated or fp64 running sums keep the numerics but their four extra live
-  // registers spill in this 96-register epilogue and cost more than the reduction they save.
+  // Statistics: every thread keeps fp64 running sums (sum, sumsq) of its rows in SHARED memory -- per tile it adds its fp32 tile partial
+  // (<= 256 values) to them, 2 DADD and no cross-lane traffic -- and the warp publishes them (one fp64 shuffle reduction + two fp64
+  // atomics) only when the sample changes or the CTA's range ends: <= 3 times per launch instead of once per tile.  Round 1 reduced per
+  // tile (two fp32 warp reductions + two atomics at the tail of every tile's dependency chain, ~10 % of the 32-channel layers); fp32
+  // running sums in registers were rejected there because they made results depend on the tile -> CTA assignment at the 1e-5
+  // level and fp64 ones spilled at the 96-register cap.  fp64 sums in shared memory have neither problem: the value of a sample's
+  // statistics is independent of how its tiles are split over CTAs to ~1e-15.
   f32x2 s1 = pk2(0.f, 0.f), s2 = pk2(0.f, 0.f);
   int stat_b = -1;
+  double2* run = s_run + (threadIdx.x - 10 * 32);
+  if (kStats) *run = make_double2(0.0, 0.0);
   auto tile_stats = [&]() {
     float l1, h1, l2, h2;
     upk2(s1, l1, h1);
     upk2(s2, l2, h2);
-    const float t1 = warp_sum(l1 + h1), t2 = warp_sum(l2 + h2);
-    if (lane == 0) {
-      atomicAdd(stats + 2 * (size_t)stat_b, (double)t1);
-      atomicAdd(stats + 2 * (size_t)stat_b + 1, (double)t2);
-    }
+    double2 r = *run;
+    r.x += (double)(l1 + h1);
+    r.y += (double)(l2 + h2);
+    *run = r;
     s1 = pk2(0.f, 0.f);
     s2 = pk2(0.f, 0.f);
+  };
+  auto flush_stats = [&]() {
+    double2 r = *run;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      r.x += __shfl_xor_sync(0xffffffffu, r.x, o);
+      r.y += __shfl_xor_sync(0xffffffffu, r.y, o);
+    }
+    if (lane == 0) {
+      atomicAdd(stats + 2 * (size_t)stat_b, r.x);
+      atomicAdd(stats + 2 * (size_t)stat_b + 1, r.y);
+    }
+    *run = make_double2(0.0, 0.0);
   };
   uint32_t it = 0;
   for (int t = grp; t < my_tiles; t += 2, ++it) {
@@ -651,11 +655,9 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
         if (k < nadd) addv[lane + 32 * k] = fa[k];
       __syncwarp();
     }
-    stat_b = b;
-    const uint32_t so = so_base + (it & 1u) * p.o_bytes;
-    if (ost) {  // staging buffer (it & 1) was handed to TMA two tiles ago: wait until that store has read it
-      if (issuer) tma_store_wait_read<1>();
-      named_bar_sync(1 + grp, 128);
+    if (kStats && b != stat_b) {
+      if (stat_b >= 0) flush_stats();
+      stat_b = b;
     }
     auto process = [&](const uint32_t (&acc)[16], const uint32_t (&rs)[8], int cc) {
       const int ng = cc * 16;
@@ -702,25 +704,9 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
           uint32_t w[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) w[j] = f2_to_bf2(v[j]);
-          if (ost) {
-            const int slab = cc >> 2;
-            uint32_t a0s, a1s;
-            if (slab < full_slabs) {
-              const uint32_t u = (uint32_t)(cc & 3) * 2u, sb = so + (uint32_t)slab * 16384u + so_row128;
-              a0s = sb + ((u ^ so_sw128) << 4);
-              a1s = sb + (((u + 1u) ^ so_sw128) << 4);
-            } else {
-              const uint32_t u = (uint32_t)(cc & 1) * 2u, sb = so + (uint32_t)full_slabs * 16384u + so_row64;
-              a0s = sb + ((u ^ so_sw64) << 4);
-              a1s = sb + (((u + 1u) ^ so_sw64) << 4);
-            }
-            h_sts128(a0s, make_uint4(w[0], w[1], w[2], w[3]));
-            h_sts128(a1s, make_uint4(w[4], w[5], w[6], w[7]));
-          } else {
 #ifndef DDIF_VAR_NO_STG
-            stg256(outp + pix * (size_t)out_ld + ng, w);
+          stg256(outp + pix * (size_t)out_ld + ng, w);
 #endif
-          }
         }
       } else {  // ragged last chunk (n_valid % 16 != 0): scalar path
         float ss1 = 0.f, ss2 = 0.f;
@@ -762,16 +748,6 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
       if (two) process(a1, rs1, cc + 1);
 #endif
     }
-    if (ost) {
-      h_fence_proxy_async();
-      named_bar_sync(1 + grp, 128);
-      if (issuer) {
-        const int cx = tx * 8, cy = ty * 16;
-        for (int sl = 0; sl < full_slabs; ++sl) tma_store_4d(&p.tmO[0], smem_o + (so - smem_u32(smem_o)) + (size_t)sl * 16384, n0 + sl * 64, cx, cy, b);
-        if (p.bn & 32) tma_store_4d(&p.tmO[1], smem_o + (so - smem_u32(smem_o)) + (size_t)full_slabs * 16384, n0 + full_slabs * 64, cx, cy, b);
-        tma_store_commit();
-      }
-    }
     if (warp == 10 && lane == 0) h_ts(dts, 2, t, 2);
     if (kStats) tile_stats();
     if (warp == 10 && lane == 0) h_ts(dts, 2, t, 3);
@@ -779,7 +755,7 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
     if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
     if (ty >= tiles_y) { ty -= tiles_y; ++b; }
   }
-  if (ost && issuer) tma_store_wait_all();  // shared memory must outlive the last store's reads
+  if (kStats && stat_b >= 0) flush_stats();
 }
 
 template <int F, bool DW>
@@ -789,8 +765,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   uint8_t* smem_a = smem;
-  uint8_t* smem_o = smem + (size_t)p.stages * p.stage_bytes;  // [4][o_bytes] output staging (1024-byte aligned), only with ostore
-  uint8_t* smem_dw = smem_o + (p.ostore ? 4u * p.o_bytes : 0u);  // [4][dw_bytes] depthwise A buffers (2 per half-pipeline), only in depthwise mode
+  uint8_t* smem_dw = smem + (size_t)p.stages * p.stage_bytes;  // [4][dw_bytes] depthwise A buffers (2 per half-pipeline), only in depthwise mode
   uint8_t* smem_b = smem_dw + (DW ? 4u * p.dw_bytes : 0u);
   uint8_t* smem_id = smem_b + (size_t)(p.ntap_w * p.nslab) * p.b_slot_bytes;  // [nslab_r][bn rows x span_r] identity weights (residual-as-operand)
   float* s_gamma = reinterpret_cast<float*>(smem_id + (size_t)p.nslab_r * p.r_slot_bytes);
@@ -798,7 +773,8 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   float2* s_stat = reinterpret_cast<float2*>(s_beta + p.cin);
   const int n_stat = p.gn_stats ? (p.batch < kHMaxStat ? p.batch : kHMaxStat) : 0;
   float* s_add = reinterpret_cast<float*>(s_stat + ((n_stat + 1) & ~1));  // [8 epilogue warps][256], 16-byte aligned
-  float* s_dw = s_add + kHEpiWarps * 256;                                  // [9][cin] depthwise weights (depthwise mode)
+  double2* s_run = reinterpret_cast<double2*>(s_add + kHEpiWarps * 256);   // [256 epilogue threads] fp64 running (sum, sumsq)
+  float* s_dw = reinterpret_cast<float*>(s_run + 32 * kHEpiWarps);         // [9][cin] depthwise weights (depthwise mode)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_dw + (DW ? ((9 * p.cin + 3) & ~3) : 0));
   uint64_t* a_tma = bars;                       // [stages] TMA landed
   uint64_t* a_ready = bars + kHMaxStages;       // [stages] transformed (count 256)
@@ -819,10 +795,6 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   if (warp == 18 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB[0]);
-    if (p.ostore) {
-      tma_prefetch_desc(&p.tmO[0]);
-      tma_prefetch_desc(&p.tmO[1]);
-    }
     if (p.nslab_r) tma_prefetch_desc(&p.tmRA);
     if (p.nslab0 < p.nslab) {
       tma_prefetch_desc(&p.tmA[1]);
@@ -905,6 +877,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   } else if (warp == 8 || warp == 9) {
     // ===================== MMA issuers (converged warps, elected lane issues) =====================
     uint64_t* a_full = gn ? a_ready : a_tma;
+    uint64_t* a_rdy = gn ? a_ready : nullptr;
     const int w = warp - 8;
     if constexpr (DW) {
       const uint32_t sa = smem_u32(smem_a), sd = smem_u32(smem_dw), sb = smem_u32(smem_b);
@@ -912,9 +885,9 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
       else if (p.kslab == 32) halo_mma_dw_loop<2>(p, sa, sd, sb, a_full, a_empty, dw_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w);
       else halo_mma_dw_loop<1>(p, sa, sd, sb, a_full, a_empty, dw_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w);
     } else
-    if (p.kslab == 64) halo_mma_loop<4>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
-    else if (p.kslab == 32) halo_mma_loop<2>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
-    else halo_mma_loop<1>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
+    if (p.kslab == 64) halo_mma_loop<4>(p, smem_u32(smem_a), smem_u32(smem_b), a_tma, a_rdy, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
+    else if (p.kslab == 32) halo_mma_loop<2>(p, smem_u32(smem_a), smem_u32(smem_b), a_tma, a_rdy, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
+    else halo_mma_loop<1>(p, smem_u32(smem_a), smem_u32(smem_b), a_tma, a_rdy, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
   } else if (warp == 18) {
     // ===================== TMA producer: the halo ring (the resident weights were requested above) =====================
     if (lane == 0) {
@@ -965,7 +938,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
     }
   } else if (warp >= 10 && warp < 18) {
     // ===================== epilogue (warps 10..17): two groups of 4 warps, one TMEM accumulator each =====================
-    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, dts, s_add, smem_o);
+    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, dts, s_add, s_run);
     tc_fence_before();
   }
   __syncthreads();
@@ -991,7 +964,11 @@ typedef void (*HaloKernel)(const HaloKParams);
 // Residual-as-operand (HaloKParams::nslab_r): needs a TMA-addressable residual (16-byte aligned base and pixel pitch).
 // DDIF_NO_RESMMA=1 keeps the epilogue-side residual add (A/B switch for profiling).
 static bool halo_res_mma(const ddif_gemm_t& g) {
-  static const bool off = getenv("DDIF_NO_RESMMA") != nullptr;
+#ifdef DDIF_VAR_NO_RESMMA  // tuning build (tools/): keep the epilogue-side residual add everywhere
+  const bool off = true;
+#else
+  const bool off = false;
+#endif
   // Measured on B200 (layer_bench, B = 256): 32 -> 32 @64^2 66.9 -> 65.8 us, 64 -> 32 @64^2 71.4 -> 67.3 us, but 64 -> 64 @32^2 35.4 -> 38.7 us and
   // 128 -> 64 @32^2 40.9 -> 58.8 us: with N >= 64 the resident weights leave only 2-3 halo stages per ring and the extra residual
   // stage per tile starves the conv slabs.  Enabled for N <= 32 only.
@@ -1027,7 +1004,7 @@ static cudaError_t halo_set_attrs() {
 }
 
 struct HaloGeom {
-  int cin, kslab, nslab, nslab0, span, stages, stage_bytes, b_slot, n_stat, misc, smem, split, bn, ostore, o_bytes, ntap_w, dw_bytes, kslab_r, r_total;
+  int cin, kslab, nslab, nslab0, span, stages, stage_bytes, b_slot, n_stat, misc, smem, split, bn, ntap_w, dw_bytes, kslab_r, r_total;
 };
 
 static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
@@ -1056,26 +1033,20 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
   if (!g.out && !g.out_nchw) return false;
   h.cin = cin;
   h.n_stat = g.gn_stats ? (int)(g.batch < kHMaxStat ? g.batch : kHMaxStat) : 0;
-  h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + (dw ? ((9 * cin + 3) & ~3) * 4 : 0) + (3 * kHMaxStages + 16) * 8 + 64 + 1024;
+  h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + kHEpiWarps * 32 * 16 + (dw ? ((9 * cin + 3) & ~3) * 4 : 0) + (3 * kHMaxStages + 16) * 8 + 64 + 1024;
   h.ntap_w = dw ? 1 : 9;
   // Resident weights of one CTA (9 taps x all K slabs x bn rows) must leave room for two rings of >= 2 halo stages:
   // split N over blockIdx.y (1, 2, 4 CTAs per tile) and, before splitting further, halve the K slab (smaller stages).
-  // The TMA-store epilogue is OFF by default: measured on B200 it is correct but slower for N >= 64 (32->64 @64^2: 57.7 -> 72.4 us,
-  // 64->128 @32^2: 35.1 -> 41.9 us) -- the staging writes + TMA reads add 2 x 16-32 KB of shared-memory traffic per tile to a kernel
-  // whose tcgen05 operand fetch already saturates shared-memory bandwidth -- and only +4 % for N = 32.  Build with -DDDIF_OSTORE_BUILD and set DDIF_OSTORE=1 to enable it.
-  static const bool no_ostore = !kOstoreBuild || getenv("DDIF_OSTORE") == nullptr;
-  for (int pass = 0; pass < 3; ++pass) {  // pass 0: >= 4 stages + TMA-store staging; pass 1: >= 4 stages; pass 2: accept 2
+#ifndef DDIF_VAR_HALO_KSLAB_MAX  // tuning builds (tools/) pass -DDDIF_VAR_HALO_KSLAB_MAX=n
+#define DDIF_VAR_HALO_KSLAB_MAX 64
+#endif
+  for (int pass = 1; pass < 3; ++pass) {  // pass 1: >= 4 stages; pass 2: accept 2
     for (int split = 1; split <= 4; split *= 2) {
       if (g.n_pad % (16 * split) != 0) break;
       if (split > 1 && (g.out_nchw || dw)) break;
       const int bn = (int)g.n_pad / split;
-      // TMA store: bf16 NHWC output, 32-channel granules, no padded channels, 16-byte aligned pixel rows
-      const bool can_ost = !no_ostore && g.out && !g.out_nchw && bn % 32 == 0 && g.n_valid == g.n_pad && g.out_ld % 8 == 0 && g.out_w % 8 == 0;
-      if (pass == 0 && !can_ost) continue;
-      const int o_bytes = pass == 0 ? 128 * bn * 2 : 0;
-      static const int kslab_cap = getenv("DDIF_HALO_KSLAB_MAX") ? atoi(getenv("DDIF_HALO_KSLAB_MAX")) : 64;  // tuning switch (tools/)
       for (int kslab = gcd; kslab >= 16; kslab >>= 1) {
-        if (kslab > kslab_cap && kslab > 16) continue;
+        if (kslab > DDIF_VAR_HALO_KSLAB_MAX && kslab > 16) continue;
         const int span = kslab * 2;
         const int stage_bytes = (kHPx * span + 1023) & ~1023;
         const int b_total = h.ntap_w * cin * bn * 2;  // independent of the slab size
@@ -1086,15 +1057,14 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
           while (bn % kslab_r != 0 || kslab_r > kslab) kslab_r >>= 1;  // bn % 16 == 0, kslab >= 16: terminates at >= 16
         }
         const int r_total = res_mma ? bn * bn * 2 : 0;  // identity weights: (bn / kslab_r) slots of bn rows x kslab_r columns
-        int st = ((227 * 1024 - h.misc - b_total - r_total - 4 * o_bytes - 4 * dw_bytes) / stage_bytes) & ~1;
+        int st = ((227 * 1024 - h.misc - b_total - r_total - 4 * dw_bytes) / stage_bytes) & ~1;
         if (st > kHMaxStages) st = kHMaxStages;
         if (st >= (pass <= 1 ? 4 : 2)) {
           h.kslab = kslab; h.nslab = cin / kslab; h.nslab0 = (int)g.a_c[0] / kslab; h.span = span;
           h.stage_bytes = stage_bytes; h.split = split; h.bn = bn; h.b_slot = bn * span; h.stages = st;
-          h.ostore = pass == 0 ? 1 : 0; h.o_bytes = o_bytes;
           h.dw_bytes = dw_bytes;
           h.kslab_r = kslab_r; h.r_total = r_total;
-          h.smem = st * stage_bytes + 4 * o_bytes + 4 * dw_bytes + b_total + r_total + h.misc;
+          h.smem = st * stage_bytes + 4 * dw_bytes + b_total + r_total + h.misc;
           return true;
         }
       }
@@ -1168,22 +1138,6 @@ int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   if (g.dw_w) {
     p.idesc_q = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.dw_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     p.idesc_r = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((p.bn - p.dw_n) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  }
-  p.ostore = h.ostore;
-  p.o_bytes = (uint32_t)h.o_bytes;
-  if (p.ostore) {
-    for (int k = 0; k < 2; ++k) {
-      const int chans = k == 0 ? 64 : 32;
-      if (k == 0 && p.bn < 64) continue;
-      if (k == 1 && !(p.bn & 32)) continue;
-      cuuint64_t dims[4] = {(cuuint64_t)g.n_valid, (cuuint64_t)g.out_w, (cuuint64_t)g.out_h, (cuuint64_t)g.batch};
-      cuuint64_t strides[3] = {(cuuint64_t)g.out_ld * 2, (cuuint64_t)g.out_w * g.out_ld * 2, (cuuint64_t)g.out_h * g.out_w * g.out_ld * 2};
-      cuuint32_t box[4] = {(cuuint32_t)chans, 8, 16, 1};
-      cuuint32_t es[4] = {1, 1, 1, 1};
-      CUresult r = enc(&p.tmO[k], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, g.out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       k == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) return DDIF_ERR_DRIVER;
-    }
   }
   p.nslab_t = p.nslab;
   p.span_r = p.span; p.layout_r = p.layout_type;  // harmless defaults (descriptors are built even when unused)

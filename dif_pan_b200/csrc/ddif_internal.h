@@ -13,16 +13,12 @@ struct alignas(64) GemmLaunch {
   unsigned char kparams[1536];
   int grid_x, grid_y, smem_bytes;
   int flags;    // variant 2: compile-time epilogue specialisation (kEpi* bits)
-  int variant;  // 0: conv_igemm_tc_kernel (TMA tap boxes), 1: conv3x3_fused_tc_kernel (LDG halo, 3 shifted copies; nearest-x2 loader),
-                // 2: conv3x3_halo_tc_kernel (one TMA halo tile feeds all nine taps; in-place GN+Swish)
+  int variant;  // 0: conv_igemm_tc_kernel (TMA tap boxes), 2: conv3x3_halo_tc_kernel (one TMA halo tile feeds all nine taps; in-place
+                // GN+Swish).  (1 was an LDG-fed 3x3 kernel with the nearest-x2 folded into its loader: slower at every level, removed.)
 };
 
 int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L);
 int gemm_launch(const GemmLaunch& L, cudaStream_t stream);
-bool conv3_applicable(const ddif_gemm_t& g);
-int conv3_prepare(const ddif_gemm_t& g, GemmLaunch& L);
-int conv3_launch(const GemmLaunch& L, cudaStream_t stream);
-int conv3_set_debug_ts(long long* ptr);
 bool conv3_halo_applicable(const ddif_gemm_t& g);
 int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L);
 int conv3_halo_launch(const GemmLaunch& L, cudaStream_t stream);

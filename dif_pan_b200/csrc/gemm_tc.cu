@@ -9,8 +9,6 @@
 // K-major stage; one elected thread issues tcgen05.mma (M128 x N x K16) into a TMEM accumulator; tcgen05.commit
 // frees the stage.  Warp roles: warp0 = TMA producer, warp1 = TMEM alloc + MMA issue, warps2-5 = epilogue
 // (tcgen05.ld -> bias / FiLM / CSM modulation / residual / SiLU / GroupNorm statistics -> bf16 NHWC store).
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "ddif_internal.h"
 #include "epilogue.cuh"
@@ -101,6 +99,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
   uint64_t* tmem_full_bar = bars + 2 * p.stages;       // [4]
   uint64_t* tmem_empty_bar = bars + 2 * p.stages + 4;  // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 8);
+  double2* s_run = reinterpret_cast<double2*>(bars + 2 * p.stages + 10);  // [32 * kEpiWarps] fp64 running statistics of the lean epilogue
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -298,6 +297,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
         nxt_ok = locate(m_tile, nxt_pix, nxt_b);
         fetch(nxt, nxt_pix, nxt_ok);
       }
+      // GroupNorm statistics of the output: per-thread fp64 running sums in shared memory, published (fp64 shuffle reduction + two
+      // atomics per warp) only when the warp's sample changes or the CTA's range ends -- see halo_epilogue_loop (conv3x3_halo.cu).
+      // The per-tile fp32 warp reduction + atomics this replaces were ~30 % of the 32 -> 32 1x1 conv (profiles/r01s5_gemm1x1_ablation_stats.txt).
+      double2* run = s_run + (threadIdx.x - 64);
+      int stat_b = -1;
+      if (kStats) *run = make_double2(0.0, 0.0);
+      auto flush_stats = [&]() {
+        double2 r = *run;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          r.x += __shfl_xor_sync(0xffffffffu, r.x, o);
+          r.y += __shfl_xor_sync(0xffffffffu, r.y, o);
+        }
+        if (lane == 0 && stat_b < p.batch) {
+          atomicAdd(p.stats + 2 * (size_t)stat_b, r.x);
+          atomicAdd(p.stats + 2 * (size_t)stat_b + 1, r.y);
+        }
+        *run = make_double2(0.0, 0.0);
+      };
       for (uint32_t tcount = 0; m_tile < tile_end; m_tile += step, ++tcount) {
         const LeanOperands<F> cur = nxt;
         const bool row_ok = nxt_ok;
@@ -371,21 +389,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
           stg256(p.out + pix * (size_t)p.out_ld + ng, w);
 #endif
         }
-#ifndef DDIF_VAR_G_NO_STATRED
         if (kStats && active) {  // all rows of one warp belong to one sample
-          s1 = warp_sum(s1);
-          s2 = warp_sum(s2);
-          const int img_grp = m_tile / tiles_per_img;
-          const int stat_sample = img_grp * p.tn + (q * 32) / px_per_img;
-          if (lane == 0 && stat_sample < p.batch) {
-            atomicAdd(p.stats + 2 * (size_t)stat_sample, (double)s1);
-            atomicAdd(p.stats + 2 * (size_t)stat_sample + 1, (double)s2);
+          const int stat_sample = (m_tile / tiles_per_img) * p.tn + (q * 32) / px_per_img;
+          if (stat_sample != stat_b) {
+            if (stat_b >= 0) flush_stats();
+            stat_b = stat_sample;
           }
+          double2 r = *run;
+          r.x += (double)s1;
+          r.y += (double)s2;
+          *run = r;
         }
-#else
-        if (kStats && s1 + s2 == 1.2345f) atomicAdd(p.stats, 1.0);
-#endif
       }
+      if (kStats && stat_b >= 0) flush_stats();
       tc_fence_before();
     } else {
     const int grp = p.groups == 4 ? sub : (sub & 1);
@@ -479,13 +495,14 @@ static IgemmKernel igemm_kernel(int f) {
 }
 
 int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
-  const bool wants_fused = g.gn_stats != nullptr || g.a_up != 0;
+  if (g.a_up != 0) return DDIF_ERR_SHAPE;  // reserved: nearest x2 runs as its own kernel (DDIF_OP_UPSAMPLE2X) in front of the conv
   if (!g.force_tma && conv3_halo_applicable(g)) {
-    static const bool no_halo = getenv("DDIF_NO_HALO") != nullptr;  // A/B switch for profiling only
-    if (!no_halo || g.nseg == 2) return conv3_halo_prepare(g, L);
+#ifdef DDIF_VAR_NO_HALO  // tuning build (tools/): plain 3x3 convs through the generic TMA kernel
+    if (g.nseg == 2 || g.gn_stats || g.dw_w)
+#endif
+      return conv3_halo_prepare(g, L);
   }
-  if (wants_fused && !conv3_applicable(g)) return DDIF_ERR_SHAPE;  // the prologues exist only in the 3x3 kernels
-  if (wants_fused || (conv3_applicable(g) && !g.force_tma)) return conv3_prepare(g, L);
+  if (g.gn_stats != nullptr || g.dw_w != nullptr) return DDIF_ERR_SHAPE;  // the fused prologues exist only in the halo kernel
   L.variant = 0;
   GemmKParams& p = *reinterpret_cast<GemmKParams*>(L.kparams);
   static_assert(sizeof(GemmKParams) <= sizeof(L.kparams), "kparams buffer too small");
@@ -564,13 +581,15 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
     stages = budget / (a_stage + b_slot);
     p.b_slots = stages;
   }
-  static const int max_stages = getenv("DDIF_GEMM_MAX_STAGES") ? atoi(getenv("DDIF_GEMM_MAX_STAGES")) : 8;  // tuning switch (tools/)
-  if (stages > max_stages) stages = max_stages;
+#ifndef DDIF_VAR_GEMM_MAX_STAGES  // tuning builds (tools/) pass -DDDIF_VAR_GEMM_MAX_STAGES=n
+#define DDIF_VAR_GEMM_MAX_STAGES 8
+#endif
+  if (stages > DDIF_VAR_GEMM_MAX_STAGES) stages = DDIF_VAR_GEMM_MAX_STAGES;
   if (stages < 2) return DDIF_ERR_SHAPE;
   if (!p.resident_b) p.b_slots = stages;
   p.stages = stages;
   p.num_m_tiles = p.tiles_x * p.tiles_y * (int)ceil_div(B, tn);
-  L.smem_bytes = stages * a_stage + p.b_slots * b_slot + (2 * stages + 10) * 8 + 1024;
+  L.smem_bytes = stages * a_stage + p.b_slots * b_slot + (2 * stages + 10) * 8 + 32 * kEpiWarps * 16 + 1024;
   const int sms = ddif_sm_count();
   L.grid_y = (int)(g.n_pad / bn);
   const int gx = (sms + L.grid_y - 1) / L.grid_y;  // persistent: ~one CTA per SM in total
@@ -620,7 +639,6 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
 }
 
 int gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
-  if (L.variant == 1) return conv3_launch(L, stream);
   if (L.variant == 2) return conv3_halo_launch(L, stream);
   const GemmKParams& p = *reinterpret_cast<const GemmKParams*>(L.kparams);
   IgemmKernel k = igemm_kernel(p.lean);

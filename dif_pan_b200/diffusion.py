@@ -52,7 +52,7 @@ def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2,
 
 
 def _stream(dev) -> int:
-    return torch.cuda.current_stream(dev).cuda_stream
+    return _lib.stream_of(dev)
 
 
 class GaussianDiffusion(nn.Module):
@@ -74,6 +74,10 @@ class GaussianDiffusion(nn.Module):
         self.pred_var = self.model.pred_var
         assert self.pred_var == False, "not supported yet"  # noqa: E712  (diffusion_ddpm_pan.py:184)
         self.seed = 0
+        # In-kernel noise is a function of (seed, step, GLOBAL element index): a rank that samples patches [lo, lo + b) of a batch of
+        # `total` sets noise_shard = (lo, total) (sharding.sample_sharded does) and draws exactly the numbers the single-process run
+        # draws for those patches, so Philox results do not depend on the number of ranks.  None = (0, local batch).
+        self.noise_shard = None
         self._coef = {}
 
     # -- schedule (diffusion_ddpm_pan.py:199-276) --------------------------------------------------------------
@@ -144,11 +148,13 @@ class GaussianDiffusion(nn.Module):
         """diffusion_ddpm_pan.py:668-681."""
         if noise is None:
             noise = device_randn(x_start.shape, x_start.device, self.seed, 1 << 40)
-        out = torch.empty_like(x_start)
+        # contiguous copies are bound to locals: a temporary freed before the launch could hand its block to the next one
+        x0c, nzc, tc = x_start.contiguous(), noise.contiguous(), t.to(torch.int64).contiguous()
+        out = torch.empty_like(x0c)
         B = x_start.shape[0]
-        _lib.launch("ddif_q_sample_t", _stream(x_start.device), x0=x_start.contiguous().data_ptr(), noise=noise.contiguous().data_ptr(),
+        _lib.launch("ddif_q_sample_t", _stream(x_start.device), x0=x0c.data_ptr(), noise=nzc.data_ptr(),
                     out=out.data_ptr(), sa=self.sqrt_alphas_cumprod.data_ptr(), s1ma=self.sqrt_one_minus_alphas_cumprod.data_ptr(),
-                    t=t.to(torch.int64).contiguous().data_ptr(), batch=B, chw=x_start[0].numel())
+                    t=tc.data_ptr(), batch=B, chw=x_start[0].numel())
         return out
 
     # -- loops -------------------------------------------------------------------------------------------------
@@ -160,6 +166,12 @@ class GaussianDiffusion(nn.Module):
         b, (h, w) = cond.shape[0], cond.shape[-2:]
         shape = (b, self.channels, h, w)
         sample_inter = 1 | (self.num_timesteps // 10)
+        lo, total = self.noise_shard if self.noise_shard is not None else (0, b)
+        per = self.channels * h * w
+        if lo < 0 or lo + b > total:
+            raise ValueError(f"noise_shard {self.noise_shard} does not contain a local batch of {b}")
+        # Philox counter of local float4 i at step k: k * (total elements) + (lo * per) / 4 + i  (csrc/sampler.cu: counter = offset + i)
+        off = lambda k: k * total * per + (lo * per) // 4
         if self._fast(cond):
             rt = self.model.runtime(b, h, w)
             rt.set_cond(cond)
@@ -167,18 +179,18 @@ class GaussianDiffusion(nn.Module):
             if noise is not None:
                 x.copy_(noise[0])
             else:
-                device_randn_(x, self.seed, 0)
+                device_randn_(x, self.seed, off(0))
             tbuf.fill_(float(n_steps - 1))
             ret = [x.clone()] if continous else None
             for k, i in enumerate(reversed(range(n_steps))):
                 rt.step()
                 self._step(kind, x, out, rt.cond_buf, i, noise[1 + k] if noise is not None else None, time_out=tbuf, eta=eta,
-                           clip=clip, offset=(k + 1) * x.numel())
+                           clip=clip, offset=off(k + 1))
                 if continous and i % sample_inter == 0:
                     ret.append(x.clone())
             return torch.cat(ret, 0) if continous else x.clone()
         # generic denoiser (any nn.Module with the reference call signature)
-        img = noise[0].clone() if noise is not None else device_randn(shape, dev, self.seed, 0)
+        img = noise[0].clone() if noise is not None else device_randn(shape, dev, self.seed, off(0))
         ret = [img.clone()] if continous else None
         x_start = None
         for k, i in enumerate(reversed(range(n_steps))):
@@ -186,7 +198,7 @@ class GaussianDiffusion(nn.Module):
             sc = x_start if (self.self_condition and kind == "ddpm") else None
             out = self.model(img, t, cond, sc).contiguous()
             self._step(kind, img, out, cond.contiguous(), i, noise[1 + k] if noise is not None else None, eta=eta, clip=clip,
-                       offset=(k + 1) * img.numel())
+                       offset=off(k + 1))
             x_start = img
             if continous and i % sample_inter == 0:
                 ret.append(img.clone())
@@ -246,9 +258,10 @@ class GaussianDiffusion(nn.Module):
     def _axpby(self, ca: torch.Tensor, x: torch.Tensor, cb: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         """out[b] = ca[b]*x[b] + cb[b]*y[b] with per-sample fp32 coefficients gathered from the schedule buffers
         (`extract`, diffusion_ddpm_pan.py:73-76): predict_start_from_noise / predict_v / predict_start_from_v (:284-312)."""
-        out = torch.empty_like(x)
-        _lib.launch("ddif_axpby_t", _stream(x.device), x=x.contiguous().data_ptr(), y=y.contiguous().data_ptr(),
-                    ca=ca.to(torch.float32).contiguous().data_ptr(), cb=cb.to(torch.float32).contiguous().data_ptr(), out=out.data_ptr(),
+        xc, yc = x.contiguous(), y.contiguous()
+        cac, cbc = ca.to(torch.float32).contiguous(), cb.to(torch.float32).contiguous()
+        out = torch.empty_like(xc)
+        _lib.launch("ddif_axpby_t", _stream(x.device), x=xc.data_ptr(), y=yc.data_ptr(), ca=cac.data_ptr(), cb=cbc.data_ptr(), out=out.data_ptr(),
                     batch=x.shape[0], chw=x[0].numel())
         return out
 
@@ -334,8 +347,9 @@ def device_randn(shape, device, seed: int, offset: int) -> torch.Tensor:
 
 def fuse_output(sample: torch.Tensor, cond: torch.Tensor, lo=0.0, hi=1.0) -> torch.Tensor:
     """sr = clip(sample + lms, 0, 1) (diffusion_engine.py:446-447); lms = first C channels of cond."""
-    out = torch.empty_like(sample)
+    sc, cc = sample.contiguous(), cond.contiguous()
+    out = torch.empty_like(sc)
     B, C = sample.shape[:2]
-    _lib.launch("ddif_axpby_clip_t", _stream(sample.device), x=sample.contiguous().data_ptr(), cond=cond.contiguous().data_ptr(),
+    _lib.launch("ddif_axpby_clip_t", _stream(sample.device), x=sc.data_ptr(), cond=cc.data_ptr(),
                 out=out.data_ptr(), batch=B, c=C, hw=sample.shape[2] * sample.shape[3], cond_c=cond.shape[1], lo=float(lo), hi=float(hi))
     return out

@@ -299,7 +299,7 @@ class DPM_Solver:
             raise RuntimeError("dif_pan_b200 sampler kernels run on CUDA only (no CPU fallback)")
         ns, wm = self.noise_schedule, self.wrapped
         B, dev = x.shape[0], x.device
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _lib.stream_of(dev)
         fast = isinstance(wm.model, UNetSR3) and wm.condition is not None and not wm.model_kwargs
         predict = 0 if self.algorithm_type == "dpmsolver++" else 1
         mt = MODEL_TYPES[wm.model_type]
@@ -381,7 +381,7 @@ class DPM_Solver:
         else:
             out = wm.raw(xb, t.to(dev).expand(B)).contiguous()
         x0 = torch.empty_like(xb)
-        _lib.launch("ddif_dpm_single_t", torch.cuda.current_stream(dev).cuda_stream, x_base=None, x_eval=xb.data_ptr(), model_out=out.data_ptr(),
+        _lib.launch("ddif_dpm_single_t", _lib.stream_of(dev), x_base=None, x_eval=xb.data_ptr(), model_out=out.data_ptr(),
                     m_cur=x0.data_ptr(), m_a=None, x_out=None, time_out=None, n=xb.numel(), batch=B, model_type=MODEL_TYPES[wm.model_type],
                     predict=0, mode=2, alpha_e=float(ns.marginal_alpha(t)), sigma_e=float(ns.marginal_std(t)), c0=0.0, c1=0.0, c2=0.0,
                     t_next_in=0.0)
@@ -398,7 +398,7 @@ class DPM_Solver:
             orders = [order] * K
             outer = self.get_time_steps(skip_type, t_T, t_0, K)
         B, dev = x.shape[0], x.device
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _lib.stream_of(dev)
         fast = isinstance(wm.model, UNetSR3) and wm.condition is not None and not wm.model_kwargs
         predict = 0 if self.algorithm_type == "dpmsolver++" else 1
         with torch.no_grad():
@@ -476,7 +476,7 @@ class DPM_Solver:
         assert ts.shape[0] - 1 == steps
         B = x.shape[0]
         dev = x.device
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _lib.stream_of(dev)
         fast = isinstance(wm.model, UNetSR3) and wm.condition is not None and not wm.model_kwargs
         with torch.no_grad():
             if fast:

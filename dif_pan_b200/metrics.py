@@ -26,7 +26,7 @@ def image_sums(gt: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     gt, out = gt.to(torch.float32).contiguous(), out.to(torch.float32).contiguous()
     B, C, H, W = gt.shape
     sums = torch.zeros(B, 2 + 6 * C, dtype=torch.float64, device=gt.device)
-    _lib.launch("ddif_metrics_t", torch.cuda.current_stream(gt.device).cuda_stream, gt=gt.data_ptr(), out=out.data_ptr(),
+    _lib.launch("ddif_metrics_t", _lib.stream_of(gt.device), gt=gt.data_ptr(), out=out.data_ptr(),
                 sums=sums.data_ptr(), batch=B, c=C, h=H, w=W)
     return sums
 

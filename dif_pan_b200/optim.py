@@ -19,8 +19,13 @@ _CHUNK = 65536
 class _TensorList:
     """Device-side table for a fixed list of up-to-4-tensor groups (all fp32, contiguous, same numel within a group)."""
 
-    def __init__(self, groups: Sequence[Sequence[Optional[torch.Tensor]]]):
+    def __init__(self, groups: Sequence[Sequence[Optional[torch.Tensor]]], written: Optional[Sequence[torch.Tensor]] = None):
+        """`written`: the tensors (normally nn.Parameters) whose storage the p0 column aliases.  The kernels write through raw device
+        pointers, which autograd's version counters cannot see; `run` bumps the counters of these tensors after every op that
+        writes p0, so that caches keyed on (data_ptr, _version) -- UNetSR3's packed bf16 weights and its captured CUDA graph --
+        notice the update (an EMA / AdamW step followed by sampling is the reference's validation flow)."""
         groups = [list(g) + [None] * (4 - len(g)) for g in groups]
+        self.written = list(written) if written is not None else []
         if not groups:
             raise ValueError("empty tensor list")
         dev = groups[0][0].device
@@ -43,17 +48,20 @@ class _TensorList:
         self.key = tuple(tuple(p) for p in ptrs)
 
     def run(self, op: int, out: Optional[torch.Tensor] = None, **s) -> None:
-        _lib.launch("ddif_multi_tensor_t", torch.cuda.current_stream(self.dev).cuda_stream, ptrs=self.ptrs.data_ptr(), sizes=self.sizes.data_ptr(),
+        _lib.launch("ddif_multi_tensor_t", _lib.stream_of(self.dev), ptrs=self.ptrs.data_ptr(), sizes=self.sizes.data_ptr(),
                     chunks=self.chunks.data_ptr(), out=out.data_ptr() if out is not None else None, nchunks=self.chunks.shape[0], chunk=_CHUNK,
                     op=op, **{k: float(v) for k, v in s.items()})
+        if op != 2:  # every op but SUMSQ writes p0
+            if self.written:
+                torch._C._increment_version(self.written)
 
 
-def _table(cache: dict, groups) -> _TensorList:
+def _table(cache: dict, groups, written=None) -> _TensorList:
     """Rebuild the device table only when a tensor of the list moved (parameters / optimizer state normally never do)."""
     key = tuple(tuple([0 if t is None else t.data_ptr() for t in g] + [0] * (4 - len(g))) for g in groups)
     tl = cache.get("tl")
     if tl is None or tl.key != key:
-        tl = _TensorList(groups)
+        tl = _TensorList(groups, written)
         cache["tl"] = tl
     return tl
 
@@ -69,8 +77,9 @@ class EmaUpdater:
     @torch.no_grad()
     def update(self, iteration):
         self.iteration = iteration
-        groups = [(pe.data, p.data) for p, pe in zip(self.model.model.parameters(), self.ema_model.model.parameters())]
-        tl = _table(self._cache, groups)
+        pairs = list(zip(self.model.model.parameters(), self.ema_model.model.parameters()))
+        groups = [(pe.data, p.data) for p, pe in pairs]
+        tl = _table(self._cache, groups, written=[pe for _, pe in pairs])
         if iteration > self.start_iter:
             tl.run(0, s0=self.decay, s1=1 - self.decay)   # p_ema = p_ema * decay + p * (1 - decay)
         else:
@@ -110,32 +119,37 @@ def grad_clip(params: Iterable[torch.nn.Parameter], mode: str = "value", value: 
     return total
 
 
-class FusedAdamW:
-    """`torch.optim.AdamW(params, lr, betas, eps, weight_decay)` semantics (no amsgrad / maximize), one launch per step."""
+class FusedAdamW(torch.optim.Optimizer):
+    """`torch.optim.AdamW(params, lr, betas, eps, weight_decay)` semantics (no amsgrad / maximize), ONE launch per parameter group and
+    step.  A real `torch.optim.Optimizer`: `param_groups` (read on every step, so `MultiStepLR` and the schedulers of
+    /root/reference/utils/lr_scheduler.py attach unchanged, diffusion_engine.py:207-210,241), `state_dict()` / `load_state_dict()` with
+    AdamW's own state layout (`step`, `exp_avg`, `exp_avg_sq` per parameter), so optimizer checkpoints round-trip with the reference's."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
-        self.params: List[torch.nn.Parameter] = [p for p in params]
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.step_count = 0
-        self.exp_avg = [torch.zeros_like(p.data) for p in self.params]
-        self.exp_avg_sq = [torch.zeros_like(p.data) for p in self.params]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._cache: dict = {}
 
-    def zero_grad(self, set_to_none: bool = False):
-        for p in self.params:
-            if p.grad is not None:
-                if set_to_none:
-                    p.grad = None
-                else:
-                    p.grad.zero_()
-
     @torch.no_grad()
-    def step(self):
-        idx = [i for i, p in enumerate(self.params) if p.grad is not None]
-        if not idx:
-            return
-        self.step_count += 1
-        groups = [(self.params[i].data, self.params[i].grad, self.exp_avg[i], self.exp_avg_sq[i]) for i in idx]
-        tl = _table(self._cache, groups)
-        b1, b2 = self.betas
-        tl.run(5, s0=self.lr, s1=b1, s2=b2, s3=self.eps, s4=self.weight_decay, s5=1 - b1 ** self.step_count, s6=1 - b2 ** self.step_count)
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            buckets = {}  # parameters of a group normally share one step count -> one launch; stragglers get their own
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p.data, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p.data, memory_format=torch.contiguous_format)
+                st["step"] += 1
+                buckets.setdefault(int(st["step"]), []).append(p)
+            b1, b2 = group["betas"]
+            for k, ps in buckets.items():
+                groups = [(p.data, p.grad, self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"]) for p in ps]
+                tl = _table(self._cache.setdefault((gi, len(ps)), {}), groups, written=ps)
+                tl.run(5, s0=group["lr"], s1=b1, s2=b2, s3=group["eps"], s4=group["weight_decay"], s5=1 - b1 ** k, s6=1 - b2 ** k)
+        return loss

@@ -124,9 +124,14 @@ class PlanBuilder:
             return [self._resolve(e, base) for e in v]
         return v
 
-    def finalize(self, base_ptr: int) -> None:
-        """Record all ops into a C plan (GEMM tensor maps are encoded here; needs the CUDA driver)."""
+    def finalize(self, base_ptr: int, device=None) -> None:
+        """Record all ops into a C plan (GEMM tensor maps are encoded here; needs the CUDA driver).  `device`: the plan's device
+        (made current while recording: tensor maps and kernel attributes belong to the current device)."""
         lib = _lib.load()
+        with _lib.guard(_lib.Stream(0, device)):
+            self._finalize(lib, base_ptr)
+
+    def _finalize(self, lib, base_ptr: int) -> None:
         if self.arena_bytes == 0 and self.bufs:
             self.layout()
         self.handle = ctypes.c_void_p(lib.ddif_plan_create())
@@ -143,20 +148,24 @@ class PlanBuilder:
 
     # -- execution ----------------------------------------------------------------------------------------
     def run(self, stream: int, first: int = 0, last: int = -1) -> None:
-        _lib.check(_lib.load().ddif_plan_run(self.handle, first, last, ctypes.c_void_p(stream)), "ddif_plan_run")
+        with _lib.guard(stream):
+            _lib.check(_lib.load().ddif_plan_run(self.handle, first, last, ctypes.c_void_p(stream)), "ddif_plan_run")
 
     def graph_build(self, stream: int) -> None:
-        _lib.check(_lib.load().ddif_plan_graph_build(self.handle, ctypes.c_void_p(stream)), "ddif_plan_graph_build")
+        with _lib.guard(stream):
+            _lib.check(_lib.load().ddif_plan_graph_build(self.handle, ctypes.c_void_p(stream)), "ddif_plan_graph_build")
 
     def graph_launch(self, stream: int) -> None:
-        _lib.check(_lib.load().ddif_plan_graph_launch(self.handle, ctypes.c_void_p(stream)), "ddif_plan_graph_launch")
+        with _lib.guard(stream):
+            _lib.check(_lib.load().ddif_plan_graph_launch(self.handle, ctypes.c_void_p(stream)), "ddif_plan_graph_launch")
 
     def profile(self, stream: int) -> List[Tuple[str, str, float, float, float]]:
         """[(label, struct, ms, flops, bytes)] per op, timed with CUDA events around each launch."""
         n = len(self.ops)
         ms = (ctypes.c_float * n)()
         kinds = (ctypes.c_int * n)()
-        _lib.check(_lib.load().ddif_plan_profile(self.handle, ctypes.c_void_p(stream), ms, kinds, n), "ddif_plan_profile")
+        with _lib.guard(stream):
+            _lib.check(_lib.load().ddif_plan_profile(self.handle, ctypes.c_void_p(stream), ms, kinds, n), "ddif_plan_profile")
         return [(op.label, op.struct, float(ms[i]), op.flops, op.bytes) for i, op in enumerate(self.ops)]
 
     def variants(self) -> List[int]:

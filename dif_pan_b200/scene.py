@@ -41,7 +41,7 @@ def tile_scene(x: torch.Tensor, patch: int = 64, overlap: int = 0) -> torch.Tens
     stride = patch - overlap
     ny, nx = _grid(H, patch, stride), _grid(W, patch, stride)
     tiles = torch.empty(B * ny * nx, C, patch, patch, dtype=torch.float32, device=x.device)
-    _lib.launch("ddif_tile_t", torch.cuda.current_stream(x.device).cuda_stream, scene=x.data_ptr(), tiles=tiles.data_ptr(), batch=B, c=C,
+    _lib.launch("ddif_tile_t", _lib.stream_of(x.device), scene=x.data_ptr(), tiles=tiles.data_ptr(), batch=B, c=C,
                 h=H, w=W, ph=patch, pw=patch, sy=stride, sx=stride, ny=ny, nx=nx, dir=0)
     return tiles
 
@@ -58,7 +58,7 @@ def stitch_tiles(tiles: torch.Tensor, scene_hw: Tuple[int, int], overlap: int = 
         raise ValueError(f"{n} tiles are not a whole number of {ny}x{nx} scenes")
     B = n // (ny * nx)
     scene = torch.empty(B, C, H, W, dtype=torch.float32, device=tiles.device)
-    _lib.launch("ddif_tile_t", torch.cuda.current_stream(tiles.device).cuda_stream, scene=scene.data_ptr(), tiles=tiles.data_ptr(), batch=B,
+    _lib.launch("ddif_tile_t", _lib.stream_of(tiles.device), scene=scene.data_ptr(), tiles=tiles.data_ptr(), batch=B,
                 c=C, h=H, w=W, ph=ph, pw=pw, sy=ph - overlap, sx=pw - overlap, ny=ny, nx=nx, dir=1)
     return scene
 

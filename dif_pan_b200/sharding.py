@@ -39,10 +39,12 @@ def gather_patches(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
 
 
 def sample_sharded(sample_fn: Callable[..., torch.Tensor], cond: torch.Tensor, noise: Optional[Sequence[torch.Tensor]] = None,
-                   group=None) -> torch.Tensor:
+                   group=None, diffusion=None) -> torch.Tensor:
     """Run `sample_fn(cond_shard, noise=noise_shards)` on this rank's patches and gather the full batch.
-    `noise` (if given) is the GLOBAL list [x_T, n_1, ...]; each rank uses its batch slice, so results do not depend
-    on the number of ranks."""
+    `noise` (if given) is the GLOBAL list [x_T, n_1, ...]; each rank uses its batch slice.  Without injected noise pass the
+    `GaussianDiffusion` that `sample_fn` drives as `diffusion`: its in-kernel Philox generator is then indexed by the GLOBAL
+    patch index (`noise_shard = (lo, total)`), so either way results do not depend on the number of ranks -- every rank
+    using the same (seed, offset 0) stream would make patch i of every shard share its noise."""
     if dist.is_available() and dist.is_initialized():
         world, rank = dist.get_world_size(group), dist.get_rank(group)
     else:
@@ -52,5 +54,11 @@ def sample_sharded(sample_fn: Callable[..., torch.Tensor], cond: torch.Tensor, n
     nz = [shard_batch(n, rank, world).contiguous() for n in noise] if noise is not None else None
     if c.shape[0] == 0:
         raise ValueError("more ranks than patches: give every rank at least one patch")
-    local = sample_fn(c, noise=nz) if nz is not None else sample_fn(c)
+    if diffusion is not None:
+        diffusion.noise_shard = (shard_range(total, rank, world)[0], total)
+    try:
+        local = sample_fn(c, noise=nz) if nz is not None else sample_fn(c)
+    finally:
+        if diffusion is not None:
+            diffusion.noise_shard = None
     return gather_patches(local, total, group)

@@ -17,7 +17,6 @@ Training-mode forward/backward is not implemented in this round (inference path 
 from __future__ import annotations
 
 import math
-import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -188,6 +187,8 @@ class UNetSR3(nn.Module):
             raise RuntimeError("dif_pan_b200.UNetSR3 runs on CUDA only (no CPU fallback): call .cuda() first")
         self._packed = pack_state_dict(sd, self)
         self._packed_key = key
+        if self._rt is not None:  # the recorded plans / captured graph point at the old packs
+            self._rt.close()
         self._rt = None
         return self._packed
 
@@ -355,8 +356,11 @@ class Act:
 class Schedule:
     """Builds the cond-cache plan and the per-step forward plan of a UNetSR3 for a fixed (B, H, W)."""
 
-    def __init__(self, net: UNetSR3, addr: Dict[str, int], B: int, H: int, W: int, io: Dict[str, int]):
-        """addr: packed-weight name -> device address; io: x, sc, t, out, cond addresses (fixed buffers)."""
+    def __init__(self, net: UNetSR3, addr: Dict[str, int], B: int, H: int, W: int, io: Dict[str, int], *, use_qconv: bool = True,
+                 use_dwq: bool = True, use_attn_block: bool = True):
+        """addr: packed-weight name -> device address; io: x, sc, t, out, cond addresses (fixed buffers).
+        use_qconv / use_dwq / use_attn_block: A/B switches for tools/ (composed q conv, in-kernel depthwise q path, fused attention block);
+        the product always builds the schedule with all three on."""
         if H % 8 or W % 8 or min(H, W) < 8 * 2 ** (self._levels(net) - 1):
             raise ValueError(f"UNetSR3 needs H, W multiples of 8 and >= {8 * 2 ** (self._levels(net) - 1)}, got {H}x{W}")
         self.net, self.addr, self.B, self.H, self.W, self.io = net, addr, B, H, W, io
@@ -371,12 +375,7 @@ class Schedule:
         self.weff: Dict[str, Buf] = {}
         self.film_offsets = None
         self.first_body_op = 0
-        self.use_qconv = os.environ.get("DDIF_NO_QCONV") is None  # A/B switch for profiling only
-        self.use_dwq = os.environ.get("DDIF_NO_DWQ") is None      # A/B switch: in-kernel depthwise q path vs composed dense 3x3
-        self.use_attn_block = os.environ.get("DDIF_NO_ATTN_BLOCK") is None  # A/B switch: fused attention block vs 4 launches
-        # nearest x2 inside the conv's loader (csrc/conv3x3_tc.cu, the LDG-fed kernel) vs upsample kernel + halo conv: the two launches are
-        # faster at every level (B = 256: 45 -> 41, 59 -> 45, 176 -> 127 us), so the fused loader is opt-in (DDIF_UPFUSE=1)
-        self.use_upfuse = os.environ.get("DDIF_UPFUSE") is not None
+        self.use_qconv, self.use_dwq, self.use_attn_block = use_qconv, use_dwq, use_attn_block
 
     @staticmethod
     def _levels(net) -> int:
@@ -398,8 +397,8 @@ class Schedule:
     def _gemm(self, pb, label, srcs, weights, n_valid, out: Optional[Act], *, taps, stride=1, bias=None, film=None,
               film_ld=0, mod=None, residual: Optional[Act] = None, act=0, out_nchw=None, per_sample=(0, 0), w_s=None, out_hw=None,
               gn=None, a_up=0, w_k=None, ref_flops=-1.0, residual_off=0, dw=None):
-        """gn = (gamma_addr, beta_addr, act): fuse GroupNorm(+Swish) of the (single) source into the conv's loader, using the
-        source's own statistics; a_up = 1: read the source through a nearest x2 up-sampling."""
+        """gn = (gamma_addr, beta_addr, act): fuse GroupNorm(+Swish) of the source(s) into the conv's loader, using the
+        sources' own statistics; a_up is reserved (must be 0)."""
         a0 = srcs[0]
         oh, ow = out_hw if out_hw else ((a0.H << a_up) // stride, (a0.W << a_up) // stride)
         n_pad = _ceil(n_valid, 16)
@@ -602,13 +601,12 @@ class Schedule:
             p = f"ups.{i}"
             if kind == "up":
                 y = self._act(pb, p, B, x.H * 2, x.W * 2, x.C, stats=True)
-                if x.W * 2 >= 16 and x.C <= 256 and self.use_upfuse:  # nearest x2 folded into the conv's loader
-                    self._gemm(pb, p + ".up+conv", [x], [A[p + ".w"]], x.C, y, taps=[9], bias=A[p + ".b"], a_up=1)
-                else:
-                    up = self._act(pb, p + ".up", B, x.H * 2, x.W * 2, x.C)
-                    pb.add("ddif_upsample2x_t", label=p + ".nearest", traffic=B * x.H * x.W * x.C * 10, **{"in": x.buf}, out=up.buf, batch=B,
-                           h=x.H, w=x.W, c=x.C)
-                    self._gemm(pb, p + ".conv", [up], [A[p + ".w"]], x.C, y, taps=[9], bias=A[p + ".b"])
+                # nearest x2 as its own (one-load-four-stores) kernel + the halo conv: faster at every level than a conv whose loader
+                # folds the up-sampling (round 1: 45 -> 41, 59 -> 45, 176 -> 127 us at B = 256)
+                up = self._act(pb, p + ".up", B, x.H * 2, x.W * 2, x.C)
+                pb.add("ddif_upsample2x_t", label=p + ".nearest", traffic=B * x.H * x.W * x.C * 10, **{"in": x.buf}, out=up.buf, batch=B,
+                       h=x.H, w=x.W, c=x.C)
+                self._gemm(pb, p + ".conv", [up], [A[p + ".w"]], x.C, y, taps=[9], bias=A[p + ".b"])
                 x = y
                 self.taps[p] = (x, len(pb.ops))
                 continue
@@ -691,7 +689,7 @@ def _resolve_cache(pb: PlanBuilder, cache_base: int) -> None:
 class _Runtime:
     """Device buffers + recorded plans of one UNetSR3 at a fixed (B, H, W)."""
 
-    def __init__(self, net: UNetSR3, B: int, H: int, W: int):
+    def __init__(self, net: UNetSR3, B: int, H: int, W: int, **schedule_options):
         _lib.load()
         P = net._packed
         dev = next(net.parameters()).device
@@ -707,7 +705,7 @@ class _Runtime:
         addr = {k: v.data_ptr() for k, v in P.items() if isinstance(v, torch.Tensor)}
         io = dict(x=self.x_buf.data_ptr(), sc=self.sc_buf.data_ptr(), t=self.t_buf.data_ptr(), out=self.out_buf.data_ptr(),
                   cond=self.cond_buf.data_ptr())
-        sch = Schedule(net, addr, B, H, W, io)
+        sch = Schedule(net, addr, B, H, W, io, **schedule_options)
         sch.build_cond()
         sch.build_forward(P["_film_offsets"], int(P["film.w"].shape[0]))
         self.sch = sch
@@ -717,14 +715,14 @@ class _Runtime:
         self.ws = torch.zeros(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         for pb in (sch.cnd, sch.fwd):
             _resolve_cache(pb, self.cache.data_ptr())
-            pb.finalize(self.ws.data_ptr())
+            pb.finalize(self.ws.data_ptr(), device=dev)
         self.cond_key = None
         self.graph_ready = False
         self.use_graph = True
 
     @property
     def stream(self) -> int:
-        return torch.cuda.current_stream(self.dev).cuda_stream
+        return _lib.stream_of(self.dev)
 
     def set_cond(self, cond: torch.Tensor, force: bool = False) -> None:
         """Rebuild the cond cache unless `cond` is the very tensor object cached last time and has not been written
@@ -753,7 +751,7 @@ class _Runtime:
                 side = torch.cuda.Stream(self.dev)
                 side.wait_stream(torch.cuda.current_stream(self.dev))
                 with torch.cuda.stream(side):
-                    fwd.graph_build(side.cuda_stream)
+                    fwd.graph_build(_lib.Stream(side.cuda_stream, self.dev))
                 torch.cuda.current_stream(self.dev).wait_stream(side)
                 self.graph_ready = True
             fwd.graph_launch(self.stream)

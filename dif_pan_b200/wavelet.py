@@ -15,7 +15,7 @@ from . import _lib
 
 
 def _stream(t: torch.Tensor) -> int:
-    return torch.cuda.current_stream(t.device).cuda_stream
+    return _lib.stream_of(t.device)
 
 
 def _check(x: torch.Tensor) -> torch.Tensor:

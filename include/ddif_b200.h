@@ -68,9 +68,9 @@ enum ddif_op_kind {
 /* ---- DDIF_OP_GEMM ------------------------------------------------------------------------------------------
  * out[b,y,x,n] = epilogue( sum_seg sum_tap sum_c  a_seg[b, y*stride+dy-pad, x*stride+dx-pad, c] * w_seg[z, n, c] )
  * z = tap (shared weights) or b (per-sample weights, 1x1 only).  Zero padding comes from TMA out-of-bounds fill.
- * Three kernels implement it: conv3x3_halo_tc_kernel (3x3, stride 1: ONE TMA halo tile feeds all nine taps, optional
- * fused GroupNorm(+Swish) prologue, 1-2 concatenated sources, N split over CTAs), conv3x3_fused_tc_kernel (its
- * nearest-x2 up-sampling variant) and conv_igemm_tc_kernel (everything else: 1x1, stride 2, per-sample weights).
+ * Two kernels implement it: conv3x3_halo_tc_kernel (3x3, stride 1: ONE TMA halo tile feeds all nine taps, optional
+ * fused GroupNorm(+Swish) prologue, 1-2 concatenated sources, N split over CTAs) and conv_igemm_tc_kernel (everything
+ * else: 1x1, stride 2, per-sample weights).
  * epilogue: v = acc + bias[n] + film[b*film_ld + n];  v = v*(1+mod[..,n]) + mod[..,n_valid+n];  v += residual;
  *           v = silu(v) if act;  stats[b] += (sum v, sum v^2);  store bf16 NHWC and/or fp32 NCHW.              */
 typedef struct {
@@ -86,8 +86,8 @@ typedef struct {
   float* out_nchw;
   double* stats;
   /* Optional fused prologue on segment 0 (3x3 stride-1 convs only): a = act(GroupNorm_1group(a)) with the per-sample
-   * (sum, sumsq) statistics of the input tensor; a_up = 1 reads the input through a nearest x2 up-sampling
-   * (sr3_dwt.py:269).  force_tma = 1 selects the generic TMA kernel even where the fused 3x3 kernel applies. */
+   * (sum, sumsq) statistics of the input tensor; a_up is reserved and must be 0 (nearest x2, sr3_dwt.py:269, is
+   * DDIF_OP_UPSAMPLE2X in front of the conv).  force_tma = 1 selects the generic TMA kernel even where the halo kernel applies. */
   const double* gn_stats; const float* gn_gamma; const float* gn_beta; double gn_eps;
   int64_t gn_act, a_up, force_tma;
   /* 3x3 stride-1 convs may take TWO segments = channel concat of two tensors (torch.cat((x, skip), 1), sr3_dwt.py:212);
@@ -246,8 +246,8 @@ void ddif_plan_destroy(ddif_plan_t* plan);
 /* Record an op (parameters are copied; GEMM tensor maps are encoded once here). Returns op index or <0. */
 int ddif_plan_add(ddif_plan_t* plan, int kind, const void* params);
 int ddif_plan_size(const ddif_plan_t* plan);
-/* Which kernel a recorded DDIF_OP_GEMM resolved to: 0 conv_igemm_tc_kernel, 1 conv3x3_fused_tc_kernel,
- * 2 conv3x3_halo_tc_kernel; -1 for every other op kind (used by bench.py to attribute time per kernel). */
+/* Which kernel a recorded DDIF_OP_GEMM resolved to: 0 conv_igemm_tc_kernel, 2 conv3x3_halo_tc_kernel; -1 for every other op kind
+ * (used by bench.py to attribute time per kernel). */
 int ddif_plan_op_variant(const ddif_plan_t* plan, int index);
 /* Enqueue ops [first, last) on `stream` (last<0 = all). */
 int ddif_plan_run(ddif_plan_t* plan, int first, int last, ddif_stream_t stream);

@@ -187,16 +187,21 @@ def test_depthwise_q_path(name, B, H, W, c1, c2, o, act):
     assert float((got - ref).abs().max()) < 0.06 * float(ref.abs().max())
 
 
-def test_fused_upsample_conv_and_epilogue():
+def test_upsample_kernel_conv_and_epilogue():
     B, H, W, C = 2, 16, 16, 64
     x = _rand(B, C, H, W, seed=31)
     w, bias = _rand(C, C, 3, 3, seed=32, scale=0.05), _rand(C, seed=33)
     xa, wp = nhwc_bf16(x), pack_w(w)
-    out, stats = gemm([xa], [wp], C, taps=[9], bias=bias, a_up=1, want_stats=True)
+    # Upsample = nearest x2 (its own kernel) -> Conv3x3 (sr3_dwt.py:266-273); a_up (a loader-side fold) is reserved and rejected
+    up = torch.empty(B, 2 * H, 2 * W, C, dtype=torch.bfloat16, device=DEV)
+    _lib.launch("ddif_upsample2x_t", stream(), **{"in": xa.data_ptr()}, out=up.data_ptr(), batch=B, h=H, w=W, c=C)
+    out, stats = gemm([up], [wp], C, taps=[9], bias=bias, want_stats=True)
     ref = F.conv2d(F.interpolate(to_nchw_f32(xa), scale_factor=2, mode="nearest"), w.to(torch.bfloat16).float(), bias, padding=1)
-    _close(to_nchw_f32(out), ref, "upsample fold")
+    _close(to_nchw_f32(out), ref, "upsample + conv")
     s_ref = torch.stack([ref.double().sum(dim=(1, 2, 3)), (ref.double() ** 2).sum(dim=(1, 2, 3))], dim=1)
     assert torch.allclose(stats, s_ref, rtol=2e-3, atol=0.5)
+    with pytest.raises(RuntimeError):
+        gemm([xa], [wp], C, taps=[9], bias=bias, a_up=1)
     # residual + FiLM + fp32 NCHW store with N = 8 (the final conv)
     res = nhwc_bf16(_rand(B, C, H, W, seed=34))
     film = _rand(B, C, seed=35)

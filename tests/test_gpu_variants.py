@@ -334,6 +334,57 @@ def test_grad_clip_and_fused_adamw_match_torch():
     assert worst <= 2e-6
     with pytest.raises(RuntimeError):
         grad_clip([_cpu_param()], mode="value", value=1.0)
+    # a real torch.optim.Optimizer: schedulers attach, and the state round-trips with torch.optim.AdamW's own layout
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[1], gamma=0.2)   # diffusion_engine.py:207-210
+    sched.step()
+    assert abs(opt.param_groups[0]["lr"] - 2e-4) < 1e-12
+    sd = opt.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 3.0
+    ref_opt.load_state_dict(sd)                                                    # FusedAdamW -> torch AdamW
+    opt2 = FusedAdamW(params, lr=1e-3)
+    opt2.load_state_dict(ref_opt.state_dict())                                     # torch AdamW -> FusedAdamW
+    assert opt2.param_groups[0]["lr"] == ref_opt.param_groups[0]["lr"]
+    assert torch.equal(opt2.state[params[5]]["exp_avg_sq"], opt.state[params[5]]["exp_avg_sq"])
+
+
+def test_raw_pointer_updates_invalidate_the_packed_weights():
+    """EmaUpdater / FusedAdamW write parameters through raw device pointers; UNetSR3 keys its packed bf16 weights and captured CUDA
+    graph on (data_ptr, _version), so those writers bump the version counters.  The reference's validation flow is exactly
+    `ema_updater.update(it)` followed by sampling with the EMA model (diffusion_engine.py:240,273-298)."""
+    from dif_pan_b200 import synth
+    from dif_pan_b200.optim import EmaUpdater, FusedAdamW
+    kw = synth.unet_kwargs("wv3")
+    net, ema = dp.UNetSR3(**kw), dp.UNetSR3(**kw)
+    net.load_state_dict(synth.make_state_dict(0, **kw))
+    ema.load_state_dict(synth.make_state_dict(1, **kw))
+    net, ema = net.to(DEV).eval(), ema.to(DEV).eval()
+
+    class Holder:  # EmaUpdater reads `.model.parameters()` (GaussianDiffusion objects in the engine)
+        def __init__(self, m):
+            self.model = m
+
+    d = synth.make_batch("wv3", 2, seed=11)
+    cond = d["cond"].to(DEV)
+    x = torch.randn(2, 8, 64, 64, generator=torch.Generator().manual_seed(3)).to(DEV)
+    t = torch.tensor([400, 20], device=DEV)
+    y_before = ema(x, t, cond)
+    up = EmaUpdater(Holder(net), Holder(ema), decay=0.5, start_iter=0)
+    up.update(10)                                      # ema <- 0.5 ema + 0.5 net, written through raw pointers
+    y_after = ema(x, t, cond)
+    fresh = dp.UNetSR3(**kw)
+    fresh.load_state_dict({k: v.clone() for k, v in ema.state_dict().items()})
+    y_fresh = fresh.to(DEV).eval()(x, t, cond)
+    assert float((y_after - y_before).abs().max()) > 1e-3, "the EMA update must change the output"
+    assert float((y_after - y_fresh).abs().max()) <= 1e-3 * float(y_fresh.abs().max()), "stale packed weights after EmaUpdater.update"
+    # same for an optimizer step
+    for p in ema.parameters():
+        p.grad = torch.full_like(p, 1e-2)
+    FusedAdamW(ema.parameters(), lr=1e-2).step()
+    y_opt = ema(x, t, cond)
+    fresh.load_state_dict({k: v.clone() for k, v in ema.state_dict().items()})
+    y_fresh = fresh(x, t, cond)
+    assert float((y_opt - y_after).abs().max()) > 1e-3
+    assert float((y_opt - y_fresh).abs().max()) <= 1e-3 * float(y_fresh.abs().max()), "stale packed weights after FusedAdamW.step"
 
 
 def _cpu_param():

@@ -38,6 +38,22 @@ def _worker(rank, world, port, total, q):
     ok = torch.equal(full, ref)
     lo, hi = shard_range(total, rank, world)
     ok = ok and torch.equal(gather_patches(ref[lo:hi], total), ref)
+
+    # without injected noise the in-kernel generator is indexed by the GLOBAL patch index: sample_sharded tells the diffusion object
+    # which slice of the batch this rank holds (noise_shard = (lo, total)) and resets it afterwards
+    class FakeDiffusion:
+        noise_shard = None
+
+    dif = FakeDiffusion()
+
+    def sampler_with_rng(c):
+        l0, tot = dif.noise_shard
+        idx = torch.arange(l0, l0 + c.shape[0], dtype=torch.float32).view(-1, 1, 1, 1)  # stand-in for Philox(seed, global index)
+        return _fake_sampler(c) + idx / tot
+
+    full2 = sample_sharded(sampler_with_rng, cond, diffusion=dif)
+    ref2 = _fake_sampler(cond) + torch.arange(total, dtype=torch.float32).view(-1, 1, 1, 1) / total
+    ok = ok and torch.equal(full2, ref2) and dif.noise_shard is None
     q.put((rank, bool(ok), tuple(full.shape)))
     dist.destroy_process_group()
 

@@ -32,9 +32,10 @@ static constexpr int kHThreads = kHxfThreads + 64 + 32 * kHEpiWarps + 32;  // + 
 static constexpr int kHW = 10, kHH = 18, kHPx = kHW * kHH;  // halo of an 8 x 16 tile
 static constexpr int kHMaxStages = 8;
 static constexpr int kHMaxStat = 1024;
-// (A TMA-store epilogue -- tile staged in shared memory, stored with cp.async.bulk.tensor -- was built and measured in round 1:
-// correct but slower for N >= 64 and +4 % for N = 32, because the staging traffic competes with the tcgen05 operand fetch for
-// shared-memory bandwidth; removed)
+// Negative results of rounds 1-2, removed from the source (numbers in DESIGN.md section 4.2): a TMA-store epilogue (tile staged in shared
+// memory, cp.async.bulk.tensor store: slower for N >= 64, +4 % for N = 32 -- the staging traffic competes with the tcgen05 operand fetch);
+// fp64 running statistics per thread in shared memory instead of the per-tile warp reduction (same-box A/B: 64 -> 64 @32^2 26.5 -> 29.2 us);
+// letting the MMA warp wait on the TMA barrier of a residual slab itself instead of the transform group's relay (32 -> 32 @64^2 60.9 -> 64.0 us).
 
 struct alignas(64) HaloKParams {
   CUtensorMap tmA[2];  // activations of K segment 0 / 1 (virtual channel concat: torch.cat((x, skip), 1), sr3_dwt.py:212)
@@ -183,8 +184,11 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
   int cur_b = -1, cur_slab = -1, tcount = 0;
   f32x2 a2[4], d2[4];
   for (; it.remaining > 0; it.next()) {
-    if (it.slab >= p.nslab) {  // residual slab (identity-weight K segment): TMA -> MMA directly (the MMA warp waits on a_tma itself);
-      if (++stage == nst) { stage = 0; phase ^= 1u; }  // this group only keeps its ring position in step
+    if (it.slab >= p.nslab) {  // residual slab (identity-weight K segment): TMA -> MMA untouched, this group only relays the barrier
+      mbar_wait(&a_tma[stage], phase);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&a_ready[stage]);
+      if (++stage == nst) { stage = 0; phase ^= 1u; }
       continue;
     }
     if (it.b != cur_b || it.slab != cur_slab) {
@@ -260,9 +264,9 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
 // tile) to the tensor pipe's critical path; with two, one warp waits for its next stage / accumulator while the other's
 // MMAs execute.
 template <int KSTEPS>
-__device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_base, uint32_t b_base, uint64_t* a_tma, uint64_t* a_ready,
-                                              uint64_t* a_empty, uint64_t* b_full, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
-                                              int my_tiles, int w, long long* dts) {
+__device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_base, uint32_t b_base, uint64_t* a_full, uint64_t* a_empty,
+                                              uint64_t* b_full, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int my_tiles,
+                                              int w, long long* dts) {
   const uint32_t span = (uint32_t)p.span;
   const uint64_t desc_b0 = make_smem_desc(b_base, 8u * span, p.layout_type);
   const uint32_t stage16 = p.stage_bytes >> 4, b16 = p.b_slot_bytes >> 4;
@@ -270,12 +274,8 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((uint32_t)((tap / 3) * kHW + (tap % 3)) * span) >> 4;
   const uint32_t nst = (uint32_t)p.stages >> 1;  // stages of this warp's ring
-  a_tma += (uint32_t)w * nst; a_empty += (uint32_t)w * nst;
-  if (a_ready) a_ready += (uint32_t)w * nst;  // nullptr without the GroupNorm prologue: the TMA barrier feeds the MMAs directly
+  a_full += (uint32_t)w * nst; a_empty += (uint32_t)w * nst;
   a_base += (uint32_t)w * nst * p.stage_bytes;
-  // a_tma[stage] completes one phase per ring wrap (every slab lands there); a_ready[stage] only when a CONV slab used the stage (residual
-  // slabs bypass the transform warps), so its parity is tracked per stage: bit s of rdy_par
-  uint32_t rdy_par = 0u;
   const uint64_t desc_a0 = make_smem_desc(a_base, (uint32_t)kHW * span, p.layout_type);  // SBO = one halo line (10 rows)
   // residual-as-operand: centre tap (one line + one pixel into the halo) of a stage holding rows of span_r bytes; identity weights
   // sit behind the conv weights
@@ -296,12 +296,7 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
     if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 1);
     uint64_t db = desc_b0;
     for (int slab = 0; slab < p.nslab; ++slab) {
-      if (a_ready) {
-        mbar_wait(&a_ready[stage], (rdy_par >> stage) & 1u);
-        rdy_par ^= 1u << stage;
-      } else {
-        mbar_wait(&a_tma[stage], phase);
-      }
+      mbar_wait(&a_full[stage], phase);
       tc_fence_after();
       if ((threadIdx.x & 31) == 0) h_ts(dts, 1, t, 2);
       const uint64_t da = desc_a0 + (uint64_t)(stage * stage16);
@@ -316,7 +311,7 @@ __device__ __forceinline__ void halo_mma_loop(const HaloKParams& p, uint32_t a_b
       if (++stage == nst) { stage = 0; phase ^= 1u; }
     }
     for (int rs = 0; rs < p.nslab_r; ++rs) {  // + residual: centre tap of the residual's halo stage x identity weights
-      mbar_wait(&a_tma[stage], phase);
+      mbar_wait(&a_full[stage], phase);
       tc_fence_after();
       const uint64_t da = desc_r0 + (uint64_t)(stage * stage16);
       const uint64_t dbr = desc_br0 + (uint64_t)((uint32_t)rs * (p.r_slot_bytes >> 4));
@@ -531,7 +526,7 @@ enum : int { kEpiRes = 1, kEpiAct = 2, kEpiStats = 4, kEpiNchw = 8 };
 
 template <int F>
 __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int warp,
-                                                   int lane, int my_tiles, long long* dts, float* s_add, double2* s_run) {
+                                                   int lane, int my_tiles, long long* dts, float* s_add) {
   constexpr bool kRes = (F & kEpiRes) != 0, kAct = (F & kEpiAct) != 0, kStats = (F & kEpiStats) != 0, kNchw = (F & kEpiNchw) != 0;
   const int q = warp & 3;
   const int grp = (warp - 10) >> 2;
@@ -579,40 +574,24 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
     r = g2 - sb * tpi;
     sy = r / tiles_x; sx = r - sy * tiles_x;
   }
-  // Statistics: every thread keeps fp64 running sums (sum, sumsq) of its rows in SHARED memory -- per tile it adds its fp32 tile partial
-  // (<= 256 values) to them, 2 DADD and no cross-lane traffic -- and the warp publishes them (one fp64 shuffle reduction + two fp64
-  // atomics) only when the sample changes or the CTA's range ends: <= 3 times per launch instead of once per tile.  Round 1 reduced per
-  // tile (two fp32 warp reductions + two atomics at the tail of every tile's dependency chain, ~10 % of the 32-channel layers); fp32
-  // running sums in registers were rejected there because they made results depend on the tile -> CTA assignment at the 1e-5
-  // level and fp64 ones spilled at the 96-register cap.  fp64 sums in shared memory have neither problem: the value of a sample's
-  // statistics is independent of how its tiles are split over CTAs to ~1e-15.
+  // Statistics are reduced per TILE (two warp reductions + two fp64 atomics): the per-tile partials are the same values whatever the
+  // tile -> CTA assignment, so results do not depend on the batch size.  Carrying per-thread sums across a sample's tiles was tried:
+  // plain fp32 running sums are 10 % faster on the 32 -> 32 layers but make the statistics batch-size dependent at the 1e-5 level
+  // (= the bf16 noise level of the network output); compensated or fp64 running sums keep the numerics but their four extra live
+  // registers spill in this 96-register epilogue and cost more than the reduction they save.
   f32x2 s1 = pk2(0.f, 0.f), s2 = pk2(0.f, 0.f);
   int stat_b = -1;
-  double2* run = s_run + (threadIdx.x - 10 * 32);
-  if (kStats) *run = make_double2(0.0, 0.0);
   auto tile_stats = [&]() {
     float l1, h1, l2, h2;
     upk2(s1, l1, h1);
     upk2(s2, l2, h2);
-    double2 r = *run;
-    r.x += (double)(l1 + h1);
-    r.y += (double)(l2 + h2);
-    *run = r;
+    const float t1 = warp_sum(l1 + h1), t2 = warp_sum(l2 + h2);
+    if (lane == 0) {
+      atomicAdd(stats + 2 * (size_t)stat_b, (double)t1);
+      atomicAdd(stats + 2 * (size_t)stat_b + 1, (double)t2);
+    }
     s1 = pk2(0.f, 0.f);
     s2 = pk2(0.f, 0.f);
-  };
-  auto flush_stats = [&]() {
-    double2 r = *run;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      r.x += __shfl_xor_sync(0xffffffffu, r.x, o);
-      r.y += __shfl_xor_sync(0xffffffffu, r.y, o);
-    }
-    if (lane == 0) {
-      atomicAdd(stats + 2 * (size_t)stat_b, r.x);
-      atomicAdd(stats + 2 * (size_t)stat_b + 1, r.y);
-    }
-    *run = make_double2(0.0, 0.0);
   };
   uint32_t it = 0;
   for (int t = grp; t < my_tiles; t += 2, ++it) {
@@ -655,10 +634,7 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
         if (k < nadd) addv[lane + 32 * k] = fa[k];
       __syncwarp();
     }
-    if (kStats && b != stat_b) {
-      if (stat_b >= 0) flush_stats();
-      stat_b = b;
-    }
+    stat_b = b;
     auto process = [&](const uint32_t (&acc)[16], const uint32_t (&rs)[8], int cc) {
       const int ng = cc * 16;
       const int nrem = n_valid - ng;
@@ -755,7 +731,6 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
     if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
     if (ty >= tiles_y) { ty -= tiles_y; ++b; }
   }
-  if (kStats && stat_b >= 0) flush_stats();
 }
 
 template <int F, bool DW>
@@ -773,8 +748,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   float2* s_stat = reinterpret_cast<float2*>(s_beta + p.cin);
   const int n_stat = p.gn_stats ? (p.batch < kHMaxStat ? p.batch : kHMaxStat) : 0;
   float* s_add = reinterpret_cast<float*>(s_stat + ((n_stat + 1) & ~1));  // [8 epilogue warps][256], 16-byte aligned
-  double2* s_run = reinterpret_cast<double2*>(s_add + kHEpiWarps * 256);   // [256 epilogue threads] fp64 running (sum, sumsq)
-  float* s_dw = reinterpret_cast<float*>(s_run + 32 * kHEpiWarps);         // [9][cin] depthwise weights (depthwise mode)
+  float* s_dw = s_add + kHEpiWarps * 256;                                  // [9][cin] depthwise weights (depthwise mode)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_dw + (DW ? ((9 * p.cin + 3) & ~3) : 0));
   uint64_t* a_tma = bars;                       // [stages] TMA landed
   uint64_t* a_ready = bars + kHMaxStages;       // [stages] transformed (count 256)
@@ -877,7 +851,6 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   } else if (warp == 8 || warp == 9) {
     // ===================== MMA issuers (converged warps, elected lane issues) =====================
     uint64_t* a_full = gn ? a_ready : a_tma;
-    uint64_t* a_rdy = gn ? a_ready : nullptr;
     const int w = warp - 8;
     if constexpr (DW) {
       const uint32_t sa = smem_u32(smem_a), sd = smem_u32(smem_dw), sb = smem_u32(smem_b);
@@ -885,9 +858,9 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
       else if (p.kslab == 32) halo_mma_dw_loop<2>(p, sa, sd, sb, a_full, a_empty, dw_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w);
       else halo_mma_dw_loop<1>(p, sa, sd, sb, a_full, a_empty, dw_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w);
     } else
-    if (p.kslab == 64) halo_mma_loop<4>(p, smem_u32(smem_a), smem_u32(smem_b), a_tma, a_rdy, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
-    else if (p.kslab == 32) halo_mma_loop<2>(p, smem_u32(smem_a), smem_u32(smem_b), a_tma, a_rdy, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
-    else halo_mma_loop<1>(p, smem_u32(smem_a), smem_u32(smem_b), a_tma, a_rdy, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
+    if (p.kslab == 64) halo_mma_loop<4>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
+    else if (p.kslab == 32) halo_mma_loop<2>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
+    else halo_mma_loop<1>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
   } else if (warp == 18) {
     // ===================== TMA producer: the halo ring (the resident weights were requested above) =====================
     if (lane == 0) {
@@ -938,7 +911,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
     }
   } else if (warp >= 10 && warp < 18) {
     // ===================== epilogue (warps 10..17): two groups of 4 warps, one TMEM accumulator each =====================
-    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, dts, s_add, s_run);
+    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, dts, s_add);
     tc_fence_before();
   }
   __syncthreads();
@@ -1033,7 +1006,7 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
   if (!g.out && !g.out_nchw) return false;
   h.cin = cin;
   h.n_stat = g.gn_stats ? (int)(g.batch < kHMaxStat ? g.batch : kHMaxStat) : 0;
-  h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + kHEpiWarps * 32 * 16 + (dw ? ((9 * cin + 3) & ~3) * 4 : 0) + (3 * kHMaxStages + 16) * 8 + 64 + 1024;
+  h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + (dw ? ((9 * cin + 3) & ~3) * 4 : 0) + (3 * kHMaxStages + 16) * 8 + 64 + 1024;
   h.ntap_w = dw ? 1 : 9;
   // Resident weights of one CTA (9 taps x all K slabs x bn rows) must leave room for two rings of >= 2 halo stages:
   // split N over blockIdx.y (1, 2, 4 CTAs per tile) and, before splitting further, halve the K slab (smaller stages).

@@ -99,7 +99,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
   uint64_t* tmem_full_bar = bars + 2 * p.stages;       // [4]
   uint64_t* tmem_empty_bar = bars + 2 * p.stages + 4;  // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 8);
-  double2* s_run = reinterpret_cast<double2*>(bars + 2 * p.stages + 10);  // [32 * kEpiWarps] fp64 running statistics of the lean epilogue
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -297,25 +296,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
         nxt_ok = locate(m_tile, nxt_pix, nxt_b);
         fetch(nxt, nxt_pix, nxt_ok);
       }
-      // GroupNorm statistics of the output: per-thread fp64 running sums in shared memory, published (fp64 shuffle reduction + two
-      // atomics per warp) only when the warp's sample changes or the CTA's range ends -- see halo_epilogue_loop (conv3x3_halo.cu).
-      // The per-tile fp32 warp reduction + atomics this replaces were ~30 % of the 32 -> 32 1x1 conv (profiles/r01s5_gemm1x1_ablation_stats.txt).
-      double2* run = s_run + (threadIdx.x - 64);
-      int stat_b = -1;
-      if (kStats) *run = make_double2(0.0, 0.0);
-      auto flush_stats = [&]() {
-        double2 r = *run;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          r.x += __shfl_xor_sync(0xffffffffu, r.x, o);
-          r.y += __shfl_xor_sync(0xffffffffu, r.y, o);
-        }
-        if (lane == 0 && stat_b < p.batch) {
-          atomicAdd(p.stats + 2 * (size_t)stat_b, r.x);
-          atomicAdd(p.stats + 2 * (size_t)stat_b + 1, r.y);
-        }
-        *run = make_double2(0.0, 0.0);
-      };
       for (uint32_t tcount = 0; m_tile < tile_end; m_tile += step, ++tcount) {
         const LeanOperands<F> cur = nxt;
         const bool row_ok = nxt_ok;
@@ -389,19 +369,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
           stg256(p.out + pix * (size_t)p.out_ld + ng, w);
 #endif
         }
+#ifndef DDIF_VAR_G_NO_STATRED
         if (kStats && active) {  // all rows of one warp belong to one sample
-          const int stat_sample = (m_tile / tiles_per_img) * p.tn + (q * 32) / px_per_img;
-          if (stat_sample != stat_b) {
-            if (stat_b >= 0) flush_stats();
-            stat_b = stat_sample;
+          s1 = warp_sum(s1);
+          s2 = warp_sum(s2);
+          const int img_grp = m_tile / tiles_per_img;
+          const int stat_sample = img_grp * p.tn + (q * 32) / px_per_img;
+          if (lane == 0 && stat_sample < p.batch) {
+            atomicAdd(p.stats + 2 * (size_t)stat_sample, (double)s1);
+            atomicAdd(p.stats + 2 * (size_t)stat_sample + 1, (double)s2);
           }
-          double2 r = *run;
-          r.x += (double)s1;
-          r.y += (double)s2;
-          *run = r;
         }
+#else
+        if (kStats && s1 + s2 == 1.2345f) atomicAdd(p.stats, 1.0);
+#endif
       }
-      if (kStats && stat_b >= 0) flush_stats();
       tc_fence_before();
     } else {
     const int grp = p.groups == 4 ? sub : (sub & 1);
@@ -589,7 +571,7 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   if (!p.resident_b) p.b_slots = stages;
   p.stages = stages;
   p.num_m_tiles = p.tiles_x * p.tiles_y * (int)ceil_div(B, tn);
-  L.smem_bytes = stages * a_stage + p.b_slots * b_slot + (2 * stages + 10) * 8 + 32 * kEpiWarps * 16 + 1024;
+  L.smem_bytes = stages * a_stage + p.b_slots * b_slot + (2 * stages + 10) * 8 + 1024;
   const int sms = ddif_sm_count();
   L.grid_y = (int)(g.n_pad / bn);
   const int gx = (sms + L.grid_y - 1) / L.grid_y;  // persistent: ~one CTA per SM in total

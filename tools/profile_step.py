@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--dataset", default="wv3")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--size", type=int, default=64, help="H = W of the input (512 with --batch 1 = whole-scene mode of test_fn)")
+    ap.add_argument("--top", type=int, default=12)
     ap.add_argument("--out", default="gpurun_out")
     ap.add_argument("--ncu", action="store_true", help="run cond build + ONE eager step between cudaProfilerStart/Stop and exit")
     a = ap.parse_args()
@@ -39,8 +41,8 @@ def main():
     net.load_state_dict(synth.make_state_dict(0, **kw))
     net = net.to(dev).eval()
     B = a.batch
-    rt = net.runtime(B, 64, 64)
-    cond = synth.make_batch(a.dataset, min(B, 16), seed=1)["cond"]
+    rt = net.runtime(B, a.size, a.size)
+    cond = synth.make_batch(a.dataset, min(B, 16), size=a.size, seed=1)["cond"]
     cond = cond.repeat((B + cond.shape[0] - 1) // cond.shape[0], 1, 1, 1)[:B].contiguous().to(dev)
     t0 = time.time()
     rt.set_cond(cond)
@@ -91,10 +93,10 @@ def main():
     print(f"gemm total: {gms:.3f} ms, {gfl / gms / 1e9:.1f} TFLOP/s executed")
     os.makedirs(a.out, exist_ok=True)
     json.dump(dict(batch=B, eager_ms=t_eager, graph_ms=t_graph, cond_ms=t_cond, ops=[dict(label=r[0], struct=r[1], ms=r[2], flops=r[3], bytes=r[4]) for r in rows]),
-              open(os.path.join(a.out, f"step_profile_B{B}.json"), "w"))
-    worst = sorted(gm, key=lambda r: -r[2])[:12]
+              open(os.path.join(a.out, f"step_profile_B{B}_{a.size}.json"), "w"))
+    worst = sorted(rows, key=lambda r: -r[2])[:a.top]
     for r in worst:
-        print(f"  {r[0]:<40}{r[2]:>8.3f} ms {r[3] / r[2] / 1e9:>8.1f} TF/s {r[4] / r[2] / 1e6:>8.0f} GB/s")
+        print(f"  {r[0] or r[1]:<40}{r[2]:>8.3f} ms {r[3] / r[2] / 1e9:>8.1f} TF/s {r[4] / r[2] / 1e6:>8.0f} GB/s")
 
 
 if __name__ == "__main__":

@@ -452,6 +452,64 @@ __global__ void __launch_bounds__(128) softmax_h_reg_kernel(const uint32_t* __re
     }
   }
 }
+// Tall images (whole-scene mode: H = 128 .. 512): the column of one (b, x, channel pair) is split over TY = H / 32 threads of a CTA that
+// owns one (b, x): each thread keeps its 32 rows packed in registers, the column maximum and the sum of exponentials are combined through
+// shared memory, and HBM is read once and written once.  The round-1 fall-back walked a whole column per thread (H serial strided loads,
+// two passes, B*W*C/8 threads in total): 175 GB/s at B = 1, 23 % of a whole-scene denoise step (profiles/r02_whole_scene_profile_before.txt).
+static constexpr int kSmRows = 32;
+__global__ void __launch_bounds__(768) softmax_h_col_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int H, int W, int cw, int ldw,
+                                                             float scale) {
+  pdl_wait();
+  __shared__ float2 red[16 * 128];
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int c = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
+  const int x = blockIdx.x;
+  const size_t b = blockIdx.y;
+  const size_t row_in = (size_t)W * ldw, row_out = (size_t)W * cw;
+  const uint32_t* src = in + (b * H + ty) * row_in + (size_t)x * ldw + c;
+  uint32_t* dst = out + (b * H + ty) * row_out + (size_t)x * cw + c;
+  uint32_t w[kSmRows];
+#pragma unroll
+  for (int i = 0; i < kSmRows; ++i) w[i] = __ldg(src + (size_t)i * TY * row_in);  // rows ty, ty + TY, ...
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kSmRows; ++i) {
+    m0 = fmaxf(m0, __uint_as_float(w[i] << 16));
+    m1 = fmaxf(m1, __uint_as_float(w[i] & 0xffff0000u));
+  }
+  red[ty * cw + c] = make_float2(m0, m1);
+  __syncthreads();
+  for (int t = 0; t < TY; ++t) {
+    const float2 v = red[t * cw + c];
+    m0 = fmaxf(m0, v.x);
+    m1 = fmaxf(m1, v.y);
+  }
+  __syncthreads();
+  const float c0 = -m0 * kLog2e, c1 = -m1 * kLog2e;
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSmRows; ++i) {
+    l0 += exp2f(fmaf(__uint_as_float(w[i] << 16), kLog2e, c0));
+    l1 += exp2f(fmaf(__uint_as_float(w[i] & 0xffff0000u), kLog2e, c1));
+  }
+  red[ty * cw + c] = make_float2(l0, l1);
+  __syncthreads();
+  l0 = 0.f;
+  l1 = 0.f;
+  for (int t = 0; t < TY; ++t) {  // same order in every thread of the column: identical totals
+    const float2 v = red[t * cw + c];
+    l0 += v.x;
+    l1 += v.y;
+  }
+  const float r0 = scale / l0, r1 = scale / l1;
+#pragma unroll
+  for (int i = 0; i < kSmRows; ++i) {  // the exponentials are recomputed (MUFU is idle, registers are not: up to 768 threads per CTA)
+    const __nv_bfloat162 t = __floats2bfloat162_rn(exp2f(fmaf(__uint_as_float(w[i] << 16), kLog2e, c0)) * r0,
+                                                   exp2f(fmaf(__uint_as_float(w[i] & 0xffff0000u), kLog2e, c1)) * r1);
+    dst[(size_t)i * TY * row_out] = *reinterpret_cast<const uint32_t*>(&t);
+  }
+}
+
 template <int H>
 static int launch_softmax_h_reg(const ddif_softmax_h_t& p, cudaStream_t s) {
   const int ld = (int)(p.in_ld ? p.in_ld : p.c);
@@ -466,6 +524,13 @@ int launch_softmax_h(const ddif_softmax_h_t& p, cudaStream_t s) {
   if (p.h == 32) return launch_softmax_h_reg<32>(p, s);
   if (p.h == 16) return launch_softmax_h_reg<16>(p, s);
   if (p.h == 8) return launch_softmax_h_reg<8>(p, s);
+  if (p.h > 64 && p.h % kSmRows == 0 && p.h <= 16 * kSmRows && (p.c / 2) <= 128 && (p.c / 2) * (p.h / kSmRows) <= 768 && p.c % 2 == 0 && p.w <= 65535 &&
+      p.batch <= 65535) {
+    const int ld = (int)(p.in_ld ? p.in_ld : p.c);
+    DDIF_CUDA_CHECK(launch_pdl(softmax_h_col_kernel, dim3((unsigned)p.w, (unsigned)p.batch), dim3((unsigned)(p.c / 2), (unsigned)(p.h / kSmRows)), (size_t)0, s,
+                               (const uint32_t*)p.in, (uint32_t*)p.out, (int)p.h, (int)p.w, (int)(p.c / 2), ld / 2, (float)p.scale));
+    return DDIF_OK;
+  }
   DDIF_CUDA_CHECK(launch_pdl(softmax_h_kernel, dim3(grid_for(p.batch * p.w * (p.c / 8), 128)), dim3(128), (size_t)0, s, (const bf16*)p.in, (bf16*)p.out,
                              (int)p.batch, (int)p.h, (int)p.w, (int)p.c, (int)(p.in_ld ? p.in_ld : p.c), (float)p.scale));
   return DDIF_OK;
@@ -592,8 +657,10 @@ __global__ void __launch_bounds__(64) attn64_kernel(const bf16* __restrict__ qkv
   }
 }
 int launch_attn(const ddif_attn_t& p, cudaStream_t s) {
-  if (p.c % p.heads != 0) return DDIF_ERR_SHAPE;
+  if (p.heads <= 0 || p.c % p.heads != 0) return DDIF_ERR_SHAPE;
   const int hd = (int)(p.c / p.heads);
+  // long token counts (whole-scene mode, non-64x64 inputs): the tcgen05 / TMEM flash kernel (attn_tc.cu)
+  if (attn_tc_applicable(p)) return launch_attn_tc(p, s);
   if (p.ntok == 64 && (hd == 16 || hd == 8) && p.c % 8 == 0) {
     const float sl2 = (float)(p.scale * 1.4426950408889634);
     const dim3 g64((unsigned)p.heads, (unsigned)p.batch);
@@ -762,9 +829,12 @@ int launch_resize(const ddif_resize_t& p, cudaStream_t s) {
   return DDIF_OK;
 }
 
-// ---- FWM cond-only context (sr3_dwt.py:541,546,563): one block per (b, head) --------------------------------
+// ---- FWM cond-only context (sr3_dwt.py:541,546,563): one block per (b, head, row range) ---------------------
 //  kv = Conv1x1(DW3x3(c));  k.softmax over W;  ctx[d][e] = sum_n k[d,n] v[e,n]
-__global__ void fwm_context_kernel(ddif_fwm_context_t p) {
+// rows_per_cta >= H: one CTA owns the whole image and stores its context (patches: deterministic, as in round 1); otherwise the rows are
+// split over blockIdx.z and the partial contexts are added with fp32 atomics into a zeroed buffer (whole-scene mode: H = 128 .. 512; one CTA
+// per (b, head) walked 512 rows serially on 8 SMs: 127 ms of cond-cache build for a 512x512 scene).
+__global__ void fwm_context_kernel(ddif_fwm_context_t p, int rows_per_cta) {
   extern __shared__ float sm[];
   const int b = blockIdx.y, head = blockIdx.x;
   const int H = (int)p.h, W = (int)p.w, cd = (int)p.cd, dim = (int)p.dim;
@@ -775,7 +845,8 @@ __global__ void fwm_context_kernel(ddif_fwm_context_t p) {
   const int tid = threadIdx.x, nt = blockDim.x;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};  // pairs tid, tid+nt, ... of the d*d context (d <= 32, nt = 256)
   const float* cb = p.c_dec + (size_t)b * cd * H * W;
-  for (int y = 0; y < H; ++y) {
+  const int y_begin = (int)blockIdx.z * rows_per_cta, y_end = min(H, y_begin + rows_per_cta);
+  for (int y = y_begin; y < y_end; ++y) {
     for (int i = tid; i < cd * W; i += nt) {
       const int cc = i / W, x = i - cc * W;
       float a = 0.f;
@@ -827,7 +898,11 @@ __global__ void fwm_context_kernel(ddif_fwm_context_t p) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int pr = tid + k * nt;
-    if (pr < d * d) p.ctx[((size_t)b * p.heads + head) * d * d + pr] = acc[k];
+    if (pr < d * d) {
+      float* dst = p.ctx + ((size_t)b * p.heads + head) * d * d + pr;
+      if (gridDim.z == 1) *dst = acc[k];
+      else atomicAdd(dst, acc[k]);
+    }
   }
 }
 int launch_fwm_context(const ddif_fwm_context_t& p, cudaStream_t s) {
@@ -837,7 +912,10 @@ int launch_fwm_context(const ddif_fwm_context_t& p, cudaStream_t s) {
   const size_t smem = (size_t)(p.cd + 2 * d) * p.w * sizeof(float);
   if (smem > 220 * 1024) return DDIF_ERR_SHAPE;
   if (smem > 48 * 1024) DDIF_CUDA_CHECK(cudaFuncSetAttribute(fwm_context_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fwm_context_kernel<<<dim3((unsigned)p.heads, (unsigned)p.batch), 256, smem, s>>>(p);
+  const int rows = p.h > 64 ? 16 : (int)p.h;  // patches (H <= 64): one CTA per (b, head), plain stores
+  const int nz = (int)ceil_div(p.h, rows);
+  if (nz > 1) DDIF_CUDA_CHECK(cudaMemsetAsync(p.ctx, 0, (size_t)p.batch * p.dim * d * sizeof(float), s));
+  fwm_context_kernel<<<dim3((unsigned)p.heads, (unsigned)p.batch, (unsigned)nz), 256, smem, s>>>(p, rows);
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;
 }

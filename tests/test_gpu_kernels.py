@@ -123,6 +123,47 @@ def test_softmax_h_and_attention():
         assert rel_err(to_nchw_f32(o), ref) < 5e-3
 
 
+@pytest.mark.parametrize("hw,B", [((16, 8), 3), ((16, 16), 2), ((32, 32), 2), ((64, 64), 1)])
+def test_tcgen05_flash_attention_long_token_counts(hw, B):
+    """attn_tc.cu: the tcgen05 / TMEM flash kernel behind DDIF_OP_ATTN for head_dim 16 and ntok % 128 == 0 (128 .. 4096 tokens: the attention
+    level of 128x64 patches up to 512x512 whole scenes) against fp32 torch attention (sr3_dwt.py:347-357: scale 1/sqrt(C), not 1/sqrt(d))."""
+    h, w = hw
+    Cc, heads = 128, 8
+    qkv = nhwc_bf16(_rand(B, 3 * Cc, h, w, seed=40 + h, scale=1.5))
+    o = torch.zeros(B, h, w, Cc, dtype=torch.bfloat16, device=DEV)
+    _lib.launch("ddif_attn_t", stream(), qkv=qkv.data_ptr(), out=o.data_ptr(), batch=B, ntok=h * w, c=Cc, heads=heads, scale=1 / math.sqrt(Cc))
+    torch.cuda.synchronize()
+    t = to_nchw_f32(qkv).view(B, heads, 3 * Cc // heads, h * w)
+    hd = Cc // heads
+    qq, kk, vv = t[:, :, :hd], t[:, :, hd:2 * hd], t[:, :, 2 * hd:]
+    att = torch.softmax(torch.einsum("bncq,bnck->bnqk", qq, kk) / math.sqrt(Cc), -1)
+    ref = torch.einsum("bnqk,bnck->bncq", att, vv).reshape(B, Cc, h, w)
+    e = rel_err(to_nchw_f32(o), ref)
+    print(f"[attn_tc {h}x{w} B={B}] rel err {e:.4g}")
+    assert e < 6e-3, (hw, e)
+    # a sharper distribution (large logits): the online-softmax rescale path matters
+    qkv2 = nhwc_bf16(_rand(B, 3 * Cc, h, w, seed=41 + h, scale=6.0))
+    _lib.launch("ddif_attn_t", stream(), qkv=qkv2.data_ptr(), out=o.data_ptr(), batch=B, ntok=h * w, c=Cc, heads=heads, scale=1 / math.sqrt(Cc))
+    t = to_nchw_f32(qkv2).view(B, heads, 3 * Cc // heads, h * w)
+    qq, kk, vv = t[:, :, :hd], t[:, :, hd:2 * hd], t[:, :, 2 * hd:]
+    att = torch.softmax(torch.einsum("bncq,bnck->bnqk", qq, kk) / math.sqrt(Cc), -1)
+    ref = torch.einsum("bnqk,bnck->bncq", att, vv).reshape(B, Cc, h, w)
+    e = rel_err(to_nchw_f32(o), ref)
+    print(f"[attn_tc sharp {h}x{w}] rel err {e:.4g}")
+    assert e < 8e-3, (hw, e)
+
+
+@pytest.mark.parametrize("H,W,C,ld", [(128, 16, 192, 0), (256, 8, 128, 192), (512, 8, 64, 96), (512, 4, 96, 128)])
+def test_softmax_h_tall_images(H, W, C, ld):
+    """softmax_h_col_kernel: column split over the threads of a CTA for H = 128 .. 512 (whole-scene mode)."""
+    B = 2
+    wide = nhwc_bf16(_rand(B, ld or C, H, W, seed=50 + H, scale=3.0))
+    out = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=DEV)
+    _lib.launch("ddif_softmax_h_t", stream(), **{"in": wide.data_ptr()}, out=out.data_ptr(), batch=B, h=H, w=W, c=C, scale=0.5, in_ld=ld)
+    ref = to_nchw_f32(wide)[:, :C].softmax(dim=-2) * 0.5
+    assert rel_err(to_nchw_f32(out), ref) < 4e-3, (H, W, C, ld)
+
+
 def test_resize_matches_interpolate():
     B, Ct, H, W = 2, 20, 64, 64
     cond = torch.rand(B, Ct, H, W, generator=torch.Generator().manual_seed(11)).to(DEV)
@@ -154,6 +195,17 @@ def test_fwm_context_and_weff():
     k = k.softmax(dim=-1).reshape(B, 8, d, H * W)
     ref = torch.einsum("bhdn,bhen->bhde", k, v.reshape(B, 8, d, H * W))
     assert rel_err(ctx, ref) < 1e-4
+    # tall image (whole-scene mode): rows split over CTAs, partial contexts added atomically into the zeroed buffer
+    H2, W2 = 160, 24
+    c2 = torch.rand(B, cd, H2, W2, generator=torch.Generator().manual_seed(21)).to(DEV)
+    ctx2 = torch.full((B, 8, d, d), 7.0, device=DEV)  # stale contents must not leak into the result
+    _lib.launch("ddif_fwm_context_t", stream(), c_dec=c2.data_ptr(), kv0_w=kv0.reshape(cd, 9).contiguous().data_ptr(),
+                kv1_w=kv1.reshape(2 * dim, cd).contiguous().data_ptr(), kv1_b=kb.data_ptr(), ctx=ctx2.data_ptr(), batch=B, h=H2, w=W2, cd=cd,
+                dim=dim, heads=8)
+    kv2 = F.conv2d(F.conv2d(c2, kv0, None, padding=1, groups=cd), kv1, kb)
+    k2, v2 = kv2.chunk(2, dim=1)
+    ref2 = torch.einsum("bhdn,bhen->bhde", k2.softmax(dim=-1).reshape(B, 8, d, H2 * W2), v2.reshape(B, 8, d, H2 * W2))
+    assert rel_err(ctx2, ref2) < 1e-4
     weff = torch.zeros(B, o, dim, dtype=torch.bfloat16, device=DEV)
     scale = 1 / math.sqrt(d)
     _lib.launch("ddif_fwm_weff_t", stream(), ctx=ctx.data_ptr(), w_out=wout.data_ptr(), weff=weff.data_ptr(), batch=B, o=o, dim=dim, heads=8,

@@ -61,7 +61,7 @@ KIND_OF_STRUCT = {
     "ddif_dpmpp_step_t": "DDIF_OP_DPMPP_STEP", "ddif_q_sample_t": "DDIF_OP_Q_SAMPLE", "ddif_cond_assemble_t": "DDIF_OP_COND_ASSEMBLE",
     "ddif_randn_t": "DDIF_OP_RANDN", "ddif_axpby_clip_t": "DDIF_OP_AXPBY_CLIP", "ddif_dpm_single_t": "DDIF_OP_DPM_SINGLE",
     "ddif_loss_t": "DDIF_OP_LOSS", "ddif_dpm_err_t": "DDIF_OP_DPM_ERR", "ddif_attn_block_t": "DDIF_OP_ATTN_BLOCK", "ddif_multi_tensor_t": "DDIF_OP_MULTI_TENSOR", "ddif_axpby_t": "DDIF_OP_AXPBY", "ddif_metrics_t": "DDIF_OP_METRICS", "ddif_tile_t": "DDIF_OP_TILE",
-    "ddif_wavelet_cond_t": "DDIF_OP_WAVELET_COND",
+    "ddif_wavelet_cond_t": "DDIF_OP_WAVELET_COND", "ddif_wgrad_t": "DDIF_OP_WGRAD", "ddif_colsum_t": "DDIF_OP_COLSUM",
 }
 
 _lib = None
@@ -134,7 +134,7 @@ def load() -> ctypes.CDLL:
     lib.ddif_plan_profile.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     for name in ("ddif_haar_dwt2_f32", "ddif_haar_idwt2_f32", "ddif_cond_assemble_f32", "ddif_ddpm_step_f32",
                  "ddif_ddim_step_f32", "ddif_dpmpp_step_f32", "ddif_q_sample_f32", "ddif_conv_igemm_bf16", "ddif_dpm_single_f32", "ddif_loss_f32", "ddif_dpm_err_f32", "ddif_multi_tensor_f32",
-                 "ddif_metrics_f32", "ddif_tile_f32", "ddif_wavelet_cond_f32"):
+                 "ddif_metrics_f32", "ddif_tile_f32", "ddif_wavelet_cond_f32", "ddif_wgrad_bf16", "ddif_colsum_bf16"):
         getattr(lib, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     _lib = lib
     return lib

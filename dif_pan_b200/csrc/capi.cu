@@ -46,6 +46,8 @@ union OpParams {
   ddif_metrics_t metrics;
   ddif_tile_t tile;
   ddif_wavelet_cond_t wavelet_cond;
+  ddif_wgrad_t wgrad;
+  ddif_colsum_t colsum;
 };
 
 static size_t params_size(int kind) {
@@ -81,6 +83,8 @@ static size_t params_size(int kind) {
     case DDIF_OP_METRICS: return sizeof(ddif_metrics_t);
     case DDIF_OP_TILE: return sizeof(ddif_tile_t);
     case DDIF_OP_WAVELET_COND: return sizeof(ddif_wavelet_cond_t);
+    case DDIF_OP_WGRAD: return sizeof(ddif_wgrad_t);
+    case DDIF_OP_COLSUM: return sizeof(ddif_colsum_t);
     default: return 0;
   }
 }
@@ -127,6 +131,8 @@ static int dispatch(const Op& op, cudaStream_t s) {
     case DDIF_OP_METRICS: return launch_metrics(op.p.metrics, s);
     case DDIF_OP_TILE: return launch_tile(op.p.tile, s);
     case DDIF_OP_WAVELET_COND: return launch_wavelet_cond(op.p.wavelet_cond, s);
+    case DDIF_OP_WGRAD: return launch_wgrad(op.p.wgrad, s);
+    case DDIF_OP_COLSUM: return launch_colsum(op.p.colsum, s);
     default: return DDIF_ERR_ARG;
   }
 }
@@ -289,6 +295,8 @@ int ddif_multi_tensor_f32(const ddif_multi_tensor_t* p, ddif_stream_t s) { retur
 int ddif_metrics_f32(const ddif_metrics_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_METRICS, p, s); }
 int ddif_tile_f32(const ddif_tile_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_TILE, p, s); }
 int ddif_wavelet_cond_f32(const ddif_wavelet_cond_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_WAVELET_COND, p, s); }
+int ddif_wgrad_bf16(const ddif_wgrad_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_WGRAD, p, s); }
+int ddif_colsum_bf16(const ddif_colsum_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_COLSUM, p, s); }
 int ddif_q_sample_f32(const ddif_q_sample_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_Q_SAMPLE, p, s); }
 int ddif_conv_igemm_bf16(const ddif_gemm_t* p, ddif_stream_t s) { return ddif_launch(DDIF_OP_GEMM, p, s); }
 

@@ -58,5 +58,7 @@ int launch_axpby(const ddif_axpby_t& p, cudaStream_t s);
 int launch_metrics(const ddif_metrics_t& p, cudaStream_t s);
 int launch_tile(const ddif_tile_t& p, cudaStream_t s);
 int launch_wavelet_cond(const ddif_wavelet_cond_t& p, cudaStream_t s);
+int launch_wgrad(const ddif_wgrad_t& p, cudaStream_t s);    // backward.cu
+int launch_colsum(const ddif_colsum_t& p, cudaStream_t s);
 
 }  // namespace ddif

@@ -266,58 +266,62 @@ class GaussianDiffusion(nn.Module):
         return out
 
     def p_losses(self, x_start, noise=None, cond=None, *, t=None, self_cond_draw=None):
-        """Training objective, FORWARD evaluation (diffusion_ddpm_pan.py:692-766): t ~ U{0..T-1}, x_t = q_sample, the
-        optional no-grad self-conditioning pass (probability 0.5, Python `random.random()` like the reference, :702),
-        the denoiser, then mean(loss_func(target, prediction)) * mean(p2_loss_weight[t]) and recon_x0.  q_sample, the x0 / v
-        conversions and the weighted L1 / L2 reduction are fused CUDA kernels.  Returns (loss, recon_x0) like the
-        reference; there is no autograd graph (the CUDA UNet has no backward yet), so this serves validation-loss
-        evaluation and parity of the objective, not optimisation.  `t` / `self_cond_draw` pin the two random draws
-        for tests."""
+        """Training objective (diffusion_ddpm_pan.py:692-766): t ~ U{0..T-1}, x_t = q_sample, the optional no-grad self-conditioning
+        pass (probability 0.5, Python `random.random()` like the reference, :702), the denoiser, then
+        mean(loss_func(target, prediction)) * mean(p2_loss_weight[t]) and recon_x0.  Returns (loss, recon_x0) like the reference.
+        With autograd enabled and a denoiser whose parameters require grad, `loss` carries the graph (`loss.backward()` reaches the
+        UNet's parameters through training.py); otherwise the objective is evaluated forward-only with the fused loss kernel.
+        `t` / `self_cond_draw` pin the two random draws for tests."""
         if self.loss_type not in ("l1", "l2"):
             raise NotImplementedError("loss_type='l1ssim' is not on the CUDA path")
         if not x_start.is_cuda:
             raise RuntimeError("dif_pan_b200 kernels run on CUDA only (no CPU fallback)")
-        if torch.is_grad_enabled() and getattr(self.model, "training", False) and any(p.requires_grad for p in self.model.parameters()):
-            raise NotImplementedError("dif_pan_b200: p_losses evaluates the objective forward-only; call model.eval() / torch.no_grad() "
-                                      "(training backward is not implemented on the CUDA path)")
+        want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters())
         b = x_start.shape[0]
         dev = x_start.device
-        x_start = x_start.to(torch.float32).contiguous()
+        x_start = x_start.detach().to(torch.float32).contiguous()
         if t is None:
             t = torch.randint(0, self.num_timesteps, (b,), device=dev).long()
         if noise is None:
             noise = device_randn(x_start.shape, dev, self.seed, 1 << 41)
-        noise = noise.to(torch.float32).contiguous()
-        x_noisy = self.q_sample(x_start, t, noise)
+        noise = noise.detach().to(torch.float32).contiguous()
         ex = lambda buf: buf.gather(-1, t)
         with torch.no_grad():
+            x_noisy = self.q_sample(x_start, t, noise)
             x_self_cond = None
             draw = random.random() if self_cond_draw is None else self_cond_draw
             if self.self_condition and draw < 0.5:
                 mo = self.model(x_noisy, t, cond=cond, self_cond=None) if self.conditional else self.model(x_noisy, t, self_cond=None)
+                mo = mo.to(torch.float32).contiguous()
                 if self.pred_mode == "noise":
                     x_self_cond = self._axpby(ex(self.sqrt_recip_alphas_cumprod), x_noisy, -ex(self.sqrt_recipm1_alphas_cumprod), mo)
                 elif self.pred_mode == "x_start":
                     x_self_cond = mo
                 else:
                     x_self_cond = self._axpby(ex(self.sqrt_alphas_cumprod), x_noisy, -ex(self.sqrt_one_minus_alphas_cumprod), mo)
+        with torch.set_grad_enabled(want_grad):
             if self.conditional:
                 pred = self.model(x_noisy, t, cond=cond, self_cond=x_self_cond)
             else:
                 pred = self.model(x_noisy, t, self_cond=x_self_cond)
-            pred = pred.to(torch.float32).contiguous()
+        with torch.no_grad():
+            pd = pred.detach().to(torch.float32).contiguous()
             if self.pred_mode == "noise":
-                recon = self._axpby(ex(self.sqrt_recip_alphas_cumprod), x_noisy, -ex(self.sqrt_recipm1_alphas_cumprod), pred)
+                recon = self._axpby(ex(self.sqrt_recip_alphas_cumprod), x_noisy, -ex(self.sqrt_recipm1_alphas_cumprod), pd)
                 target = noise
             elif self.pred_mode == "x_start":
-                recon, target = pred, x_start
+                recon, target = pd, x_start
             else:
                 target = self._axpby(ex(self.sqrt_alphas_cumprod), noise, -ex(self.sqrt_one_minus_alphas_cumprod), x_start)
                 recon = self._axpby(ex(self.sqrt_alphas_cumprod), x_noisy, -ex(self.sqrt_one_minus_alphas_cumprod), target)
-            # nn.L1Loss() / nn.MSELoss() reduce to a scalar first (:189-193), so the reference's objective is
-            # mean(l) * mean_b(p2_loss_weight[t_b]) (:759-762), not a per-sample weighting
+        # nn.L1Loss() / nn.MSELoss() reduce to a scalar first (:189-193), so the reference's objective is
+        # mean(l) * mean_b(p2_loss_weight[t_b]) (:759-762), not a per-sample weighting
+        if want_grad:
+            l = (target - pred).abs().mean() if self.loss_type == "l1" else ((target - pred) ** 2).mean()
+            return (l * ex(self.p2_loss_weight)).mean(), recon
+        with torch.no_grad():
             acc = torch.zeros(1, dtype=torch.float64, device=dev)
-            _lib.launch("ddif_loss_t", _stream(dev), a=target.data_ptr(), b=pred.data_ptr(), weight=None, out=acc.data_ptr(),
+            _lib.launch("ddif_loss_t", _stream(dev), a=target.data_ptr(), b=pd.data_ptr(), weight=None, out=acc.data_ptr(),
                         batch=b, chw=x_start[0].numel(), squared=0 if self.loss_type == "l1" else 1)
             loss = ((acc / float(x_start.numel())).to(torch.float32) * ex(self.p2_loss_weight)).mean()
         return loss, recon

@@ -12,7 +12,7 @@ launches (include/ddif_b200.h) over NHWC bf16 activations:
     the 4-level cond pyramid) is computed ONCE per `cond` and cached.
 
 There is no PyTorch / CPU fallback: without the CUDA library or a CUDA device, forward raises.
-Training-mode forward/backward is not implemented in this round (inference path only).
+In train() mode, or when an autograd graph is requested, forward goes through training.py (first slice of the training path).
 """
 from __future__ import annotations
 
@@ -204,13 +204,15 @@ class UNetSR3(nn.Module):
         return rt
 
     def forward(self, x, time, cond=None, self_cond=None):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("dif_pan_b200.UNetSR3: training-mode forward/backward is not implemented yet "
-                                      "(inference kernels only); call .eval() and torch.no_grad()")
         if cond is None:
             raise ValueError("UNetSR3.forward needs cond=[lms, pan, wavelets] (sr3_dwt.py:197,214)")
         if not x.is_cuda:
             raise RuntimeError("dif_pan_b200.UNetSR3 has no CPU fallback; inputs must be CUDA tensors")
+        if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            # train() mode (Dropout / DropPath active, like the reference's nn.Module) or an autograd graph is wanted: the training path
+            # (training.py: convolutions forward / dgrad / wgrad on the CUDA kernels).  Sampling = .eval() under torch.no_grad().
+            from . import training
+            return training.unet_forward(self, x, time, cond, self_cond)
         B, C, H, W = x.shape
         rt = self.runtime(B, H, W)
         rt.set_cond(cond)

@@ -60,6 +60,9 @@ enum ddif_op_kind {
   DDIF_OP_TILE = 27,         /* scene -> patch batch (gather) and patch batch -> scene (overlap-averaged stitch) */
   DDIF_OP_ATTN_BLOCK = 30,   /* whole SelfAttention block at 64 tokens: GN + qkv + attention + out + residual   sr3_dwt.py:330-360 */
   DDIF_OP_MULTI_TENSOR = 31, /* one launch over a LIST of tensors: EMA, copy, sum of squares, scale, clamp, AdamW   utils/optim_utils.py:24-58, utils/misc.py:25-36 */
+  DDIF_OP_WGRAD = 32,        /* convolution weight gradient: dW[tap][o][i] += sum_p dY[p][o] X[p + tap][i]  (autograd of F.conv2d in p_losses().backward(),
+                                diffusion_ddpm_pan.py:692-766, diffusion_engine.py:233) */
+  DDIF_OP_COLSUM = 33,       /* per-channel sum of a gradient tensor over all pixels (bias gradient) or per sample (FiLM gradient, sr3_dwt.py:241-258) */
   DDIF_OP_DPM_ERR = 29,      /* adaptive DPM-Solver error estimate per sample                      dpm_solver.py:1003-1006 */
   DDIF_OP_WAVELET_COND = 28  /* raw lms, pan -> cond in one pass: Haar DWT, /division, channel order, bilinear up, concat
                                 dataset/pan_dataset.py:73-142, dataset/hisr.py:48-59, diffusion_engine.py:221-228 */
@@ -233,6 +236,15 @@ typedef struct { float* x; float* ll; float* ch; float* cv; float* cd; int64_t p
 /* cond[b] = cat(lms[b] (c), pan[b] (p), bilinear_up(wavelets[b] (cw), h x w)); wavelets at h/2 x w/2 (any size) */
 typedef struct { const float* lms; const float* pan; const float* wav; float* cond; int64_t batch, c, p, cw, h, w, wh, ww; } ddif_cond_assemble_t;
 typedef struct { float* out; int64_t n, seed, offset; } ddif_randn_t;
+/* Weight gradient of a convolution (3x3 pad 1 | 1x1; stride 1 | 2) from NHWC bf16 tensors: x [batch, in_h, in_w, x_ld] (first cin channels),
+ * dy [batch, out_h, out_w, dy_ld] (first cout channels); dw: fp32 [taps][cout][cin], ACCUMULATED (the caller zeroes it), tap = ky*3+kx.
+ * per_sample = 1 (1x1 only): dw is [batch][cout][cin], one gradient per sample (the FWM per-sample attn_out weights W_eff). */
+typedef struct {
+  const void* x; int64_t x_ld, cin; const void* dy; int64_t dy_ld, cout; float* dw;
+  int64_t batch, in_h, in_w, out_h, out_w, taps, stride, per_sample;
+} ddif_wgrad_t;
+/* out[g][c] += sum over the pixels of group g of dy[p][c]; dy NHWC bf16 [batch, hw, ld]; per_sample = 0: one group (out[c]); 1: out[batch][c]. */
+typedef struct { const void* dy; float* out; int64_t batch, hw, c, ld, per_sample; } ddif_colsum_t;
 typedef struct { const float* x; const float* cond; float* out; int64_t batch, c, hw, cond_c; double lo, hi; } ddif_axpby_clip_t;
 
 /* ---- entry points ---------------------------------------------------------------------------------------- */
@@ -280,6 +292,8 @@ int ddif_loss_f32(const ddif_loss_t* p, ddif_stream_t s);
 int ddif_metrics_f32(const ddif_metrics_t* p, ddif_stream_t s);
 int ddif_tile_f32(const ddif_tile_t* p, ddif_stream_t s);
 int ddif_wavelet_cond_f32(const ddif_wavelet_cond_t* p, ddif_stream_t s);
+int ddif_wgrad_bf16(const ddif_wgrad_t* p, ddif_stream_t s);
+int ddif_colsum_bf16(const ddif_colsum_t* p, ddif_stream_t s);
 
 #ifdef __cplusplus
 }

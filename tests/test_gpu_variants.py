@@ -124,10 +124,9 @@ def test_p_losses_with_cuda_unet_and_random_draws():
     assert _rel(recon.cpu(), ref_recon) <= 1.5e-2
     loss2, _ = dif(x0, "train", cond=d["cond"].to(DEV))  # internal draws
     assert torch.isfinite(loss2)
-    net.train()
-    with torch.enable_grad(), pytest.raises(NotImplementedError):
-        dif(x0, "train", cond=d["cond"].to(DEV))
-    net.eval()
+    with torch.enable_grad():  # with autograd on, the loss carries a graph (training.py; gradient parity: tests/test_gpu_training.py)
+        loss3, _ = dif(x0, "train", noise=nz.to(DEV), cond=d["cond"].to(DEV), t=t.to(DEV), self_cond_draw=0.2)
+        assert loss3.requires_grad and abs(float(loss3) - float(loss)) <= 1e-2 * abs(float(loss))
 
 
 # ---- metrics -------------------------------------------------------------------------------------------------------------------

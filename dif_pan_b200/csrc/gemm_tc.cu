@@ -42,6 +42,15 @@ struct alignas(64) GemmKParams {
   int groups;              // epilogue warp groups working on different tiles (generic: 2 or 4; lean: 1)
   int naccs;               // TMEM accumulators (generic: = groups; lean: 2)
   int lean;                // kLean* flags of the compile-time epilogue, 0 = generic
+  // kLeanOpTma: the epilogue operands of a tile (CSM modulation maps scale | shift, or the residual) are brought into a shared-memory ring by
+  // the TMA producer instead of per-thread global loads (see the enum below)
+  CUtensorMap tmOp;        // mod: [B, H, W, 2N] box 64 ch x tw x th x tn (SWIZZLE_128B); residual: [B, H, W, res_ld] box N ch x tw x th x tn
+  int op_stages;           // ring depth (multiple of `groups`), 0 = operands via global loads
+  int op_slabs;            // TMA boxes per tile: mod 2N / 64, residual 1
+  int op_span;             // bytes per row of one slab: 128 (SWIZZLE_128B), 64 (SWIZZLE_64B) or 32 (SWIZZLE_32B)
+  int op_chan0;            // first channel of the residual inside its tensor (n_tile * bn is added)
+  uint32_t op_bytes;       // bytes of one ring slot = op_slabs * 128 rows * op_span
+  uint32_t op_off, bar_off;  // shared-memory offsets of the operand ring and of the barriers
   const float* bias;
   const float* film;
   int film_ld;
@@ -74,7 +83,20 @@ __device__ __forceinline__ void gemm_range(int num_m_tiles, int& base, int& coun
 // the NEXT tile's residual / modulation vectors requested before the current tile is processed (the generic path exposed
 // one L2/DRAM round trip per tile and chunk: 80 us instead of 30 for the 64x64-level 1x1 convs,
 // profiles/r01s4_gemm1x1_ablation.txt).
-enum : int { kLean = 1, kLeanMod = 2, kLeanRes = 4, kLeanStats = 8 };
+// F & 16 (kLeanOpTma, round 2): with kLeanMod / kLeanRes the operands of a tile are NOT fetched by the epilogue threads (32 bytes per thread at a
+// 64-256 byte pixel pitch, one tile ahead: ncu showed the epilogue warps stalled on exactly those loads -- long_scoreboard 4.3 per issue,
+// DRAM at 38 % -- profiles/r02_ncu_prof_igemm_xconv_*) but by the TMA producer, as swizzled boxes into a 4-deep shared-memory ring
+// (full / empty mbarriers per slot, one slot per M tile); the epilogue reads them with conflict-free LDS.128.
+enum : int { kLean = 1, kLeanMod = 2, kLeanRes = 4, kLeanStats = 8, kLeanOpTma = 16 };
+// shared-memory address of 16-byte chunk `chunk` of row `row` inside a TMA box whose rows are `span` bytes (hardware swizzle of that span)
+__device__ __forceinline__ uint32_t op_addr(uint32_t base, int row, int chunk, int span) {
+  const int sw = span == 128 ? (row & 7) : (span == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+  return base + (uint32_t)(row * span) + ((uint32_t)(chunk ^ sw) << 4);
+}
+__device__ __forceinline__ void lds256(uint32_t a0, uint32_t a1, uint32_t* r) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a0) : "memory");
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(a1) : "memory");
+}
 
 template <int F>
 struct LeanOperands {
@@ -93,12 +115,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
   const int b_slot_bytes = p.bn * p.span;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.stages * a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.b_slots * b_slot_bytes);
+  uint8_t* smem_op = smem + p.op_off;                  // [op_stages][op_bytes] epilogue operand ring (kLeanOpTma), 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tmem_full_bar = bars + 2 * p.stages;       // [4]
   uint64_t* tmem_empty_bar = bars + 2 * p.stages + 4;  // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 8);
+  uint64_t* op_full = bars + 2 * p.stages + 8;         // [4] operand slot landed
+  uint64_t* op_empty = bars + 2 * p.stages + 12;       // [4] operand slot read by the tile group's warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +138,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
       tma_prefetch_desc(&p.tmA[s]);
       tma_prefetch_desc(&p.tmB[s]);
     }
+    if (p.op_stages) tma_prefetch_desc(&p.tmOp);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -123,6 +149,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
       for (int i = 0; i < p.naccs; ++i) {
         mbar_init(&tmem_full_bar[i], 1);
         mbar_init(&tmem_empty_bar[i], kEpiWarps / p.groups);  // one arrive per epilogue warp of the group that drains it
+      }
+      for (int i = 0; i < p.op_stages; ++i) {
+        mbar_init(&op_full[i], 1);
+        mbar_init(&op_empty[i], kEpiWarps / p.groups);
       }
       mbar_fence_init();
     }
@@ -148,6 +178,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
       const uint32_t tx_ab = a_bytes + (uint32_t)b_slot_bytes;
       const uint32_t nstages = (uint32_t)p.stages;
       uint32_t stage = 0, phase = 0;
+      uint32_t ostage = 0, ophase = 0;
       uint8_t* a_dst = smem_a;
       bool first = true;
       int img_grp = tile_base / tiles_per_img;
@@ -160,6 +191,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
         const int n0 = img_grp * p.tn;
         const bool load_b = !p.resident_b || first;
         const uint32_t tx_bytes = load_b ? tx_ab : a_bytes;
+        if (p.op_stages) {  // this tile's epilogue operands (stride 1: output pixel box == the box of the operand tensor)
+          mbar_wait(&op_empty[ostage], ophase ^ 1u);
+          mbar_expect_tx(&op_full[ostage], (uint32_t)(p.op_slabs * p.a_rows * p.op_span));
+          uint8_t* dst = smem_op + (size_t)ostage * p.op_bytes;
+          const uint32_t slab_bytes = 128u * (uint32_t)p.op_span;
+          for (int sl = 0; sl < p.op_slabs; ++sl)
+            tma_load_4d(&p.tmOp, &op_full[ostage], dst + (size_t)sl * slab_bytes, p.op_chan0 + n_tile * p.bn + sl * 64, tx0, ty0, n0);
+          if (++ostage == (uint32_t)p.op_stages) { ostage = 0; ophase ^= 1u; }
+        }
         int j = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const int ntaps = p.taps[s], nkc = p.kchunks[s];
@@ -253,6 +293,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
     const int sub = (warp - 2) >> 2;
     if constexpr ((F & kLean) != 0) {
       constexpr bool kMod = (F & kLeanMod) != 0, kRes = (F & kLeanRes) != 0, kStats = (F & kLeanStats) != 0;
+      constexpr bool kOpTma = (F & kLeanOpTma) != 0 && (kMod || kRes);
       // N <= 32 needs only 1-2 of the 4 column groups: the others form further TILE groups (group g drains accumulator g for the
       // CTA's tiles g, g + groups, ...), so two (four) tiles' wait -> tcgen05.ld -> math -> store chains overlap instead of running
       // back to back (a single group left the 64x64-level 1x1 convs latency-bound at ~3400 cycles per 128 x 32 tile).
@@ -292,18 +333,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
         }
       };
       int m_tile = tile_base + grp;
-      if (m_tile < tile_end) {
+      if (!kOpTma && m_tile < tile_end) {
         nxt_ok = locate(m_tile, nxt_pix, nxt_b);
         fetch(nxt, nxt_pix, nxt_ok);
       }
+      const uint32_t op_base = smem_u32(smem_op), op_mask = (uint32_t)p.op_stages - 1u, op_shift = p.op_stages == 4 ? 2u : 1u;
+      const uint32_t op_slab_bytes = 128u * (uint32_t)p.op_span;
       for (uint32_t tcount = 0; m_tile < tile_end; m_tile += step, ++tcount) {
-        const LeanOperands<F> cur = nxt;
-        const bool row_ok = nxt_ok;
-        const size_t pix = nxt_pix;
-        const int b = nxt_b;
-        if (m_tile + step < tile_end) {
-          nxt_ok = locate(m_tile + step, nxt_pix, nxt_b);
-          fetch(nxt, nxt_pix, nxt_ok);  // next tile's operands travel while this tile is processed
+        LeanOperands<F> cur;
+        bool row_ok;
+        size_t pix;
+        int b;
+        if constexpr (kOpTma) {
+          row_ok = locate(m_tile, pix, b);
+        } else {
+          cur = nxt;
+          row_ok = nxt_ok;
+          pix = nxt_pix;
+          b = nxt_b;
+          if (m_tile + step < tile_end) {
+            nxt_ok = locate(m_tile + step, nxt_pix, nxt_b);
+            fetch(nxt, nxt_pix, nxt_ok);  // next tile's operands travel while this tile is processed
+          }
         }
         float fv[16];
         if (p.film) {
@@ -326,6 +377,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        uint32_t op_slot = 0;
+        if constexpr (kOpTma) {  // this tile's operands: slot (tile index in the CTA's range) % op_stages of the ring the producer fills
+          const uint32_t jt = (uint32_t)(m_tile - tile_base);
+          op_slot = jt & op_mask;
+          mbar_wait(&op_full[op_slot], (jt >> op_shift) & 1u);
+          if (row_ok) {
+            const uint32_t ob = op_base + op_slot * p.op_bytes;
+            if (kMod) {  // channels [ng, ng + 16) of scale and [N + ng, N + ng + 16) of shift inside the 64-channel slabs
+              const int g1 = p.n_valid + ng;
+              lds256(op_addr(ob + (uint32_t)(ng >> 6) * op_slab_bytes, row, (ng & 63) >> 3, 128), op_addr(ob + (uint32_t)(ng >> 6) * op_slab_bytes, row, ((ng & 63) >> 3) + 1, 128), cur.sc);
+              lds256(op_addr(ob + (uint32_t)(g1 >> 6) * op_slab_bytes, row, (g1 & 63) >> 3, 128), op_addr(ob + (uint32_t)(g1 >> 6) * op_slab_bytes, row, ((g1 & 63) >> 3) + 1, 128), cur.sh);
+            }
+            if (kRes) lds256(op_addr(ob, row, ng >> 3, p.op_span), op_addr(ob, row, (ng >> 3) + 1, p.op_span), cur.res);
+          }
+        }
         float s1 = 0.f, s2 = 0.f;
         if (row_ok) {
           float v[16];
@@ -368,6 +434,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) conv_igemm_tc_kernel(const __
 #ifndef DDIF_VAR_G_NO_STG
           stg256(p.out + pix * (size_t)p.out_ld + ng, w);
 #endif
+        }
+        if constexpr (kOpTma) {  // the operand values have been consumed: hand the slot back to the producer
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&op_empty[op_slot]);
         }
 #ifndef DDIF_VAR_G_NO_STATRED
         if (kStats && active) {  // all rows of one warp belong to one sample
@@ -472,6 +542,10 @@ static IgemmKernel igemm_kernel(int f) {
     case kLean | kLeanStats: return conv_igemm_tc_kernel<kLean | kLeanStats>;
     case kLean | kLeanMod | kLeanStats: return conv_igemm_tc_kernel<kLean | kLeanMod | kLeanStats>;
     case kLean | kLeanRes | kLeanStats: return conv_igemm_tc_kernel<kLean | kLeanRes | kLeanStats>;
+    case kLean | kLeanOpTma | kLeanMod: return conv_igemm_tc_kernel<kLean | kLeanOpTma | kLeanMod>;
+    case kLean | kLeanOpTma | kLeanRes: return conv_igemm_tc_kernel<kLean | kLeanOpTma | kLeanRes>;
+    case kLean | kLeanOpTma | kLeanMod | kLeanStats: return conv_igemm_tc_kernel<kLean | kLeanOpTma | kLeanMod | kLeanStats>;
+    case kLean | kLeanOpTma | kLeanRes | kLeanStats: return conv_igemm_tc_kernel<kLean | kLeanOpTma | kLeanRes | kLeanStats>;
     default: return nullptr;
   }
 }
@@ -493,7 +567,7 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   if (!enc) return DDIF_ERR_DRIVER;
   static bool smem_attr_set = false;  // outside any stream capture: gemm_prepare runs at plan-build time
   if (!smem_attr_set) {
-    for (int f = 0; f < 16; ++f) {
+    for (int f = 0; f < 32; ++f) {
       IgemmKernel k = igemm_kernel(f);
       if (k) DDIF_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
@@ -541,6 +615,26 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   const bool lean = bn <= 64 && g.n_pad == bn && g.n_valid % 16 == 0 && g.out && !g.out_nchw && g.out_ld % 16 == 0 &&
                     (!g.residual || g.res_ld % 16 == 0) && (!g.film || g.film_ld % 4 == 0) && !(g.mod && g.residual);
   p.lean = lean ? (kLean | (g.mod ? kLeanMod : 0) | (g.residual ? kLeanRes : 0) | (g.stats ? kLeanStats : 0)) : 0;
+  // epilogue operands through a TMA-fed shared-memory ring (kLeanOpTma): stride-1 convs whose operand rows are whole swizzle spans
+  int op_slot_bytes = 0;
+#ifndef DDIF_VAR_G_NO_OPTMA  // A/B build: per-thread global loads one tile ahead (round 1)
+  if (lean && g.stride == 1 && g.mod && g.n_valid % 32 == 0 && (reinterpret_cast<uintptr_t>(g.mod) & 15u) == 0) {
+    p.op_slabs = (int)(2 * g.n_valid / 64);
+    p.op_span = 128;
+  }
+#ifdef DDIF_VAR_G_RES_OPTMA  // the residual through the same ring: implemented and correct, but a wash in a same-box A/B (64 -> 32 @64^2 61.4 -> 55.7 us,
+  // 32 -> 32 @64^2 44.6 -> 53.5 us, the UNet's attn_out GEMMs 0.545 -> 0.538 ms per step), so the product keeps the one-tile-ahead global loads
+  else if (lean && g.stride == 1 && g.residual && !g.mod && (bn == 16 || bn == 32 || bn == 64) && g.n_valid == bn &&
+           (reinterpret_cast<uintptr_t>(g.residual) & 15u) == 0) {
+    p.op_slabs = 1;
+    p.op_span = bn * 2;
+  }
+#endif
+  if (p.op_slabs) {
+    op_slot_bytes = p.op_slabs * 128 * p.op_span;
+    p.lean |= kLeanOpTma;
+  }
+#endif
   // lean: N = 64 (48) -> all 16 warps on one tile, two alternating accumulators; N = 32 -> 2 tile groups; N = 16 -> 4 tile groups
   p.groups = lean ? (bn <= 16 ? 4 : (bn <= 32 ? 2 : 1)) : (4 * bn <= 512 ? 4 : 2);
   p.naccs = lean ? (p.groups == 1 ? 2 : p.groups) : p.groups;
@@ -552,7 +646,13 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   int total_iters = 0;
   for (int s = 0; s < g.nseg; ++s) total_iters += (int)(g.taps[s] * (g.a_c[s] / bk));
   const int a_stage = 128 * p.span, b_slot = bn * p.span;
-  const int budget = 200 * 1024;
+  // operand ring: 4 slots when they leave >= 4 A stages, else 2 (the slot count must be a multiple of the tile groups sharing the ring)
+  if (op_slot_bytes) {
+    p.op_stages = (200 * 1024 - 4 * op_slot_bytes >= 4 * (a_stage + b_slot)) ? 4 : 2;
+    if (p.op_stages < p.groups) p.op_stages = p.groups;
+    if (p.op_stages != 2 && p.op_stages != 4) return DDIF_ERR_SHAPE;
+  }
+  const int budget = 200 * 1024 - p.op_stages * op_slot_bytes;
   // weights of this N tile stay resident in smem when they fit next to >= 4 A stages (never for per-sample weights)
   p.resident_b = (!per_sample && (int64_t)total_iters * b_slot + 4 * a_stage <= budget) ? 1 : 0;
   int stages;
@@ -571,7 +671,23 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   if (!p.resident_b) p.b_slots = stages;
   p.stages = stages;
   p.num_m_tiles = p.tiles_x * p.tiles_y * (int)ceil_div(B, tn);
-  L.smem_bytes = stages * a_stage + p.b_slots * b_slot + (2 * stages + 10) * 8 + 1024;
+  p.op_off = (uint32_t)((stages * a_stage + p.b_slots * b_slot + 1023) & ~1023);
+  p.op_bytes = (uint32_t)op_slot_bytes;
+  p.bar_off = p.op_off + (uint32_t)(p.op_stages * op_slot_bytes);
+  L.smem_bytes = (int)p.bar_off + (2 * stages + 18) * 8 + 1024;
+  if (p.op_stages) {  // tensor map of the epilogue operand: pixel box of one M tile, rows = tw * th * tn in the TMEM lane order
+    const bool is_mod = g.mod != nullptr;
+    const cuuint64_t ch = is_mod ? (cuuint64_t)(2 * g.n_valid) : (cuuint64_t)g.n_valid;
+    const cuuint64_t ld = is_mod ? ch : (cuuint64_t)g.res_ld;
+    cuuint64_t dims[4] = {ch, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)(p.op_span / 2), (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&p.tmOp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(is_mod ? g.mod : g.residual), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_span(p.op_span), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return DDIF_ERR_DRIVER;
+    p.op_chan0 = 0;
+  }
   const int sms = ddif_sm_count();
   L.grid_y = (int)(g.n_pad / bn);
   const int gx = (sms + L.grid_y - 1) / L.grid_y;  // persistent: ~one CTA per SM in total

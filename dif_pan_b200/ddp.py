@@ -26,6 +26,9 @@ class GradientAllReducer:
         self._pending: List[int] = []
         self._expected: List[int] = []
         self._work = []
+        # False: the hooks do nothing and finish() reduces every bucket after backward (no overlap) -- for CUDA-graph replay of the
+        # backward pass (training.GraphedLossStep), where Python hooks do not run
+        self.hooks_enabled = True
         cur, cur_bytes = [], 0
         groups = []
         for p in reversed(self.params):                       # gradients become final roughly back to front
@@ -58,6 +61,8 @@ class GradientAllReducer:
         self._work = []
 
     def _hook(self, p: torch.nn.Parameter) -> None:
+        if not self.hooks_enabled:
+            return
         bi = self._bucket_of[p]
         if p.grad.data_ptr() < self.buckets[bi].data_ptr() or p.grad.data_ptr() >= self.buckets[bi].data_ptr() + self.buckets[bi].numel() * 4:
             raise RuntimeError("a gradient was re-allocated outside its bucket (zero_grad(set_to_none=True)?): use GradientAllReducer.zero_grad()")

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pred-mode", default="x_start", choices=["x_start", "noise"])
+    ap.add_argument("--graph", action="store_true", help="replay the forward + backward from CUDA graphs (training.GraphedLossStep)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -52,15 +53,24 @@ def main():
     x0, cond = rep(d["hr"] - d["lms"]), rep(d["cond"])
     ev = lambda: torch.cuda.Event(enable_timing=True)
     split = [0.0, 0.0, 0.0]
+    graphed = None
+    if a.graph:
+        from dif_pan_b200.training import GraphedLossStep
+        red.hooks_enabled = False  # hooks do not run at graph replay: finish() reduces all buckets after the backward graph
+        graphed = GraphedLossStep(dif, x0, cond)
 
     def step(it, timed):
         e = [ev() for _ in range(4)]
         red.zero_grad()
         e[0].record()
-        with torch.enable_grad():
-            loss, _ = dif(x0, cond=cond)
-        e[1].record()
-        loss.backward()
+        if graphed is not None:
+            loss = graphed.run(x0, cond)
+            e[1].record()
+        else:
+            with torch.enable_grad():
+                loss, _ = dif(x0, cond=cond)
+            e[1].record()
+            loss.backward()
         e[2].record()
         red.finish()
         grad_clip(red.params, mode="norm", value=0.003)
@@ -93,7 +103,7 @@ def main():
                               ms_per_step=float(ms), patches_per_s=a.batch * world / float(ms) * 1e3, loss=float(loss),
                               split_ms=dict(forward_and_loss=split[0] / a.steps, backward_with_overlapped_allreduce=split[1] / a.steps,
                                             reduce_wait_clip_adamw_ema=split[2] / a.steps),
-                              grad_bytes_allreduced=red.nbytes if world > 1 else 0, buckets=len(red.buckets),
+                              grad_bytes_allreduced=red.nbytes if world > 1 else 0, buckets=len(red.buckets), cuda_graph=bool(a.graph),
                               note="first slice: dense convolutions (fwd / dgrad / wgrad) on the repo's CUDA kernels, ops between them via torch autograd; "
                                    "host-bound at this batch size")))
     if world > 1:

@@ -35,7 +35,9 @@ static constexpr int kHMaxStat = 1024;
 // Negative results of rounds 1-2, removed from the source (numbers in DESIGN.md section 4.2): a TMA-store epilogue (tile staged in shared
 // memory, cp.async.bulk.tensor store: slower for N >= 64, +4 % for N = 32 -- the staging traffic competes with the tcgen05 operand fetch);
 // fp64 running statistics per thread in shared memory instead of the per-tile warp reduction (same-box A/B: 64 -> 64 @32^2 26.5 -> 29.2 us);
-// letting the MMA warp wait on the TMA barrier of a residual slab itself instead of the transform group's relay (32 -> 32 @64^2 60.9 -> 64.0 us).
+// letting the MMA warp wait on the TMA barrier of a residual slab itself instead of the transform group's relay (32 -> 32 @64^2 60.9 -> 64.0 us);
+// a TMA-fed shared-memory ring for the epilogue-side residual of the N >= 64 layers (one slot per epilogue group, loaded one tile ahead by the
+// group's elected thread): it costs two of the six halo stages of the 64 -> 64 layers and loses (34.9 -> 36.5 us; profiles/r02_halo_*_negative.txt).
 
 struct alignas(64) HaloKParams {
   CUtensorMap tmA[2];  // activations of K segment 0 / 1 (virtual channel concat: torch.cat((x, skip), 1), sr3_dwt.py:212)

@@ -28,6 +28,7 @@ def _model():
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_grad_enabled(True)
     g = torch.Generator().manual_seed(1)
     x, y = torch.randn(8, 3, 8, 8, generator=g), torch.randn(8, 3, 8, 8, generator=g)
     ref = _model()
@@ -60,6 +61,7 @@ def test_two_rank_gloo_gradient_all_reduce():
 
 
 def test_single_process_is_a_no_op():
+    torch.set_grad_enabled(True)   # sibling test modules switch autograd off at import
     net = _model()
     red = GradientAllReducer(net.parameters())
     red.zero_grad()

@@ -28,16 +28,26 @@ namespace ddif {
 static constexpr int kHxfThreads = 256;                    // transform warps 0..7: two groups of 128, alternating stages
 static constexpr int kHxfGroup = kHxfThreads / 2;
 static constexpr int kHEpiWarps = 8;                       // warps 10..17: two groups of 4, one TMEM accumulator each
-static constexpr int kHThreads = kHxfThreads + 64 + 32 * kHEpiWarps + 32;  // + MMA warps 8, 9 + TMA producer warp 18
+#ifdef DDIF_VAR_HALO_2PROD  // tuning build: one TMA producer warp per half-pipeline ring (warps 18, 19)
+static constexpr int kHProducers = 2;
+#else
+static constexpr int kHProducers = 1;
+#endif
+static constexpr int kHThreads = kHxfThreads + 64 + 32 * kHEpiWarps + 32 * kHProducers;  // + MMA warps 8, 9 + TMA producer warp(s) 18(, 19)
 static constexpr int kHW = 10, kHH = 18, kHPx = kHW * kHH;  // halo of an 8 x 16 tile
-static constexpr int kHMaxStages = 8;
+#ifndef DDIF_VAR_HALO_MAX_STAGES  // tuning builds (tools/) pass -DDDIF_VAR_HALO_MAX_STAGES=n
+#define DDIF_VAR_HALO_MAX_STAGES 12
+#endif
+static constexpr int kHMaxStages = DDIF_VAR_HALO_MAX_STAGES;
 static constexpr int kHMaxStat = 1024;
 // Negative results of rounds 1-2, removed from the source (numbers in DESIGN.md section 4.2): a TMA-store epilogue (tile staged in shared
 // memory, cp.async.bulk.tensor store: slower for N >= 64, +4 % for N = 32 -- the staging traffic competes with the tcgen05 operand fetch);
 // fp64 running statistics per thread in shared memory instead of the per-tile warp reduction (same-box A/B: 64 -> 64 @32^2 26.5 -> 29.2 us);
 // letting the MMA warp wait on the TMA barrier of a residual slab itself instead of the transform group's relay (32 -> 32 @64^2 60.9 -> 64.0 us);
 // a TMA-fed shared-memory ring for the epilogue-side residual of the N >= 64 layers (one slot per epilogue group, loaded one tile ahead by the
-// group's elected thread): it costs two of the six halo stages of the 64 -> 64 layers and loses (34.9 -> 36.5 us; profiles/r02_halo_*_negative.txt).
+// group's elected thread): it costs two of the six halo stages of the 64 -> 64 layers and loses (34.9 -> 36.5 us; profiles/r02_halo_*_negative.txt);
+// an L2 prefetch (cp.async.bulk.prefetch.tensor) of the halo box 4 / 8 tiles ahead of the loads: 32 -> 32 @64^2 53.2 -> 59.5 us, 64 -> 32 @64^2
+// 66.5 -> 69.7 / 85.3 us (profiles/r02s2_halo_sweep.txt); K slabs of 32 for the 64-channel layers (more, smaller stages): 26.0 -> 28.6 us.
 
 struct alignas(64) HaloKParams {
   CUtensorMap tmA[2];  // activations of K segment 0 / 1 (virtual channel concat: torch.cat((x, skip), 1), sr3_dwt.py:212)
@@ -863,28 +873,31 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
     if (p.kslab == 64) halo_mma_loop<4>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
     else if (p.kslab == 32) halo_mma_loop<2>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
     else halo_mma_loop<1>(p, smem_u32(smem_a), smem_u32(smem_b), a_full, a_empty, b_full, tmem_full, tmem_empty, tmem_base, my_tiles, w, dts);
-  } else if (warp == 18) {
+  } else if (warp >= 18) {
     // ===================== TMA producer: the halo ring (the resident weights were requested above) =====================
     if (lane == 0) {
       const uint32_t tx = (uint32_t)(kHPx * p.span);
       const uint32_t nst = (uint32_t)p.stages >> 1;  // per ring
+      const bool own_ring = kHProducers == 2;        // this producer feeds ring (warp - 18) only: tiles base + ring, base + ring + 2, ...
       HaloIter it;
       {
         int base, count;
         halo_range(p, base, count);
-        it.init(p, base, 1, base + count);
+        if (own_ring) it.init(p, base + (warp - 18), 2, base + count);
+        else it.init(p, base, 1, base + count);
       }
+      long long* const pts = warp == 18 ? dts : nullptr;
       // (stage, phase) of ring 0 / 1 as scalars: a run-time indexed rs[ring] lives in LOCAL memory (LDL/STL on the producer's
       // dependent chain every tile)
       uint32_t st0 = 0u, ph0 = 0u, st1 = 0u, ph1 = 0u;
-      uint32_t ring = 0;
+      uint32_t ring = own_ring ? (uint32_t)(warp - 18) : 0u;
       int u = 0;
       for (; it.remaining > 0; it.next(), ++u) {
         const uint32_t rs = ring ? st1 : st0, rp = ring ? ph1 : ph0;
         const uint32_t stage = ring * nst + rs;
-        h_ts(dts, 0, u, 0);
+        h_ts(pts, 0, u, 0);
         mbar_wait(&a_empty[stage], rp ^ 1u);
-        h_ts(dts, 0, u, 1);
+        h_ts(pts, 0, u, 1);
 #ifdef DDIF_VAR_NO_TMA
         mbar_arrive(&a_tma[stage]);
 #else
@@ -907,7 +920,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
           if (ns == nst) { ns = 0u; np ^= 1u; }
           if (ring) { st1 = ns; ph1 = np; } else { st0 = ns; ph0 = np; }
         }
-        if (it.slab == p.nslab_t - 1) ring ^= 1u;  // next tile -> other half-pipeline
+        if (!own_ring && it.slab == p.nslab_t - 1) ring ^= 1u;  // next tile -> other half-pipeline
       }
       pdl_trigger();  // all loads of this CTA are in flight: the next kernel's CTAs may take over SMs as ours exit
     }
@@ -1015,13 +1028,23 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
 #ifndef DDIF_VAR_HALO_KSLAB_MAX  // tuning builds (tools/) pass -DDDIF_VAR_HALO_KSLAB_MAX=n
 #define DDIF_VAR_HALO_KSLAB_MAX 64
 #endif
+  // Ring depth (same-box sweep, profiles/r02s2_halo_sweep.txt): with the GroupNorm prologue a stage is held by the transform group and then
+  // by the MMAs, so only `stages - 4` halo tiles are really in flight from L2 / HBM; 12 stages instead of 8 take the 32 -> 32 @64^2 layers from
+  // 61.0 to 52.6 us (residual) / 56.9 to 45.3 us (no residual) and 16 are no better.  Without the prologue (TMA -> MMA directly) deeper rings
+  // LOSE (32 -> 64 + Swish epilogue: 54.3 -> 57.3 us at 12, 59.1 at 16), so those layers keep 8.  (Layers with >= 64 input channels never have
+  // room for more than 6-8 stages next to their resident weights.)
+  int max_stages = (g.gn_stats && !dw) ? kHMaxStages : (kHMaxStages < 8 ? kHMaxStages : 8), kslab_max = DDIF_VAR_HALO_KSLAB_MAX;
+#ifdef DDIF_VAR_HALO_TUNE_ENV  // tuning build only (tools/): sweep the ring depth / K slab from the environment
+  if (const char* e = getenv("DDIF_HALO_STAGES")) max_stages = atoi(e) < kHMaxStages ? atoi(e) : kHMaxStages;
+  if (const char* e = getenv("DDIF_HALO_KSLAB")) kslab_max = atoi(e);
+#endif
   for (int pass = 1; pass < 3; ++pass) {  // pass 1: >= 4 stages; pass 2: accept 2
     for (int split = 1; split <= 4; split *= 2) {
       if (g.n_pad % (16 * split) != 0) break;
       if (split > 1 && (g.out_nchw || dw)) break;
       const int bn = (int)g.n_pad / split;
       for (int kslab = gcd; kslab >= 16; kslab >>= 1) {
-        if (kslab > DDIF_VAR_HALO_KSLAB_MAX && kslab > 16) continue;
+        if (kslab > kslab_max && kslab > 16) continue;
         const int span = kslab * 2;
         const int stage_bytes = (kHPx * span + 1023) & ~1023;
         const int b_total = h.ntap_w * cin * bn * 2;  // independent of the slab size
@@ -1033,7 +1056,7 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
         }
         const int r_total = res_mma ? bn * bn * 2 : 0;  // identity weights: (bn / kslab_r) slots of bn rows x kslab_r columns
         int st = ((227 * 1024 - h.misc - b_total - r_total - 4 * dw_bytes) / stage_bytes) & ~1;
-        if (st > kHMaxStages) st = kHMaxStages;
+        if (st > max_stages) st = max_stages;
         if (st >= (pass <= 1 ? 4 : 2)) {
           h.kslab = kslab; h.nslab = cin / kslab; h.nslab0 = (int)g.a_c[0] / kslab; h.span = span;
           h.stage_bytes = stage_bytes; h.split = split; h.bn = bn; h.b_slot = bn * span; h.stages = st;

@@ -9,6 +9,7 @@ gnflag = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 resflag = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 stflag = int(sys.argv[8]) if len(sys.argv) > 8 else 1
 nrows = int(sys.argv[9]) if len(sys.argv) > 9 else 14
+row0 = int(sys.argv[10]) if len(sys.argv) > 10 else 0
 g=torch.Generator().manual_seed(1)
 x=(torch.randn(B,Cin,H,W,generator=g)).to(DEV); w=(torch.randn(Cout,Cin,3,3,generator=g)*0.03).to(DEV)
 bias=torch.zeros(Cout,device=DEV)
@@ -28,7 +29,7 @@ t0=int(t[t>0].min())
 r=lambda v: (int(v)-t0) if v>0 else -1
 print(f"B={B} {H}x{W} {Cin}->{Cout} gn={gnflag} res={resflag}")
 print("tile | producer: pre-wait issue | xform: pre-wait landed stored arrived | mma: pre-empty got-empty got-a_full committed | epi: got-full tmem-loaded processed done")
-for i in range(nrows):
+for i in range(row0, row0 + nrows):
     print(i, '|', [r(v) for v in t[0,i][:2]], '|', [r(v) for v in t[3,i]], '|', [r(v) for v in t[1,i]], '|', [r(v) for v in t[2,i]])
 n=min(40, int((t[1,:,3]>0).sum()))
 d=[int(t[1,i+1,3]-t[1,i,3]) for i in range(4,n-1)]

@@ -158,12 +158,14 @@ struct HaloIter {
 // ---- transform warps: GroupNorm affine (+Swish) of a landed stage, in place -------------------------------------------
 // Group g (warps 4g..4g+3) serves half-pipeline g: its wait -> LDS -> math -> STS -> fence -> arrive latency chain on one
 // stage overlaps the other group's.
-template <int NCK>
+// SHORT (images of <= 8 lines, i.e. the 8 x 8 level: the lower half of every 8 x 16 tile is padding): chunks are batched in pairs and the
+// batches whose halo rows all lie below the image are skipped (a group-uniform test), a third of the transform at that level.
+template <int NCK, bool SHORT = false>
 __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32_t a_base, uint64_t* a_tma, uint64_t* a_ready,
                                                     const float* s_gamma, const float* s_beta, const float2* s_stat, int tid, long long* dts) {
   constexpr int RPP = kHxfGroup / NCK;                 // halo rows per pass of one group
   constexpr int NPASS = (kHPx + RPP - 1) / RPP;        // 12 / 6 / 3 chunks per thread
-  constexpr int BATCH = NPASS % 6 == 0 ? 6 : 3;
+  constexpr int BATCH = SHORT ? 2 : (NPASS % 6 == 0 ? 6 : 3);
   static_assert(NPASS % BATCH == 0, "pass batching");
   const int grp = tid / kHxfGroup, lt = tid % kHxfGroup;
   const int c = lt % NCK;
@@ -232,8 +234,10 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
     // whatever is there) and only the STORE is predicated, so the BATCH chunks of a thread form independent dependency
     // chains the scheduler can interleave (MUFU.TANH issues at 8 cycles per warp instruction per SM sub-partition:
     // profiles/r01_microbench_sfu_rate.txt); per-chunk divergent regions serialised them.
+    const int rlim = ((int)H - y0 < kHH ? (int)H - y0 : kHH) * kHW;  // halo rows >= rlim lie below the image
 #pragma unroll
     for (int k0 = 0; k0 < NPASS; k0 += BATCH) {
+      if (SHORT && k0 * RPP >= rlim) break;
       uint4 v[BATCH];
       bool ok[BATCH];
 #pragma unroll
@@ -857,6 +861,7 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
     } else if (gn) {
       const uint32_t a_base = smem_u32(smem_a);
       if (p.kslab == 64) halo_transform_loop<8>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x, dts);
+      else if (p.kslab == 32 && p.out_h <= 8) halo_transform_loop<4, true>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x, dts);
       else if (p.kslab == 32) halo_transform_loop<4>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x, dts);
       else halo_transform_loop<2>(p, a_base, a_tma, a_ready, s_gamma, s_beta, s_stat, threadIdx.x, dts);
     }

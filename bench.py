@@ -353,7 +353,7 @@ def main():
         var = rt.sch.fwd.variants()
         ops = rt.sch.fwd.ops
         tot_ms = sum(r[2] for r in rows)
-        names = {0: "conv_igemm_tc_kernel", 2: "conv3x3_halo_tc_kernel"}
+        names = {0: "conv_igemm_tc_kernel", 2: "conv3x3_halo_tc_kernel", 3: "cs_gemm_tc_kernel"}
         per = {}
         for i, r in enumerate(rows):
             if var[i] >= 0:

@@ -74,6 +74,10 @@ struct alignas(64) HaloKParams {
   uint32_t stage_bytes, b_slot_bytes;
   uint32_t idesc, layout_type, tmem_cols;
   int nacc;            // TMEM accumulators: 2 (one per half-pipeline) or 4 (two per half-pipeline: the MMA warp runs one tile ahead of its epilogue group)
+  int tile_w_log2, tile_h;  // output tile = (1 << tile_w_log2) x tile_h pixels, row = y * tile_w + x: 8 x 16 for the halo conv, (128 / H) x H for
+                            // the column-softmax GEMM below
+  uint32_t a_bytes;         // column-softmax GEMM: bytes of the A slab of a stage (the sample's weight slab follows it)
+  int w_per_sample;         // column-softmax GEMM: weights indexed by the sample (FWM W_eff) instead of shared
   const double* gn_stats;
   const double* gn_stats2;  // statistics of segment 1 (the GroupNorm runs over the concatenated tensor)
   const float* gn_gamma;
@@ -547,7 +551,8 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
   const int q = warp & 3;
   const int grp = (warp - 10) >> 2;
   const int row = q * 32 + lane;
-  const int ry = row >> 3, rx = row & 7;
+  const int twl = p.tile_w_log2, tile_h = p.tile_h;
+  const int ry = row >> twl, rx = row & ((1 << twl) - 1);
   const int nch = p.bn >> 4;
   const int n0 = (int)blockIdx.y * p.bn;           // first output channel of this CTA's N tile
   const int n_valid = p.epi.n_valid - n0;          // valid channels of the tile (may exceed bn: clipped by nch)
@@ -611,7 +616,7 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
   };
   uint32_t it = 0;
   for (int t = grp; t < my_tiles; t += 2, ++it) {
-    const int y = ty * 16 + ry, x = tx * 8 + rx;
+    const int y = ty * tile_h + ry, x = (tx << twl) + rx;
     const bool row_ok = (y < out_h) && (x < out_w);
     const size_t pix = ((size_t)b * out_h + y) * out_w + x;
     const bf16* res_px = kRes ? resid + pix * (size_t)res_ld : nullptr;
@@ -941,6 +946,246 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   }
 }
 
+// =====================================================================================================================
+// Column-softmax GEMM (round 2): out = W[b] . softmax_over_H(a) + bias (+ residual) in ONE kernel.
+//
+// Replaces `q.softmax(dim=-2)` followed by the per-sample `attn_out` 1x1 product of FastAttnCondInjection
+// (/root/reference/models/sr3_dwt.py:541-573): the stand-alone softmax kernel wrote the normalised q tensor to HBM and the 1x1 GEMM read it
+// back (4 + 2 bytes per element: 0.99 ms of the 5.84 ms denoise step at B = 256 for the two launches of the 12 FWM blocks at >= 16 lines).
+// Here a tile of the GEMM is (128 / H) image columns x ALL H lines (H = 16, 32, 64; row = y * tile_w + x), so the softmax over the height is
+// local to the tile: the TMA producer brings the raw q tile (and the sample's W_eff slab: per-sample weights cannot stay resident) into a
+// ring stage, the transform warps replace it IN PLACE by its column softmax, the MMA warp multiplies (one tap), the epilogue of the halo
+// conv adds bias and the residual.  Same warp roles, barriers and two half-pipelines as conv3x3_halo_tc_kernel.
+//
+// Transform of one stage (128 rows x NCK 16-byte chunks) by one group of 128 threads: thread (j, rq, c8) owns chunk c8 of the rows
+// j + 8 (rq * NR + i): eight consecutive lanes read eight consecutive rows of one chunk column (conflict-free under the TMA swizzle), and all
+// rows of a thread belong to image column x = j mod tile_w.  (1) column maximum with packed max.bf16x2, finished over the lanes that share
+// (x, c8) by xor-shuffles (lane masks tile_w .. 4 RQ); (2) e = 2^((v - max) log2 e) in fp32, summed in fp32, parked as f16x2 (values in
+// (0, 1]: 11 bits against the 8 of the bf16 result, where fp32 would need 64 live registers per thread); (3) e / sum -> bf16 -> STS.128.
+__device__ __forceinline__ float cs_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t cs_max_bf2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t cs_pack_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ f32x2 cs_unpack_h2(uint32_t w) {
+  float lo, hi;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}\n" : "=f"(lo), "=f"(hi) : "r"(w));
+  return pk2(lo, hi);
+}
+
+template <int NCK>
+__device__ __forceinline__ void cs_transform_loop(const HaloKParams& p, uint32_t a_base, uint64_t* a_tma, uint64_t* a_ready, int tid) {
+  constexpr int RQ = 128 / (8 * NCK);  // row blocks of 8 * NR rows: 2 (64-channel slabs) or 4 (32-channel slabs)
+  constexpr int NR = 16 / RQ;          // rows per thread: 8 or 4
+  constexpr uint32_t SPAN = NCK * 16;
+  const int grp = tid / kHxfGroup, lt = tid % kHxfGroup;
+  const int j = lt & 7, rq = (lt >> 3) % RQ, c8 = lt / (8 * RQ);
+  const uint32_t sw = NCK == 8 ? (uint32_t)j : (((uint32_t)j >> 1) & 3u);  // rows j + 8 m all share the swizzle phase of row j
+  const uint32_t off0 = (uint32_t)(j + 8 * rq * NR) * SPAN + (((uint32_t)c8 ^ sw) << 4);
+  const int tw = 1 << p.tile_w_log2;
+  const uint32_t nst = (uint32_t)p.stages >> 1;
+  int remaining;
+  {
+    int base, count;
+    halo_range(p, base, count);
+    remaining = count > grp ? ((count - grp + 1) / 2) * p.nslab : 0;  // this group's tiles (positions grp, grp + 2, ...) x K slabs
+  }
+  a_tma += grp * nst; a_ready += grp * nst;
+  a_base += (uint32_t)grp * nst * p.stage_bytes;
+  uint32_t stage = 0, phase = 0;
+  const f32x2 l2e = pk2(1.4426950408889634f, 1.4426950408889634f);
+  for (; remaining > 0; --remaining) {
+    const uint32_t sbase = a_base + stage * p.stage_bytes + off0;
+    mbar_wait(&a_tma[stage], phase);
+    uint4 v[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) v[i] = h_lds128(sbase + (uint32_t)i * 8u * SPAN);
+    uint32_t mx[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+#pragma unroll
+    for (int i = 1; i < NR; ++i) {
+      mx[0] = cs_max_bf2(mx[0], v[i].x); mx[1] = cs_max_bf2(mx[1], v[i].y);
+      mx[2] = cs_max_bf2(mx[2], v[i].z); mx[3] = cs_max_bf2(mx[3], v[i].w);
+    }
+    for (int m = tw; m <= 4 * RQ; m <<= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mx[q] = cs_max_bf2(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], m));
+    }
+    f32x2 nm[4], sum[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      nm[q] = mul2(bf2_to_f2(mx[q]), pk2(-1.4426950408889634f, -1.4426950408889634f));
+      sum[q] = pk2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float lo, hi;
+        upk2(fma2(bf2_to_f2(w[q]), l2e, nm[q]), lo, hi);
+        const float e0 = cs_ex2(lo), e1 = cs_ex2(hi);
+        sum[q] = add2(sum[q], pk2(e0, e1));
+        w[q] = cs_pack_h2(e0, e1);
+      }
+      v[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    for (int m = tw; m <= 4 * RQ; m <<= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float lo, hi;
+        upk2(sum[q], lo, hi);
+        lo += __shfl_xor_sync(0xffffffffu, lo, m);
+        hi += __shfl_xor_sync(0xffffffffu, hi, m);
+        sum[q] = pk2(lo, hi);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float lo, hi;
+      upk2(sum[q], lo, hi);
+      sum[q] = pk2(__frcp_rn(lo), __frcp_rn(hi));
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = f2_to_bf2(mul2(cs_unpack_h2(w[q]), sum[q]));
+      h_sts128(sbase + (uint32_t)i * 8u * SPAN, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+    h_fence_proxy_async();
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&a_ready[stage]);
+    if (++stage == nst) { stage = 0; phase ^= 1u; }
+  }
+}
+
+template <int KSTEPS>
+__device__ __forceinline__ void cs_mma_loop(const HaloKParams& p, uint32_t a_base, uint64_t* a_full, uint64_t* a_empty, uint64_t* tmem_full,
+                                            uint64_t* tmem_empty, uint32_t tmem_base, int my_tiles, int w) {
+  const uint32_t span = (uint32_t)p.span, nst = (uint32_t)p.stages >> 1, stage16 = p.stage_bytes >> 4;
+  a_full += (uint32_t)w * nst; a_empty += (uint32_t)w * nst;
+  a_base += (uint32_t)w * nst * p.stage_bytes;
+  const uint64_t desc_a0 = make_smem_desc(a_base, 8u * span, p.layout_type);              // dense rows: SBO = 8 rows
+  const uint64_t desc_b0 = make_smem_desc(a_base + p.a_bytes, 8u * span, p.layout_type);  // the stage's weight slab
+  uint32_t stage = 0, phase = 0, itn = 0;
+  const bool four = p.nacc == 4;
+  for (int t = w; t < my_tiles; t += 2, ++itn) {
+    const uint32_t acc = (uint32_t)w + (four ? 2u * (itn & 1u) : 0u);
+    const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.bn;
+    mbar_wait(&tmem_empty[acc], ((four ? itn >> 1 : itn) & 1u) ^ 1u);
+    tc_fence_after();
+    for (int slab = 0; slab < p.nslab; ++slab) {
+      mbar_wait(&a_full[stage], phase);
+      tc_fence_after();
+      const uint64_t so = (uint64_t)(stage * stage16);
+      umma_bf16_ss_steps<KSTEPS>(tmem_d, desc_a0 + so, desc_b0 + so, p.idesc, slab != 0 ? 1u : 0u);
+      umma_commit_elect(&a_empty[stage]);
+      if (++stage == nst) { stage = 0; phase ^= 1u; }
+    }
+    umma_commit_elect(&tmem_full[acc]);
+  }
+}
+
+template <int F>
+__global__ void __launch_bounds__(kHThreads, 1) cs_gemm_tc_kernel(const __grid_constant__ HaloKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  uint8_t* smem_a = smem;                                                       // [stages][A slab | weight slab]
+  float* s_add = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);  // [8 epilogue warps][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_add + kHEpiWarps * 256);
+  uint64_t* a_tma = bars;
+  uint64_t* a_ready = bars + kHMaxStages;
+  uint64_t* a_empty = bars + 2 * kHMaxStages;
+  uint64_t* tmem_full = bars + 3 * kHMaxStages;
+  uint64_t* tmem_empty = tmem_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int tile_base, my_tiles;
+  halo_range(p, tile_base, my_tiles);
+  if (warp == 18 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB[0]);
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(&a_tma[i], 1);
+        mbar_init(&a_ready[i], kHxfGroup / 32);
+        mbar_init(&a_empty[i], 1);
+      }
+      for (int i = 0; i < p.nacc; ++i) {
+        mbar_init(&tmem_full[i], 1);
+        mbar_init(&tmem_empty[i], kHEpiWarps / 2);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything below reads what earlier kernels of the step wrote
+
+  if (warp < 8) {
+    if (p.kslab == 64) cs_transform_loop<8>(p, smem_u32(smem_a), a_tma, a_ready, threadIdx.x);
+    else cs_transform_loop<4>(p, smem_u32(smem_a), a_tma, a_ready, threadIdx.x);
+  } else if (warp == 8 || warp == 9) {
+    if (p.kslab == 64) cs_mma_loop<4>(p, smem_u32(smem_a), a_ready, a_empty, tmem_full, tmem_empty, tmem_base, my_tiles, warp - 8);
+    else cs_mma_loop<2>(p, smem_u32(smem_a), a_ready, a_empty, tmem_full, tmem_empty, tmem_base, my_tiles, warp - 8);
+  } else if (warp == 18) {
+    if (lane == 0) {
+      const uint32_t tx = p.a_bytes + p.b_slot_bytes;
+      const uint32_t nst = (uint32_t)p.stages >> 1;
+      const int twl = p.tile_w_log2;
+      HaloIter it;
+      it.init(p, tile_base, 1, tile_base + my_tiles);
+      uint32_t st0 = 0u, ph0 = 0u, st1 = 0u, ph1 = 0u, ring = 0u;
+      for (; it.remaining > 0; it.next()) {
+        const uint32_t rs = ring ? st1 : st0, rp = ring ? ph1 : ph0;
+        const uint32_t stage = ring * nst + rs;
+        uint8_t* dst = smem_a + (size_t)stage * p.stage_bytes;
+        mbar_wait(&a_empty[stage], rp ^ 1u);
+        mbar_expect_tx(&a_tma[stage], tx);
+        tma_load_4d(&p.tmA[0], &a_tma[stage], dst, it.slab * p.kslab, it.tx << twl, 0, it.b);
+        tma_load_3d(&p.tmB[0], &a_tma[stage], dst + p.a_bytes, it.slab * p.kslab, 0, p.w_per_sample ? it.b : 0);
+        if (p.has_res_map && it.slab == 0) tma_prefetch_l2_4d(&p.tmR, 0, it.tx << twl, 0, it.b);  // residual tile -> L2, a ring ahead of its use
+        {
+          uint32_t ns = rs + 1u, np = rp;
+          if (ns == nst) { ns = 0u; np ^= 1u; }
+          if (ring) { st1 = ns; ph1 = np; } else { st0 = ns; ph0 = np; }
+        }
+        if (it.slab == p.nslab - 1) ring ^= 1u;
+      }
+      pdl_trigger();
+    }
+  } else if (warp >= 10 && warp < 18) {
+    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, nullptr, s_add);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 int conv3_halo_set_debug_ts(long long* ptr) {
   DDIF_CUDA_CHECK(cudaMemcpyToSymbol(g_halo_ts, &ptr, sizeof(ptr)));
   return DDIF_OK;
@@ -1102,6 +1347,7 @@ int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   p.b_slot_bytes = (uint32_t)h.b_slot;
   p.layout_type = p.span == 128 ? 2u : p.span == 64 ? 4u : 6u;
   p.nacc = 4 * p.bn <= 512 ? 4 : 2;
+  p.tile_w_log2 = 3; p.tile_h = 16;
   uint32_t cols = 32;
   while ((int)cols < p.nacc * p.bn) cols <<= 1;
   p.tmem_cols = cols;
@@ -1186,6 +1432,113 @@ int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
 int conv3_halo_launch(const GemmLaunch& L, cudaStream_t stream) {
   const HaloKParams& p = *reinterpret_cast<const HaloKParams*>(L.kparams);
   HaloKernel k = halo_kernel(L.flags, p.dw_w != nullptr);
+  if (!k) return DDIF_ERR_STATE;
+  DDIF_CUDA_CHECK(launch_pdl(k, dim3(L.grid_x, L.grid_y), dim3(kHThreads), (size_t)L.smem_bytes, stream, p));
+  return DDIF_OK;
+}
+
+// ---- column-softmax GEMM: host side ---------------------------------------------------------------------------------------------------
+typedef void (*CsKernel)(const HaloKParams);
+static CsKernel cs_kernel(int f) { return f == 0 ? cs_gemm_tc_kernel<0> : (f == kEpiRes ? cs_gemm_tc_kernel<kEpiRes> : nullptr); }
+
+bool cs_gemm_applicable(const ddif_gemm_t& g) {
+  if (!g.a_softmax_h || g.nseg != 1 || g.taps[0] != 1 || g.stride != 1 || g.a_up != 0) return false;
+  if (g.gn_stats || g.mod || g.film || g.dw_w || g.act || g.stats || g.out_nchw || !g.out) return false;
+  const int64_t H = g.out_h, W = g.out_w;
+  if (g.a_h[0] != H || g.a_w[0] != W || (H != 16 && H != 32 && H != 64) || W % (128 / H) != 0) return false;
+  if (g.a_c[0] % 32 != 0 || g.a_c[0] <= 0 || g.a_c[0] > 512 || g.a_ld[0] % 8 != 0 || g.w_k[0] % 8 != 0 || g.w_k[0] < g.a_c[0]) return false;
+  if (g.n_pad % 16 != 0 || g.n_pad < 16 || g.n_pad > 128 || g.n_valid > g.n_pad || g.n_valid < 1) return false;
+  if (g.out_ld % 16 != 0 || (g.residual && g.res_ld % 16 != 0)) return false;
+  if (g.w_per_sample[0] && g.w_s[0] < g.batch) return false;
+  return true;
+}
+
+int cs_gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
+  HaloKParams& p = *reinterpret_cast<HaloKParams*>(L.kparams);
+  memset(&p, 0, sizeof(p));
+  PFN_encodeTiled enc = ddif_get_encode();
+  if (!enc) return DDIF_ERR_DRIVER;
+  if (!cs_gemm_applicable(g)) return DDIF_ERR_SHAPE;
+  static bool attrs = false;
+  if (!attrs) {
+    DDIF_CUDA_CHECK(cudaFuncSetAttribute(cs_kernel(0), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DDIF_CUDA_CHECK(cudaFuncSetAttribute(cs_kernel(kEpiRes), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attrs = true;
+  }
+  const int H = (int)g.out_h, W = (int)g.out_w, tw = 128 / H;
+  p.cin = (int)g.a_c[0];
+  p.kslab = p.cin % 64 == 0 ? 64 : 32;
+  p.nslab = p.nslab0 = p.nslab_t = p.cin / p.kslab;
+  p.span = p.kslab * 2;
+  p.ntap_w = 1;
+  p.batch = (int)g.batch; p.out_h = H; p.out_w = W;
+  p.tile_h = H;
+  p.tile_w_log2 = tw == 8 ? 3 : (tw == 4 ? 2 : 1);
+  p.tiles_x = W / tw; p.tiles_y = 1;
+  p.num_tiles = p.tiles_x * p.batch;
+  p.bn = (int)g.n_pad;
+  p.a_bytes = 128u * (uint32_t)p.span;
+  p.b_slot_bytes = (((uint32_t)p.bn * (uint32_t)p.span) + 1023u) & ~1023u;
+  p.stage_bytes = p.a_bytes + p.b_slot_bytes;
+  p.w_per_sample = g.w_per_sample[0] ? 1 : 0;
+  p.layout_type = p.span == 128 ? 2u : 4u;
+  p.span_r = p.span; p.layout_r = p.layout_type;
+  const int misc = kHEpiWarps * 256 * 4 + (3 * kHMaxStages + 16) * 8 + 64 + 1024;
+  int st = ((227 * 1024 - misc) / (int)p.stage_bytes) & ~1;
+  if (st > kHMaxStages) st = kHMaxStages;
+  if (st < 2) return DDIF_ERR_SHAPE;
+  p.stages = st;
+  p.nacc = 4;
+  uint32_t cols = 32;
+  while ((int)cols < p.nacc * p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  L.smem_bytes = st * (int)p.stage_bytes + misc;
+  L.grid_y = 1;
+  const int sms = ddif_sm_count();
+  L.grid_x = p.num_tiles < sms ? p.num_tiles : sms;
+  L.variant = 3;
+  L.flags = g.residual ? kEpiRes : 0;
+  const CUtensorMapSwizzle sw = p.span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.a_c[0], (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)g.batch};
+    cuuint64_t strides[3] = {(cuuint64_t)g.a_ld[0] * 2, (cuuint64_t)W * g.a_ld[0] * 2, (cuuint64_t)H * W * g.a_ld[0] * 2};
+    cuuint32_t box[4] = {(cuuint32_t)p.kslab, (cuuint32_t)tw, (cuuint32_t)H, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (enc(&p.tmA[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g.a[0]), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return DDIF_ERR_DRIVER;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)g.w_k[0], (cuuint64_t)g.n_pad, (cuuint64_t)g.w_s[0]};
+    cuuint64_t strides[2] = {(cuuint64_t)g.w_k[0] * 2, (cuuint64_t)g.n_pad * g.w_k[0] * 2};
+    cuuint32_t box[3] = {(cuuint32_t)p.kslab, (cuuint32_t)p.bn, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    if (enc(&p.tmB[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(g.w[0]), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return DDIF_ERR_DRIVER;
+  }
+  if (g.residual) {
+    const int nb = (int)(g.n_valid < p.bn ? g.n_valid : p.bn) / 8 * 8;
+    cuuint64_t dims[4] = {(cuuint64_t)g.n_valid, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)g.batch};
+    cuuint64_t strides[3] = {(cuuint64_t)g.res_ld * 2, (cuuint64_t)W * g.res_ld * 2, (cuuint64_t)H * W * g.res_ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)nb, (cuuint32_t)tw, (cuuint32_t)H, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    if (nb >= 8 && nb <= 256 && (reinterpret_cast<uintptr_t>(g.residual) & 15u) == 0 &&
+        enc(&p.tmR, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g.residual), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+      p.has_res_map = 1;
+  }
+  EpiParams& e = p.epi;
+  e.bias = g.bias; e.film = nullptr; e.film_ld = 0; e.mod = nullptr; e.residual = (const bf16*)g.residual;
+  e.res_ld = (int)g.res_ld; e.act = 0; e.out = (bf16*)g.out; e.out_ld = (int)g.out_ld; e.out_nchw = nullptr; e.stats = nullptr;
+  e.n_valid = (int)g.n_valid; e.batch = p.batch; e.out_h = p.out_h; e.out_w = p.out_w;
+  return DDIF_OK;
+}
+
+int cs_gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
+  const HaloKParams& p = *reinterpret_cast<const HaloKParams*>(L.kparams);
+  CsKernel k = cs_kernel(L.flags);
   if (!k) return DDIF_ERR_STATE;
   DDIF_CUDA_CHECK(launch_pdl(k, dim3(L.grid_x, L.grid_y), dim3(kHThreads), (size_t)L.smem_bytes, stream, p));
   return DDIF_OK;

@@ -13,7 +13,7 @@ struct alignas(64) GemmLaunch {
   unsigned char kparams[1536];
   int grid_x, grid_y, smem_bytes;
   int flags;    // variant 2: compile-time epilogue specialisation (kEpi* bits)
-  int variant;  // 0: conv_igemm_tc_kernel (TMA tap boxes), 2: conv3x3_halo_tc_kernel (one TMA halo tile feeds all nine taps; in-place
+  int variant;  // 3: cs_gemm_tc_kernel (column softmax fused into a 1x1 GEMM), 0: conv_igemm_tc_kernel (TMA tap boxes), 2: conv3x3_halo_tc_kernel (one TMA halo tile feeds all nine taps; in-place
                 // GN+Swish).  (1 was an LDG-fed 3x3 kernel with the nearest-x2 folded into its loader: slower at every level, removed.)
 };
 
@@ -23,6 +23,9 @@ bool conv3_halo_applicable(const ddif_gemm_t& g);
 int conv3_halo_prepare(const ddif_gemm_t& g, GemmLaunch& L);
 int conv3_halo_launch(const GemmLaunch& L, cudaStream_t stream);
 int conv3_halo_set_debug_ts(long long* ptr);
+bool cs_gemm_applicable(const ddif_gemm_t& g);           // conv3x3_halo.cu: column-softmax GEMM (FWM softmax over H fused into attn_out)
+int cs_gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L);
+int cs_gemm_launch(const GemmLaunch& L, cudaStream_t stream);
 
 // elementwise.cu
 int launch_in_convert(const ddif_in_convert_t& p, cudaStream_t s);

@@ -552,6 +552,7 @@ static IgemmKernel igemm_kernel(int f) {
 
 int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   if (g.a_up != 0) return DDIF_ERR_SHAPE;  // reserved: nearest x2 runs as its own kernel (DDIF_OP_UPSAMPLE2X) in front of the conv
+  if (g.a_softmax_h) return cs_gemm_prepare(g, L);  // softmax over the image height fused into the loader (DDIF_ERR_SHAPE if unsupported)
   if (!g.force_tma && conv3_halo_applicable(g)) {
 #ifdef DDIF_VAR_NO_HALO  // tuning build (tools/): plain 3x3 convs through the generic TMA kernel
     if (g.nseg == 2 || g.gn_stats || g.dw_w)
@@ -738,6 +739,7 @@ int gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
 
 int gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   if (L.variant == 2) return conv3_halo_launch(L, stream);
+  if (L.variant == 3) return cs_gemm_launch(L, stream);
   const GemmKParams& p = *reinterpret_cast<const GemmKParams*>(L.kparams);
   IgemmKernel k = igemm_kernel(p.lean);
   if (!k) return DDIF_ERR_STATE;

@@ -169,7 +169,7 @@ class PlanBuilder:
         return [(op.label, op.struct, float(ms[i]), op.flops, op.bytes) for i, op in enumerate(self.ops)]
 
     def variants(self) -> List[int]:
-        """Kernel variant of every op (GEMM ops: 0 generic TMA, 1 fused LDG 3x3, 2 halo 3x3; others -1)."""
+        """Kernel variant of every op (GEMM ops: 0 generic TMA, 2 halo 3x3, 3 column-softmax GEMM; others -1)."""
         lib = _lib.load()
         return [int(lib.ddif_plan_op_variant(self.handle, i)) for i in range(len(self.ops))]
 

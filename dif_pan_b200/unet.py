@@ -359,10 +359,10 @@ class Schedule:
     """Builds the cond-cache plan and the per-step forward plan of a UNetSR3 for a fixed (B, H, W)."""
 
     def __init__(self, net: UNetSR3, addr: Dict[str, int], B: int, H: int, W: int, io: Dict[str, int], *, use_qconv: bool = True,
-                 use_dwq: bool = True, use_attn_block: bool = True):
+                 use_dwq: bool = True, use_attn_block: bool = True, use_cs_gemm: bool = True):
         """addr: packed-weight name -> device address; io: x, sc, t, out, cond addresses (fixed buffers).
-        use_qconv / use_dwq / use_attn_block: A/B switches for tools/ (composed q conv, in-kernel depthwise q path, fused attention block);
-        the product always builds the schedule with all three on."""
+        use_qconv / use_dwq / use_attn_block / use_cs_gemm: A/B switches for tools/ (composed q conv, in-kernel depthwise q path, fused attention
+        block, softmax-over-H fused into the attn_out GEMM); the product always builds the schedule with all of them on."""
         if H % 8 or W % 8 or min(H, W) < 8 * 2 ** (self._levels(net) - 1):
             raise ValueError(f"UNetSR3 needs H, W multiples of 8 and >= {8 * 2 ** (self._levels(net) - 1)}, got {H}x{W}")
         self.net, self.addr, self.B, self.H, self.W, self.io = net, addr, B, H, W, io
@@ -377,7 +377,7 @@ class Schedule:
         self.weff: Dict[str, Buf] = {}
         self.film_offsets = None
         self.first_body_op = 0
-        self.use_qconv, self.use_dwq, self.use_attn_block = use_qconv, use_dwq, use_attn_block
+        self.use_qconv, self.use_dwq, self.use_attn_block, self.use_cs_gemm = use_qconv, use_dwq, use_attn_block, use_cs_gemm
 
     @staticmethod
     def _levels(net) -> int:
@@ -398,17 +398,17 @@ class Schedule:
 
     def _gemm(self, pb, label, srcs, weights, n_valid, out: Optional[Act], *, taps, stride=1, bias=None, film=None,
               film_ld=0, mod=None, residual: Optional[Act] = None, act=0, out_nchw=None, per_sample=(0, 0), w_s=None, out_hw=None,
-              gn=None, a_up=0, w_k=None, ref_flops=-1.0, residual_off=0, dw=None):
+              gn=None, a_up=0, w_k=None, ref_flops=-1.0, residual_off=0, dw=None, softmax_h=False, a_c=None):
         """gn = (gamma_addr, beta_addr, act): fuse GroupNorm(+Swish) of the source(s) into the conv's loader, using the
         sources' own statistics; a_up is reserved (must be 0)."""
         a0 = srcs[0]
         oh, ow = out_hw if out_hw else ((a0.H << a_up) // stride, (a0.W << a_up) // stride)
         n_pad = _ceil(n_valid, 16)
         nseg = len(srcs)
-        k_total = sum(s.C * taps[i] for i, s in enumerate(srcs))
+        k_total = sum((a_c[i] if a_c else s.C) * taps[i] for i, s in enumerate(srcs))
         fields = dict(
             a=[s.buf for s in srcs] + [None] * (2 - nseg), a_ld=[s.C for s in srcs] + [0] * (2 - nseg),
-            a_c=[s.C for s in srcs] + [0] * (2 - nseg), a_h=[s.H for s in srcs] + [0] * (2 - nseg),
+            a_c=(list(a_c) if a_c else [s.C for s in srcs]) + [0] * (2 - nseg), a_h=[s.H for s in srcs] + [0] * (2 - nseg),
             a_w=[s.W for s in srcs] + [0] * (2 - nseg), w=list(weights) + [None] * (2 - nseg),
             w_s=[(w_s[i] if w_s else taps[i]) for i in range(nseg)] + [0] * (2 - nseg),
             w_k=(list(w_k) if w_k else [s.C for s in srcs]) + [0] * (2 - nseg), taps=list(taps) + [0] * (2 - nseg),
@@ -420,11 +420,12 @@ class Schedule:
             stats=out.stats if (out is not None and out.stats is not None) else None,
             gn_stats=a0.stats if gn else None, gn_gamma=gn[0] if gn else None, gn_beta=gn[1] if gn else None, gn_eps=1e-5,
             gn_act=gn[2] if gn else 0, a_up=a_up, force_tma=0,
-            gn_stats2=srcs[1].stats if (gn and nseg == 2) else None, dw_w=dw[0] if dw else None, dw_n=dw[1] if dw else 0)
+            gn_stats2=srcs[1].stats if (gn and nseg == 2) else None, dw_w=dw[0] if dw else None, dw_n=dw[1] if dw else 0,
+            a_softmax_h=1 if softmax_h else 0)
         if gn:
             assert all(s.stats is not None for s in srcs), label
         m = a0.B * oh * ow
-        nbytes = sum(s.B * s.H * s.W * s.C * 2 for s in srcs) + m * n_valid * (2 if out else 4)
+        nbytes = sum(s.B * s.H * s.W * (a_c[i] if a_c else s.C) * 2 for i, s in enumerate(srcs)) + m * n_valid * (2 if out else 4)
         if residual:
             nbytes += m * n_valid * 2
         if mod is not None:
@@ -633,12 +634,19 @@ class Schedule:
                     self._gemm(pb, q + ".qconv", [x, skip], [A[q + ".qcr.w"], A[q + ".qcr.w"] + 2 * x.C], dim + o, qr, taps=[9, 9], bias=A[q + ".qcr.b"],
                                gn=(A[q + ".gamma"], A[q + ".beta"], 0), w_k=[dim, dim],
                                ref_flops=2.0 * B * x.H * x.W * dim * (9 + dim + o))  # reference: depthwise 3x3 + 1x1 (q) + 1x1 (attn_res)
-                qs = self._act(pb, q + ".qs", B, x.H, x.W, dim)
-                pb.add("ddif_softmax_h_t", label=q + ".softmax_h", traffic=B * x.H * x.W * dim * 4, **{"in": qr.buf}, out=qs.buf, batch=B,
-                       h=x.H, w=x.W, c=dim, scale=1.0, in_ld=dim + o)
                 y = self._act(pb, q + ".y", B, x.H, x.W, o)
-                self._gemm(pb, q + ".attn_out", [qs], [("cache", self.weff[p])], o, y, taps=[1], bias=A[q + ".attn.b"], per_sample=(1,), w_s=[B],
-                           residual=qr, residual_off=dim, ref_flops=2.0 * B * x.H * x.W * o * dim)
+                if self.use_cs_gemm and x.H in (16, 32, 64) and x.W % (128 // x.H) == 0 and dim % 32 == 0 and _ceil(o, 16) <= 128:
+                    # q.softmax(dim=-2) inside the attn_out GEMM's loader (cs_gemm_tc_kernel: a tile = 128/H columns x all H lines); the
+                    # normalised q tensor never goes to HBM
+                    self._gemm(pb, q + ".softmax_h+attn_out", [qr], [("cache", self.weff[p])], o, y, taps=[1], bias=A[q + ".attn.b"],
+                               per_sample=(1,), w_s=[B], w_k=[dim], a_c=[dim], residual=qr, residual_off=dim, softmax_h=True,
+                               ref_flops=2.0 * B * x.H * x.W * o * dim)
+                else:
+                    qs = self._act(pb, q + ".qs", B, x.H, x.W, dim)
+                    pb.add("ddif_softmax_h_t", label=q + ".softmax_h", traffic=B * x.H * x.W * dim * 4, **{"in": qr.buf}, out=qs.buf, batch=B,
+                           h=x.H, w=x.W, c=dim, scale=1.0, in_ld=dim + o)
+                    self._gemm(pb, q + ".attn_out", [qs], [("cache", self.weff[p])], o, y, taps=[1], bias=A[q + ".attn.b"], per_sample=(1,),
+                               w_s=[B], residual=qr, residual_off=dim, ref_flops=2.0 * B * x.H * x.W * o * dim)
             else:
                 qt = self._act(pb, q + ".q", B, x.H, x.W, dim)
                 if qconv:

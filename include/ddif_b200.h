@@ -102,6 +102,11 @@ typedef struct {
    * kernel and `w` holds 1x1 weights ([1][n_pad][K], w_s = 1): output channels [0, dw_n) = w[0:dw_n] . dw3x3(a), channels
    * [dw_n, n_valid) = w[dw_n:] . a (the un-convolved normalised input: attn_res(x_hat)).  Needs gn_stats. */
   const float* dw_w; int64_t dw_n;
+  /* a_softmax_h != 0 (one segment, 1x1, stride 1; shared or per-sample weights; epilogue = bias + optional residual): segment 0 is read
+   * through a softmax over the image HEIGHT, a'[b,y,x,c] = exp(a[b,y,x,c]) / sum_y' exp(a[b,y',x,c]) -- FWM `q.softmax(dim=-2)` followed by
+   * attn_out (sr3_dwt.py:541-573) in ONE kernel (cs_gemm_tc_kernel: a tile = 128/H image columns x all H lines).  Needs out_h in
+   * {16, 32, 64}, out_w % (128 / out_h) == 0, a_c % 32 == 0, n_pad <= 128; DDIF_ERR_SHAPE otherwise (run DDIF_OP_SOFTMAX_H + a plain GEMM). */
+  int64_t a_softmax_h;
 } ddif_gemm_t;
 
 typedef struct { const float* x; const float* self_cond; void* out; int64_t batch, c, h, w, c_pad; } ddif_in_convert_t;

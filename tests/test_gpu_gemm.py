@@ -279,3 +279,36 @@ def test_bad_arguments_return_errors():
         gemm([x], [w], 32, taps=[9], stride=3)  # stride 1|2
     with pytest.raises(RuntimeError):
         gemm([nhwc_bf16(_rand(1, 24, 16, 16))], [w], 32, taps=[9])  # Cin % 16
+
+@pytest.mark.parametrize("shape", [(3, 64, 64, 64, 32), (2, 64, 64, 96, 32), (3, 32, 32, 128, 64), (2, 32, 32, 96, 64), (5, 16, 16, 128, 64),
+                                   (2, 16, 16, 256, 128), (2, 64, 16, 64, 32), (2, 16, 64, 64, 48)])
+def test_softmax_h_fused_into_per_sample_gemm(shape):
+    """FWM `q.softmax(dim=-2)` + per-sample attn_out + bias + attn_res residual (sr3_dwt.py:541-573) in ONE kernel (cs_gemm_tc_kernel):
+    q and r live in one [B, H, W, dim + o] tensor like the q conv writes them; checked against the fp32 torch expression on the same
+    bf16 inputs and against the two-kernel path (DDIF_OP_SOFTMAX_H + plain GEMM)."""
+    B, H, W, dim, o = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    qr = (torch.randn(B, H, W, dim + o, generator=g) * 2.0).to(torch.bfloat16).to(DEV)
+    weff = (torch.randn(B, (o + 15) // 16 * 16, dim, generator=g) * 0.2).to(torch.bfloat16).to(DEV)
+    weff[:, o:] = 0
+    bias = torch.randn(o, generator=g).to(DEV)
+    out, _ = gemm([qr], [weff], o, taps=[1], bias=bias, per_sample=[1], w_s=[B], a_c=[dim], residual=qr, residual_off=dim, softmax_h=True)
+    q, r = qr[..., :dim].float(), qr[..., dim:].float()
+    ref = torch.einsum("bhwc,boc->bhwo", torch.softmax(q, dim=1), weff[:, :o].float()) + bias + r
+    assert rel_err(out[..., :o].float(), ref) < 6e-3, rel_err(out[..., :o].float(), ref)
+    # two-kernel path on the same inputs
+    qs = torch.zeros(B, H, W, dim, dtype=torch.bfloat16, device=DEV)
+    _lib.launch("ddif_softmax_h_t", stream(), **{"in": qr.data_ptr()}, out=qs.data_ptr(), batch=B, h=H, w=W, c=dim, scale=1.0, in_ld=dim + o)
+    out2, _ = gemm([qs], [weff], o, taps=[1], bias=bias, per_sample=[1], w_s=[B], residual=qr, residual_off=dim)
+    assert rel_err(out[..., :o].float(), out2[..., :o].float()) < 4e-3
+    # no residual, shared weights
+    out3, _ = gemm([qr], [weff[:1].contiguous()], o, taps=[1], bias=bias, a_c=[dim], softmax_h=True)
+    ref3 = torch.einsum("bhwc,oc->bhwo", torch.softmax(q, dim=1), weff[0, :o].float()) + bias
+    assert rel_err(out3[..., :o].float(), ref3) < 6e-3
+
+
+def test_softmax_h_gemm_rejects_unsupported_shapes():
+    qr = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(1, 32, 64, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(RuntimeError):
+        gemm([qr], [w], 32, taps=[1], softmax_h=True)  # 8 lines: a tile would need 16 columns

@@ -375,6 +375,7 @@ class Schedule:
         self.n_cstats = 0
         self.mod: Dict[str, Buf] = {}
         self.weff: Dict[str, Buf] = {}
+        self.weff_k: Dict[str, int] = {}
         self.film_offsets = None
         self.first_body_op = 0
         self.use_qconv, self.use_dwq, self.use_attn_block, self.use_cs_gemm = use_qconv, use_dwq, use_attn_block, use_cs_gemm
@@ -546,11 +547,16 @@ class Schedule:
                    traffic=B * h * w * cd * 4, c_dec=dbuf, kv0_w=A[p + ".kv0"], kv1_w=A[p + ".kv1.w"], kv1_b=A[p + ".kv1.b"],
                    ctx=ctx, batch=B, h=h, w=w, cd=cd, dim=dim, heads=net.N_HEADS)
             o_pad = _ceil(o, 16)
-            weff = self.cache.buf(p + ".weff", B * o_pad * dim * 2, persistent=True)
+            # K padded to a multiple of 64 (dim 96 -> 128; the cache arena is zero-initialised and these columns are never written): the
+            # column-softmax GEMM then reads the [q | attn_res] tensor as two 64-channel slabs instead of three 32-channel ones -- the padding
+            # channels are the first attn_res channels of the same pixel, multiplied by zero weights
+            k_pad = _ceil(dim, 64) if _ceil(dim, 64) <= dim + o else dim
+            weff = self.cache.buf(p + ".weff", B * o_pad * k_pad * 2, persistent=True)
             self.weff[f"ups.{i}"] = weff
+            self.weff_k[f"ups.{i}"] = k_pad
             pb.add("ddif_fwm_weff_t", label=p + ".weff", flops=2.0 * B * o * dim * dh, traffic=B * o * dim * 2, ctx=ctx,
                    w_out=A[p + ".attn_out.w32"], weff=("cache", weff), batch=B, o=o, dim=dim, heads=net.N_HEADS, o_pad=o_pad,
-                   k_pad=dim, scale=1.0 / math.sqrt(dh))
+                   k_pad=k_pad, scale=1.0 / math.sqrt(dh))
         self.cstats_buf.nbytes = max(self.n_cstats * B * 16, 16)
         pb.ops[0].fields["bytes"] = self.cstats_buf.nbytes
 
@@ -639,14 +645,14 @@ class Schedule:
                     # q.softmax(dim=-2) inside the attn_out GEMM's loader (cs_gemm_tc_kernel: a tile = 128/H columns x all H lines); the
                     # normalised q tensor never goes to HBM
                     self._gemm(pb, q + ".softmax_h+attn_out", [qr], [("cache", self.weff[p])], o, y, taps=[1], bias=A[q + ".attn.b"],
-                               per_sample=(1,), w_s=[B], w_k=[dim], a_c=[dim], residual=qr, residual_off=dim, softmax_h=True,
-                               ref_flops=2.0 * B * x.H * x.W * o * dim)
+                               per_sample=(1,), w_s=[B], w_k=[self.weff_k[p]], a_c=[self.weff_k[p]], residual=qr, residual_off=dim,
+                               softmax_h=True, ref_flops=2.0 * B * x.H * x.W * o * dim)
                 else:
                     qs = self._act(pb, q + ".qs", B, x.H, x.W, dim)
                     pb.add("ddif_softmax_h_t", label=q + ".softmax_h", traffic=B * x.H * x.W * dim * 4, **{"in": qr.buf}, out=qs.buf, batch=B,
                            h=x.H, w=x.W, c=dim, scale=1.0, in_ld=dim + o)
                     self._gemm(pb, q + ".attn_out", [qs], [("cache", self.weff[p])], o, y, taps=[1], bias=A[q + ".attn.b"], per_sample=(1,),
-                               w_s=[B], residual=qr, residual_off=dim, ref_flops=2.0 * B * x.H * x.W * o * dim)
+                               w_s=[B], w_k=[self.weff_k[p]], residual=qr, residual_off=dim, ref_flops=2.0 * B * x.H * x.W * o * dim)
             else:
                 qt = self._act(pb, q + ".q", B, x.H, x.W, dim)
                 if qconv:
@@ -664,9 +670,10 @@ class Schedule:
                 weff = ("cache", self.weff[p])
                 if has_res:
                     self._gemm(pb, q + ".attn_out+res", [qs, xh], [weff, A[q + ".attn_res.w"]], o, y, taps=[1, 1], bias=A[q + ".attn.b"],
-                               per_sample=(1, 0), w_s=[B, 1])
+                               per_sample=(1, 0), w_s=[B, 1], w_k=[self.weff_k[p], xh.C])
                 else:
-                    self._gemm(pb, q + ".attn_out", [qs], [weff], o, y, taps=[1], bias=A[q + ".attn.b"], per_sample=(1,), w_s=[B], residual=xh)
+                    self._gemm(pb, q + ".attn_out", [qs], [weff], o, y, taps=[1], bias=A[q + ".attn.b"], per_sample=(1,), w_s=[B],
+                               w_k=[self.weff_k[p]], residual=xh)
             f1 = self._act(pb, q + ".f1", B, x.H, x.W, 2 * o)
             self._gemm(pb, q + ".ffn0", [y], [A[q + ".ffn0.w"]], 2 * o, f1, taps=[9], act=1)
             z = self._act(pb, q + ".z", B, x.H, x.W, o, stats=True)

@@ -171,6 +171,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// (A suspend-time hint on try_wait -- 20 us, so that a waiting warp sleeps in hardware instead of re-issuing the poll -- changes nothing:
+// profiles/r02s2_wait_hint_ab.txt.)
 // Bounded wait: a protocol bug must trap (kernel error) instead of hanging the GPU.  try_wait itself may block for a
 // driver-defined time slice, so the bound is wall-clock (%globaltimer, ns): 2 s without progress -> trap.
 __device__ __forceinline__ uint64_t global_ns() {

@@ -546,10 +546,13 @@ enum : int { kEpiRes = 1, kEpiAct = 2, kEpiStats = 4, kEpiNchw = 8 };
 
 template <int F>
 __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, int warp,
-                                                   int lane, int my_tiles, long long* dts, float* s_add) {
+                                                   int lane, int my_tiles, long long* dts, float* s_add, int grp, int ng, int slot, int tile_first, int tile_step) {
+  // tile_first / tile_step: the CTA's tiles are tile_first + k * tile_step, k < my_tiles (contiguous range for the halo conv, grid-strided for the
+  // column-softmax GEMM)
+  // grp / ng: this warp's tile group and the number of groups (2: warps 10..17; 4: + warps 0..7, which have no GroupNorm transform to do --
+  // then group g drains accumulator g alone); slot: this warp's 256-float vector in s_add
   constexpr bool kRes = (F & kEpiRes) != 0, kAct = (F & kEpiAct) != 0, kStats = (F & kEpiStats) != 0, kNchw = (F & kEpiNchw) != 0;
   const int q = warp & 3;
-  const int grp = (warp - 10) >> 2;
   const int row = q * 32 + lane;
   const int twl = p.tile_w_log2, tile_h = p.tile_h;
   const int ry = row >> twl, rx = row & ((1 << twl) - 1);
@@ -571,7 +574,7 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
   const bool four = p.nacc == 4;
   // per-warp additive vector (bias, or FiLM row of the tile's sample [+ bias]) in shared memory: with ~200 KB of dynamic
   // smem the L1 is a few KB, so per-tile __ldg of these vectors paid an L2 round trip per 16-channel chunk
-  float* addv = s_add + (warp - 10) * 256;
+  float* addv = s_add + slot * 256;
   const bool has_add = bias != nullptr || film != nullptr;
   const int nadd = (p.bn + 31) >> 5;  // values per lane
   if (!film && bias) {
@@ -585,9 +588,7 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
   int b, ty, tx, sb, sy, sx;
   {
     const int tpi = tiles_x * tiles_y;
-    int base, count;
-    halo_range(p, base, count);
-    const int m0 = base + grp, g2 = 2;
+    const int m0 = tile_first + grp * tile_step, g2 = ng * tile_step;
     b = m0 / tpi;
     int r = m0 - b * tpi;
     ty = r / tiles_x; tx = r - ty * tiles_x;
@@ -615,7 +616,8 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
     s2 = pk2(0.f, 0.f);
   };
   uint32_t it = 0;
-  for (int t = grp; t < my_tiles; t += 2, ++it) {
+  const bool solo = ng == 4;  // four groups: accumulator grp belongs to this group alone
+  for (int t = grp; t < my_tiles; t += ng, ++it) {
     const int y = ty * tile_h + ry, x = (tx << twl) + rx;
     const bool row_ok = (y < out_h) && (x < out_w);
     const size_t pix = ((size_t)b * out_h + y) * out_w + x;
@@ -642,10 +644,10 @@ __device__ __forceinline__ void halo_epilogue_loop(const HaloKParams& p, uint32_
       }
 #endif
     }
-    const uint32_t acc = (uint32_t)grp + (four ? 2u * (it & 1u) : 0u);
+    const uint32_t acc = solo ? (uint32_t)grp : (uint32_t)grp + (four ? 2u * (it & 1u) : 0u);
     const uint32_t tm_lane = tm_lane0 + acc * (uint32_t)p.bn;
     uint64_t* empty = &tmem_empty[acc];
-    mbar_wait(&tmem_full[acc], (four ? it >> 1 : it) & 1u);
+    mbar_wait(&tmem_full[acc], (solo ? it : (four ? it >> 1 : it)) & 1u);
     tc_fence_after();
     if (warp == 10 && lane == 0) h_ts(dts, 2, t, 0);
     if (film) {
@@ -768,8 +770,8 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   float* s_beta = s_gamma + p.cin;
   float2* s_stat = reinterpret_cast<float2*>(s_beta + p.cin);
   const int n_stat = p.gn_stats ? (p.batch < kHMaxStat ? p.batch : kHMaxStat) : 0;
-  float* s_add = reinterpret_cast<float*>(s_stat + ((n_stat + 1) & ~1));  // [8 epilogue warps][256], 16-byte aligned
-  float* s_dw = s_add + kHEpiWarps * 256;                                  // [9][cin] depthwise weights (depthwise mode)
+  float* s_add = reinterpret_cast<float*>(s_stat + ((n_stat + 1) & ~1));  // [8 epilogue warps (16 without the GN prologue)][256], 16-byte aligned
+  float* s_dw = s_add + (p.gn_stats ? 1 : 2) * kHEpiWarps * 256;          // [9][cin] depthwise weights (depthwise mode)
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_dw + (DW ? ((9 * p.cin + 3) & ~3) : 0));
   uint64_t* a_tma = bars;                       // [stages] TMA landed
   uint64_t* a_ready = bars + kHMaxStages;       // [stages] transformed (count 256)
@@ -844,7 +846,13 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
   }
   pdl_wait();  // everything below reads what earlier kernels of the step wrote
 
-  if (warp < 8) {
+  // Without the GroupNorm prologue warps 0..7 have nothing to transform: they can form two MORE epilogue groups (four in all, one per TMEM
+  // accumulator).
+  // Same-box A/B (profiles/r02s2_extra_epi_cs4pipe_ab.txt): a gain only where the epilogue is heavy AND has no global operand -- Swish without residual
+  // (FWM ffn0: 32 -> 64 @64^2 55.0 -> 51.4 us, 64 -> 128 @32^2 32.2 -> 30.7 us); with an epilogue-side residual four groups LOSE (128 -> 64 @32^2
+  // 40.0 -> 44.5 us), so those keep two.
+  const bool extra_epi = !gn && !DW && p.nacc == 4 && (F & kEpiAct) != 0 && (F & kEpiRes) == 0;
+  if (warp < 8 && !extra_epi) {
     if (gn) {
       // GroupNorm tables are private to the transform warps: the TMA producer, the MMA issuers and the epilogue warps start
       // their loops right after the dependency wait instead of behind this block's global loads + fp64 math.
@@ -934,9 +942,11 @@ __global__ void __launch_bounds__(kHThreads, 1) conv3x3_halo_tc_kernel(const __g
       }
       pdl_trigger();  // all loads of this CTA are in flight: the next kernel's CTAs may take over SMs as ours exit
     }
-  } else if (warp >= 10 && warp < 18) {
-    // ===================== epilogue (warps 10..17): two groups of 4 warps, one TMEM accumulator each =====================
-    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, dts, s_add);
+  } else if ((warp >= 10 && warp < 18) || warp < 8) {
+    // ===================== epilogue (warps 10..17 [+ 0..7]): groups of 4 warps =====================
+    const int grp = warp >= 10 ? (warp - 10) >> 2 : 2 + (warp >> 2);
+    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, dts, s_add, grp, extra_epi ? 4 : 2, warp >= 10 ? warp - 10 : 8 + warp,
+                          tile_base, 1);
     tc_fence_before();
   }
   __syncthreads();
@@ -983,6 +993,30 @@ __device__ __forceinline__ f32x2 cs_unpack_h2(uint32_t w) {
   return pk2(lo, hi);
 }
 
+// Warp roles of the column-softmax GEMM: kCsPipes transform groups of 4 warps (one ring each; tile t of the CTA's walk goes through pipeline
+// t % kCsPipes), 2 MMA warps (even / odd tiles), 2 epilogue groups of 4 warps (even / odd tiles), 1 TMA producer warp.  Same-box A/B of 2 pipelines
+// (608 threads, 96 registers) against 4 (864 threads, 72 registers, 76-212 bytes of spills), profiles/r02s2_cs_walk_ab.txt: dim 64 @64^2 73.2 vs
+// 73.0 us, dim 128 @64^2 124.4 vs 101.1 us, dim 128 @32^2 45.6 vs 48.9 us, whole step 5.422 vs 5.450 ms -> 2 (the transform is not what paces the
+// common dim-64 case).
+#ifndef DDIF_VAR_CS_PIPES  // tuning builds: 2 (608 threads, 96 registers) or 4 (864 threads, 72 registers)
+#define DDIF_VAR_CS_PIPES 2
+#endif
+static constexpr int kCsPipes = DDIF_VAR_CS_PIPES;
+// Tile walk of a CTA: grid-strided (tile c, c + G, ...: at any time neighbouring CTAs read neighbouring column groups of the same image lines, so
+// the 256-512 byte line segments of a tile's TMA box combine into full DRAM pages) unless DDIF_VAR_CS_CONTIG (contiguous ranges like the halo conv).
+__device__ __forceinline__ void cs_walk(const HaloKParams& p, int& first, int& step, int& count) {
+#ifdef DDIF_VAR_CS_CONTIG
+  halo_range(p, first, count);
+  step = 1;
+#else
+  first = (int)blockIdx.x;
+  step = (int)gridDim.x;
+  count = first < p.num_tiles ? (p.num_tiles - first + step - 1) / step : 0;
+#endif
+}
+static constexpr int kCsMmaWarp = 4 * kCsPipes, kCsEpiWarp = kCsMmaWarp + 2, kCsProdWarp = kCsEpiWarp + kHEpiWarps;
+static constexpr int kCsThreads = 32 * (kCsProdWarp + 1);
+
 template <int NCK>
 __device__ __forceinline__ void cs_transform_loop(const HaloKParams& p, uint32_t a_base, uint64_t* a_tma, uint64_t* a_ready, int tid) {
   constexpr int RQ = 128 / (8 * NCK);  // row blocks of 8 * NR rows: 2 (64-channel slabs) or 4 (32-channel slabs)
@@ -993,12 +1027,12 @@ __device__ __forceinline__ void cs_transform_loop(const HaloKParams& p, uint32_t
   const uint32_t sw = NCK == 8 ? (uint32_t)j : (((uint32_t)j >> 1) & 3u);  // rows j + 8 m all share the swizzle phase of row j
   const uint32_t off0 = (uint32_t)(j + 8 * rq * NR) * SPAN + (((uint32_t)c8 ^ sw) << 4);
   const int tw = 1 << p.tile_w_log2;
-  const uint32_t nst = (uint32_t)p.stages >> 1;
+  const uint32_t nst = (uint32_t)p.stages / kCsPipes;
   int remaining;
   {
-    int base, count;
-    halo_range(p, base, count);
-    remaining = count > grp ? ((count - grp + 1) / 2) * p.nslab : 0;  // this group's tiles (positions grp, grp + 2, ...) x K slabs
+    int first, step, count;
+    cs_walk(p, first, step, count);
+    remaining = count > grp ? ((count - grp + kCsPipes - 1) / kCsPipes) * p.nslab : 0;  // this group's tiles (positions grp, grp + P, ...) x K slabs
   }
   a_tma += grp * nst; a_ready += grp * nst;
   a_base += (uint32_t)grp * nst * p.stage_bytes;
@@ -1070,35 +1104,39 @@ __device__ __forceinline__ void cs_transform_loop(const HaloKParams& p, uint32_t
   }
 }
 
+// MMA warp w takes tiles t = w, w + 2, ... into TMEM accumulator w + 2 * (itn & 1); tile t runs in pipeline t % kCsPipes (4 pipelines: = that
+// accumulator index, the warp alternates between the rings w and w + 2; 2 pipelines: ring w).
 template <int KSTEPS>
 __device__ __forceinline__ void cs_mma_loop(const HaloKParams& p, uint32_t a_base, uint64_t* a_full, uint64_t* a_empty, uint64_t* tmem_full,
                                             uint64_t* tmem_empty, uint32_t tmem_base, int my_tiles, int w) {
-  const uint32_t span = (uint32_t)p.span, nst = (uint32_t)p.stages >> 1, stage16 = p.stage_bytes >> 4;
-  a_full += (uint32_t)w * nst; a_empty += (uint32_t)w * nst;
-  a_base += (uint32_t)w * nst * p.stage_bytes;
+  static_assert(kCsPipes == 4 || kCsPipes == 2, "pipelines");
+  const uint32_t span = (uint32_t)p.span, nst = (uint32_t)p.stages / kCsPipes, stage16 = p.stage_bytes >> 4;
   const uint64_t desc_a0 = make_smem_desc(a_base, 8u * span, p.layout_type);              // dense rows: SBO = 8 rows
   const uint64_t desc_b0 = make_smem_desc(a_base + p.a_bytes, 8u * span, p.layout_type);  // the stage's weight slab
-  uint32_t stage = 0, phase = 0, itn = 0;
-  const bool four = p.nacc == 4;
+  uint32_t st0 = 0, ph0 = 0, st1 = 0, ph1 = 0, itn = 0;  // ring state of pipelines w and (4 pipelines) w + 2
   for (int t = w; t < my_tiles; t += 2, ++itn) {
-    const uint32_t acc = (uint32_t)w + (four ? 2u * (itn & 1u) : 0u);
+    const uint32_t acc = (uint32_t)w + 2u * (itn & 1u);
+    const uint32_t hi = kCsPipes == 4 ? (itn & 1u) : 0u, pl = (uint32_t)w + 2u * hi;
     const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.bn;
-    mbar_wait(&tmem_empty[acc], ((four ? itn >> 1 : itn) & 1u) ^ 1u);
+    mbar_wait(&tmem_empty[acc], ((itn >> 1) & 1u) ^ 1u);
     tc_fence_after();
+    uint32_t stage = hi ? st1 : st0, phase = hi ? ph1 : ph0;
+    const uint32_t ring0 = pl * nst;
     for (int slab = 0; slab < p.nslab; ++slab) {
-      mbar_wait(&a_full[stage], phase);
+      mbar_wait(&a_full[ring0 + stage], phase);
       tc_fence_after();
-      const uint64_t so = (uint64_t)(stage * stage16);
+      const uint64_t so = (uint64_t)((ring0 + stage) * stage16);
       umma_bf16_ss_steps<KSTEPS>(tmem_d, desc_a0 + so, desc_b0 + so, p.idesc, slab != 0 ? 1u : 0u);
-      umma_commit_elect(&a_empty[stage]);
+      umma_commit_elect(&a_empty[ring0 + stage]);
       if (++stage == nst) { stage = 0; phase ^= 1u; }
     }
+    if (hi) { st1 = stage; ph1 = phase; } else { st0 = stage; ph0 = phase; }
     umma_commit_elect(&tmem_full[acc]);
   }
 }
 
 template <int F>
-__global__ void __launch_bounds__(kHThreads, 1) cs_gemm_tc_kernel(const __grid_constant__ HaloKParams p) {
+__global__ void __launch_bounds__(kCsThreads, 1) cs_gemm_tc_kernel(const __grid_constant__ HaloKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1114,13 +1152,13 @@ __global__ void __launch_bounds__(kHThreads, 1) cs_gemm_tc_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  int tile_base, my_tiles;
-  halo_range(p, tile_base, my_tiles);
-  if (warp == 18 && lane == 0) {
+  int tile_first, tile_step, my_tiles;
+  cs_walk(p, tile_first, tile_step, my_tiles);
+  if (warp == kCsProdWarp && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB[0]);
   }
-  if (warp == 8) {
+  if (warp == kCsMmaWarp) {
     if (lane == 0) {
       for (int i = 0; i < p.stages; ++i) {
         mbar_init(&a_tma[i], 1);
@@ -1143,22 +1181,25 @@ __global__ void __launch_bounds__(kHThreads, 1) cs_gemm_tc_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything below reads what earlier kernels of the step wrote
 
-  if (warp < 8) {
+  if (warp < kCsMmaWarp) {
     if (p.kslab == 64) cs_transform_loop<8>(p, smem_u32(smem_a), a_tma, a_ready, threadIdx.x);
     else cs_transform_loop<4>(p, smem_u32(smem_a), a_tma, a_ready, threadIdx.x);
-  } else if (warp == 8 || warp == 9) {
-    if (p.kslab == 64) cs_mma_loop<4>(p, smem_u32(smem_a), a_ready, a_empty, tmem_full, tmem_empty, tmem_base, my_tiles, warp - 8);
-    else cs_mma_loop<2>(p, smem_u32(smem_a), a_ready, a_empty, tmem_full, tmem_empty, tmem_base, my_tiles, warp - 8);
-  } else if (warp == 18) {
+  } else if (warp < kCsEpiWarp) {
+    if (p.kslab == 64) cs_mma_loop<4>(p, smem_u32(smem_a), a_ready, a_empty, tmem_full, tmem_empty, tmem_base, my_tiles, warp - kCsMmaWarp);
+    else cs_mma_loop<2>(p, smem_u32(smem_a), a_ready, a_empty, tmem_full, tmem_empty, tmem_base, my_tiles, warp - kCsMmaWarp);
+  } else if (warp == kCsProdWarp) {
     if (lane == 0) {
       const uint32_t tx = p.a_bytes + p.b_slot_bytes;
-      const uint32_t nst = (uint32_t)p.stages >> 1;
+      const uint32_t nst = (uint32_t)p.stages / kCsPipes;
       const int twl = p.tile_w_log2;
       HaloIter it;
-      it.init(p, tile_base, 1, tile_base + my_tiles);
-      uint32_t st0 = 0u, ph0 = 0u, st1 = 0u, ph1 = 0u, ring = 0u;
+      it.init(p, tile_first, tile_step, tile_first + my_tiles * tile_step);
+      // (stage, phase) of the kCsPipes rings packed into one word (8 bits per ring: stage | phase << 7): a run-time indexed array would live
+      // in local memory on this thread's dependent chain
+      uint32_t rstate = 0u, ring = 0u;
       for (; it.remaining > 0; it.next()) {
-        const uint32_t rs = ring ? st1 : st0, rp = ring ? ph1 : ph0;
+        const uint32_t sh = ring * 8u;
+        const uint32_t rs = (rstate >> sh) & 0x7fu, rp = (rstate >> (sh + 7u)) & 1u;
         const uint32_t stage = ring * nst + rs;
         uint8_t* dst = smem_a + (size_t)stage * p.stage_bytes;
         mbar_wait(&a_empty[stage], rp ^ 1u);
@@ -1169,18 +1210,19 @@ __global__ void __launch_bounds__(kHThreads, 1) cs_gemm_tc_kernel(const __grid_c
         {
           uint32_t ns = rs + 1u, np = rp;
           if (ns == nst) { ns = 0u; np ^= 1u; }
-          if (ring) { st1 = ns; ph1 = np; } else { st0 = ns; ph0 = np; }
+          rstate = (rstate & ~(0xffu << sh)) | ((ns | (np << 7)) << sh);
         }
-        if (it.slab == p.nslab - 1) ring ^= 1u;
+        if (it.slab == p.nslab - 1) ring = (ring + 1u) & (uint32_t)(kCsPipes - 1);
       }
       pdl_trigger();
     }
-  } else if (warp >= 10 && warp < 18) {
-    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, nullptr, s_add);
+  } else if (warp >= kCsEpiWarp && warp < kCsProdWarp) {
+    halo_epilogue_loop<F>(p, tmem_base, tmem_full, tmem_empty, warp, lane, my_tiles, nullptr, s_add, (warp - kCsEpiWarp) >> 2, 2, warp - kCsEpiWarp,
+                          tile_first, tile_step);
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kCsMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -1271,7 +1313,7 @@ static bool halo_geometry(const ddif_gemm_t& g, HaloGeom& h) {
   if (!g.out && !g.out_nchw) return false;
   h.cin = cin;
   h.n_stat = g.gn_stats ? (int)(g.batch < kHMaxStat ? g.batch : kHMaxStat) : 0;
-  h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + kHEpiWarps * 256 * 4 + (dw ? ((9 * cin + 3) & ~3) * 4 : 0) + (3 * kHMaxStages + 16) * 8 + 64 + 1024;
+  h.misc = 2 * ((cin + 3) & ~3) * 4 + ((h.n_stat + 1) & ~1) * 8 + (g.gn_stats ? 1 : 2) * kHEpiWarps * 256 * 4 + (dw ? ((9 * cin + 3) & ~3) * 4 : 0) + (3 * kHMaxStages + 16) * 8 + 64 + 1024;
   h.ntap_w = dw ? 1 : 9;
   // Resident weights of one CTA (9 taps x all K slabs x bn rows) must leave room for two rings of >= 2 halo stages:
   // split N over blockIdx.y (1, 2, 4 CTAs per tile) and, before splitting further, halve the K slab (smaller stages).
@@ -1484,9 +1526,10 @@ int cs_gemm_prepare(const ddif_gemm_t& g, GemmLaunch& L) {
   p.layout_type = p.span == 128 ? 2u : 4u;
   p.span_r = p.span; p.layout_r = p.layout_type;
   const int misc = kHEpiWarps * 256 * 4 + (3 * kHMaxStages + 16) * 8 + 64 + 1024;
-  int st = ((227 * 1024 - misc) / (int)p.stage_bytes) & ~1;
+  int st = (227 * 1024 - misc) / (int)p.stage_bytes;
   if (st > kHMaxStages) st = kHMaxStages;
-  if (st < 2) return DDIF_ERR_SHAPE;
+  st = st / kCsPipes * kCsPipes;  // one ring per pipeline
+  if (st < kCsPipes) return DDIF_ERR_SHAPE;
   p.stages = st;
   p.nacc = 4;
   uint32_t cols = 32;
@@ -1540,7 +1583,7 @@ int cs_gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   const HaloKParams& p = *reinterpret_cast<const HaloKParams*>(L.kparams);
   CsKernel k = cs_kernel(L.flags);
   if (!k) return DDIF_ERR_STATE;
-  DDIF_CUDA_CHECK(launch_pdl(k, dim3(L.grid_x, L.grid_y), dim3(kHThreads), (size_t)L.smem_bytes, stream, p));
+  DDIF_CUDA_CHECK(launch_pdl(k, dim3(L.grid_x, L.grid_y), dim3(kCsThreads), (size_t)L.smem_bytes, stream, p));
   return DDIF_OK;
 }
 

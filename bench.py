@@ -138,6 +138,31 @@ def cpu_reference_run(cpu_batch: int, timesteps: int, steps: int, warmup: int):
                        f"patches/s extrapolated to T={timesteps}")
 
 
+def cpu_config0_run():
+    """BASELINE configs[0] exactly as written -- WV3 batch 1, DPM-Solver++ 2M with 20 steps, fp32 on the CPU -- with the oracle port on all host
+    cores: ms per complete sampling (20 UNet forwards + the solver updates), one warm-up sampling, one timed."""
+    import torch
+    from dif_pan_b200 import synth
+    from oracle import sampler_oracle as so, unet_oracle as uo
+
+    torch.set_grad_enabled(False)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kw = synth.unet_kwargs("wv3")
+    sd = synth.make_state_dict(0, **kw)
+    kw2 = dict(kw)
+    kw2.pop("dropout")
+    cfg = uo.UNetCfg(**kw2)
+    cond = synth.make_batch("wv3", 1, seed=1)["cond"]
+    ns = so.VPSchedule(torch.tensor(so.make_beta_schedule("cosine", 500), dtype=torch.float32))
+    model = lambda x, t, c, sc: uo.unet_forward(sd, cfg, x, t, c, x)
+    x_T = torch.randn(1, 8, 64, 64, generator=torch.Generator().manual_seed(0))
+    so.dpmpp_multistep_sample(model, ns, x_T.clone(), cond, steps=2, order=2)
+    t0 = time.perf_counter()
+    so.dpmpp_multistep_sample(model, ns, x_T.clone(), cond, steps=20, order=2)
+    return dict(cpu_ms_per_sampling=(time.perf_counter() - t0) * 1e3, cores=cores, kind="port")
+
+
 def gpu_eager_run(dev, batches=(1, 32, 256), nsteps=20):
     """The reference algorithm (oracle port = functional restatement of models/sr3_dwt.py + the DDPM posterior, pinned to the reference's
     golden vectors) as EAGER PyTorch on this GPU: cuDNN convolutions (channels-last, cudnn.benchmark), native group_norm, cuBLAS bmm -- what
@@ -215,6 +240,13 @@ def other_configs_run(dev):
     x_T = torch.randn(1, 8, 64, 64, device=dev)
     ms = timed(lambda: dp.sample_cond(net, cond, 8, "dpm20", x_T=x_T), warm=2)
     out["configs[0] WV3 B=1 DPM-Solver++ 2M-20"] = dict(ms_per_sampling=ms, patches_per_s=1e3 / ms, ms_per_denoise_step=ms / 20)
+    try:  # the same configuration on the host CPU (BASELINE configs[0] is the reference's CPU-runnable case)
+        c0 = cpu_config0_run()
+        out["configs[0] WV3 B=1 DPM-Solver++ 2M-20"].update(cpu_reference_ms_per_sampling=c0["cpu_ms_per_sampling"], cpu_cores=c0["cores"],
+                                                            cpu_kind=c0["kind"], speedup_vs_cpu=c0["cpu_ms_per_sampling"] / ms)
+    except Exception as e:
+        out["configs[0] WV3 B=1 DPM-Solver++ 2M-20"]["cpu_error"] = repr(e)[:200]
+    torch.set_grad_enabled(False)
     del net
     net = net_for("gf2")
     d = synth.make_batch("gf2", 1, size=512, seed=2)
@@ -359,6 +391,23 @@ def main():
             if var[i] >= 0:
                 d = per.setdefault(names[var[i]], dict(ms=0.0, ref_flops=0.0, executed_flops=0.0, bytes=0.0, launches=0))
                 d["ms"] += r[2]; d["ref_flops"] += ops[i].ref_flops; d["executed_flops"] += r[3]; d["bytes"] += r[4]; d["launches"] += 1
+        # Physical floor of every halo-conv launch: max(algorithmic bytes / HBM peak, MMA issue time).  One M128 x N x K16 tcgen05.mma cannot
+        # issue faster than max(44.8, N / 2) cycles (profiles/r01_microbench_umma_rate.txt), so with this network's N = 32 / 64 the tensor pipe
+        # tops out at 36 % / 71 % of its peak whatever the kernel does; N is taken unsplit (a lower bound of the issue time).
+        sm_hz = 1.965e9
+        floor_ms = {"hbm": 0.0, "mma_issue": 0.0, "max": 0.0}
+        for i, r in enumerate(rows):
+            if var[i] != 2:
+                continue
+            f = ops[i].fields
+            tiles = f["batch"] * ((f["out_h"] + 15) // 16) * ((f["out_w"] + 7) // 8)
+            if f.get("dw_w"):
+                k16 = sum(f["a_c"]) / 16.0 * 2
+            else:
+                k16 = sum(t * c for t, c in zip(f["taps"], f["a_c"])) / 16.0
+            mma = tiles * k16 * max(44.8, f["n_pad"] / 2.0) / (148 * sm_hz) * 1e3
+            hbm = r[4] / (pk["hbm_gbs"] * 1e9) * 1e3
+            floor_ms["hbm"] += hbm; floor_ms["mma_issue"] += mma; floor_ms["max"] += max(hbm, mma)
         dom = max(per, key=lambda k: per[k]["ms"])
         d = per[dom]
         traffic = None
@@ -377,6 +426,11 @@ def main():
                                   frac=d["ref_flops"] / (in_graph * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
                                   how="share of the eager per-launch events x measured in-graph step time"),
                     launches_per_denoise_step=d["launches"], avg_launch_ms=d["ms"] / d["launches"], share_of_step=d["ms"] / tot_ms,
+                    floor=dict(hbm_ms=floor_ms["hbm"], mma_issue_ms=floor_ms["mma_issue"], per_launch_max_ms=floor_ms["max"],
+                               measured_ms=per.get("conv3x3_halo_tc_kernel", d)["ms"],
+                               frac_of_floor=floor_ms["max"] / per.get("conv3x3_halo_tc_kernel", d)["ms"],
+                               how="sum over the halo conv launches of max(algorithmic bytes / HBM peak, tiles x K16 steps x max(44.8, N/2) cycles "
+                                   "/ 148 SMs at 1.965 GHz): the tcgen05.mma issue-rate floor at this network's small N"),
                     algorithmic_flops_per_launch=d["ref_flops"] / d["launches"], executed_flops_per_launch=d["executed_flops"] / d["launches"],
                     algorithmic_bytes_per_launch=d["bytes"] / d["launches"],
                     hbm=dict(achieved=d["bytes"] / (d["ms"] * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s",

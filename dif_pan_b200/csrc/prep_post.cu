@@ -39,97 +39,102 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 }
 
 // ---- fused conditioning prep ----------------------------------------------------------------------------------------
-// Haar coefficient k (0 LL, 1 cH, 2 cV, 3 cD) of the 2x2 block (by, bx) of one plane, scaled by inv = 1 / division.  The multiply by the
-// reciprocal (<= 1.5 ulp from the IEEE division of haar_dwt2_kernel) replaces eight ~18-instruction divisions per thread: ncu showed
-// this kernel instruction-bound on them (FCHK + slow path), 333 us for 64 WV3 scenes of 256x256.
-__device__ __forceinline__ float haar_coef(const float* __restrict__ pl, int w, int by, int bx, int k, float inv) {
-  const float2 r0 = *reinterpret_cast<const float2*>(pl + (size_t)(2 * by) * w + 2 * bx);
-  const float2 r1 = *reinterpret_cast<const float2*>(pl + (size_t)(2 * by + 1) * w + 2 * bx);
-  const float ab = ADD(r0.x, r0.y), cd = ADD(r1.x, r1.y), amb = SUB(r0.x, r0.y), cmd = SUB(r1.x, r1.y);
-  float v;
-  if (k == 0) v = ADD(ab, cd);
-  else if (k == 1) v = SUB(ab, cd);
-  else if (k == 2) v = ADD(amb, cmd);
-  else v = SUB(amb, cmd);
-  return MUL(MUL(v, 0.5f), inv);
-}
+// One CTA (256 threads) per 32 x 64 pixel tile of one INPUT plane (lms band or pan band); grid (tiles, c + p, batch), 32-bit indexing.  The CTA
+// writes everything that derives from that plane: the scaled copy (cond channel) and the bilinear x2 of its Haar sub-bands (LL for an lms band; the
+// three detail bands for a pan band) -- so every input element is read once (+ a one-coefficient halo) instead of once per derived channel.
+// The coefficients the tile's outputs need -- (32/2 + 2) x (64/2 + 2) per sub-band, with index clamping at the image edges, exactly the clamped
+// rows / columns the per-output expressions pick -- are computed ONCE into shared memory (two float2 loads give all four sub-bands of a 2x2
+// block); every thread then forms its 4 consecutive outputs per sub-band from 8 shared-memory values.  Round 1 recomputed 8 coefficients per
+// thread and channel (~500 instructions per 4 outputs) and ran at 0.21-0.25 of the HBM rate.
+static constexpr int kWcTh = 32, kWcTw = 64, kWcCh = kWcTh / 2 + 2, kWcCw = kWcTw / 2 + 2;
 
-// grid (ceil(h * w/4 / 256), channels of cond, batch): one thread per 4 consecutive output pixels of one cond plane, 32-bit indexing.
-// A wavelet-channel thread needs coefficient columns 2q-1 .. 2q+2 of two coefficient rows for its 4 bilinear outputs: 8 Haar
-// coefficients (16 float2 loads) instead of 16 per 4 outputs, and it also emits the two raw coefficients of its 2x2 blocks.
 __global__ void __launch_bounds__(256) wavelet_cond_kernel(ddif_wavelet_cond_t p) {
-  const int c = (int)p.c, pp = (int)p.p, h = (int)p.h, w = (int)p.w, hh = h / 2, wh = w / 2, wq = w / 4;
+  __shared__ float cs[3][kWcCh][kWcCw + 1];
+  const int c = (int)p.c, pp = (int)p.p, h = (int)p.h, w = (int)p.w, hh = h / 2, wh = w / 2;
   const int cw = c + 3 * pp, ct = c + pp + cw;
-  const int ch = blockIdx.y, b = blockIdx.z;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= h * wq) return;
-  const int oy = idx / wq, q = idx - oy * wq;
+  const int plane = blockIdx.y, b = blockIdx.z;
+  const bool is_lms = plane < c;
+  const int nsub = is_lms ? 1 : 3;  // sub-bands derived from this plane
+  const int tiles_x = (w + kWcTw - 1) / kWcTw;
+  const int ty = (int)blockIdx.x / tiles_x, tx = (int)blockIdx.x - ty * tiles_x;
+  const int oy0 = ty * kWcTh, ox0 = tx * kWcTw;
   const size_t hw = (size_t)h * w;
-  const float dv = (float)(1.0 / p.divisor);  // reciprocal, see haar_coef
-  float4* dst = reinterpret_cast<float4*>(p.cond + ((size_t)b * ct + ch) * hw + (size_t)oy * w + 4 * q);
-  if (ch < c + pp) {
-    const float* src = ch < c ? p.lms + ((size_t)b * c + ch) * hw : p.pan + ((size_t)b * pp + (ch - c)) * hw;
-    const float4 v = *reinterpret_cast<const float4*>(src + (size_t)oy * w + 4 * q);
-    *dst = make_float4(MUL(v.x, dv), MUL(v.y, dv), MUL(v.z, dv), MUL(v.w, dv));
-    return;
-  }
-  const int k = ch - c - pp;  // wavelet channel: [LL(lms) x c | pan sub-band 0 x p | sub-band 1 x p | sub-band 2 x p]
-  const float* pl;
-  int coef;
-  if (k < c) {
-    pl = p.lms + ((size_t)b * c + k) * hw;
-    coef = 0;
-  } else {
-    const int g = (k - c) / pp, j = (k - c) % pp;
-    pl = p.pan + ((size_t)b * pp + j) * hw;
-    coef = p.order == 0 ? (g == 0 ? 1 : (g == 1 ? 3 : 2)) : g + 1;  // Pan: h, d, v;  HISR: h, v, d
-  }
-  float sy = 0.5f * ((float)oy + 0.5f) - 0.5f;
-  if (sy < 0.f) sy = 0.f;
-  int y0 = (int)sy;
-  if (y0 > hh - 1) y0 = hh - 1;
-  const int y1 = y0 + (y0 < hh - 1 ? 1 : 0);
-  const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
-  float cf[2][4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    int bx = 2 * q - 1 + j;
+  const float dv = (float)(1.0 / p.divisor);  // reciprocal (<= 1.5 ulp from the IEEE division of haar_dwt2_kernel): the divisions made the first
+                                              // version of this kernel instruction-bound (FCHK + slow path)
+  const float* pl = is_lms ? p.lms + ((size_t)b * c + plane) * hw : p.pan + ((size_t)b * pp + (plane - c)) * hw;
+  // coefficient tiles: slot (i, j) = block (clamp(ry0 + i), clamp(rx0 + j)); edge rows / columns repeat like the clamped bilinear taps
+  const int ry0 = oy0 / 2 - 1, rx0 = ox0 / 2 - 1;
+  for (int s = threadIdx.x; s < kWcCh * kWcCw; s += 256) {
+    const int i = s / kWcCw, j = s - i * kWcCw;
+    int by = ry0 + i, bx = rx0 + j;
+    by = by < 0 ? 0 : (by > hh - 1 ? hh - 1 : by);
     bx = bx < 0 ? 0 : (bx > wh - 1 ? wh - 1 : bx);
-    cf[0][j] = haar_coef(pl, w, y0, bx, coef, dv);
-    cf[1][j] = y1 == y0 ? cf[0][j] : haar_coef(pl, w, y1, bx, coef, dv);
+    const float2 r0 = *reinterpret_cast<const float2*>(pl + (size_t)(2 * by) * w + 2 * bx);
+    const float2 r1 = *reinterpret_cast<const float2*>(pl + (size_t)(2 * by + 1) * w + 2 * bx);
+    const float ab = ADD(r0.x, r0.y), cd = ADD(r1.x, r1.y), amb = SUB(r0.x, r0.y), cmd = SUB(r1.x, r1.y);
+    if (is_lms) {
+      cs[0][i][j] = MUL(MUL(ADD(ab, cd), 0.5f), dv);                       // LL
+    } else {
+      const float vh = MUL(MUL(SUB(ab, cd), 0.5f), dv), vv = MUL(MUL(ADD(amb, cmd), 0.5f), dv), vd = MUL(MUL(SUB(amb, cmd), 0.5f), dv);
+      cs[0][i][j] = vh;                                                    // group 0: cH
+      cs[1][i][j] = p.order == 0 ? vd : vv;                                // Pan: h, d, v;  HISR: h, v, d
+      cs[2][i][j] = p.order == 0 ? vv : vd;
+    }
   }
-  float o[4];
+  __syncthreads();
+  for (int qd = threadIdx.x; qd < kWcTh * kWcTw / 4; qd += 256) {  // quads of 4 consecutive output pixels
+    const int ly = qd / (kWcTw / 4), q4 = qd - ly * (kWcTw / 4);
+    const int oy = oy0 + ly, ox = ox0 + 4 * q4;
+    if (oy >= h || ox >= w) continue;                       // w % 4 == 0: a quad is entirely inside or outside
+    const size_t px = (size_t)oy * w + ox;
+    {  // scaled copy: cond channel `plane`
+      const float4 v = *reinterpret_cast<const float4*>(pl + px);
+      *reinterpret_cast<float4*>(p.cond + ((size_t)b * ct + plane) * hw + px) = make_float4(MUL(v.x, dv), MUL(v.y, dv), MUL(v.z, dv), MUL(v.w, dv));
+    }
+    float sy = 0.5f * ((float)oy + 0.5f) - 0.5f;
+    if (sy < 0.f) sy = 0.f;
+    int y0 = (int)sy;
+    if (y0 > hh - 1) y0 = hh - 1;
+    const int y1 = y0 + (y0 < hh - 1 ? 1 : 0);
+    const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+    int xi0[4], xi1[4];
+    float lx1v[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int ox = 4 * q + e;
-    float sx = 0.5f * ((float)ox + 0.5f) - 0.5f;
-    if (sx < 0.f) sx = 0.f;
-    int x0 = (int)sx;
-    if (x0 > wh - 1) x0 = wh - 1;
-    const int x1 = x0 + (x0 < wh - 1 ? 1 : 0);
-    const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
-    // cached column index of coefficient column x: x - (2q - 1), valid after the same clamping (edge columns repeat)
-    int j0 = x0 - (2 * q - 1), j1 = x1 - (2 * q - 1);
-    j0 = j0 < 0 ? 0 : (j0 > 3 ? 3 : j0);
-    j1 = j1 < 0 ? 0 : (j1 > 3 ? 3 : j1);
-    float v00, v01, v10, v11;
-    // compile-time indices after unrolling e: (e=0: cols 0,1) (e=1,2: cols 1,2) (e=3: cols 2,3), except at the clamped image edges
-    v00 = j0 == 0 ? cf[0][0] : (j0 == 1 ? cf[0][1] : (j0 == 2 ? cf[0][2] : cf[0][3]));
-    v01 = j1 == 0 ? cf[0][0] : (j1 == 1 ? cf[0][1] : (j1 == 2 ? cf[0][2] : cf[0][3]));
-    v10 = j0 == 0 ? cf[1][0] : (j0 == 1 ? cf[1][1] : (j0 == 2 ? cf[1][2] : cf[1][3]));
-    v11 = j1 == 0 ? cf[1][0] : (j1 == 1 ? cf[1][1] : (j1 == 2 ? cf[1][2] : cf[1][3]));
-    o[e] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);  // same expression as cond_assemble_kernel
-  }
-  *dst = make_float4(o[0], o[1], o[2], o[3]);
-  if (p.wav && !(oy & 1)) {  // raw coefficients of blocks (oy/2, 2q) and (oy/2, 2q+1): row oy/2 is y1 (y0 at the top edge)
-    const int r = (y1 == (oy >> 1)) ? 1 : 0;
-    *reinterpret_cast<float2*>(p.wav + (((size_t)b * cw + k) * hh + (oy >> 1)) * wh + 2 * q) = make_float2(cf[r][1], cf[r][2]);
+    for (int e = 0; e < 4; ++e) {
+      float sx = 0.5f * ((float)(ox + e) + 0.5f) - 0.5f;
+      if (sx < 0.f) sx = 0.f;
+      int x0 = (int)sx;
+      if (x0 > wh - 1) x0 = wh - 1;
+      const int x1 = x0 + (x0 < wh - 1 ? 1 : 0);
+      lx1v[e] = sx - (float)x0;
+      xi0[e] = x0 - rx0;
+      xi1[e] = x1 - rx0;
+    }
+    for (int g = 0; g < nsub; ++g) {
+      // wavelet channel k: [LL(lms) x c | pan sub-band 0 x p | sub-band 1 x p | sub-band 2 x p]
+      const int k = is_lms ? plane : c + g * pp + (plane - c);
+      const float* r0 = cs[g][y0 - ry0];
+      const float* r1 = cs[g][y1 - ry0];
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lx1 = lx1v[e], lx0 = 1.f - lx1;
+        const float v00 = r0[xi0[e]], v01 = r0[xi1[e]], v10 = r1[xi0[e]], v11 = r1[xi1[e]];
+        o[e] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);  // same expression as cond_assemble_kernel
+      }
+      *reinterpret_cast<float4*>(p.cond + ((size_t)b * ct + c + pp + k) * hw + px) = make_float4(o[0], o[1], o[2], o[3]);
+      if (p.wav && !(oy & 1)) {  // raw coefficients of blocks (oy/2, ox/2) and (oy/2, ox/2 + 1)
+        const float* rr = cs[g][(oy >> 1) - ry0];
+        *reinterpret_cast<float2*>(p.wav + (((size_t)b * cw + k) * hh + (oy >> 1)) * wh + (ox >> 1)) = make_float2(rr[(ox >> 1) - rx0], rr[(ox >> 1) + 1 - rx0]);
+      }
+    }
   }
 }
 int launch_wavelet_cond(const ddif_wavelet_cond_t& p, cudaStream_t s) {
   if (p.h % 2 || p.w % 4 || p.c < 1 || p.p < 1 || p.order < 0 || p.order > 1 || p.batch > 65535 || p.h * p.w > (1 << 28)) return DDIF_ERR_SHAPE;
   if (p.batch < 1) return DDIF_OK;
-  const dim3 grid((unsigned)ceil_div(p.h * (p.w / 4), 256), (unsigned)(2 * p.c + 4 * p.p), (unsigned)p.batch);
+  const int64_t tiles = ceil_div(p.h, (int64_t)kWcTh) * ceil_div(p.w, (int64_t)kWcTw);
+  const dim3 grid((unsigned)tiles, (unsigned)(p.c + p.p), (unsigned)p.batch);
   wavelet_cond_kernel<<<grid, 256, 0, s>>>(p);
   DDIF_LAUNCH_CHECK();
   return DDIF_OK;

@@ -131,6 +131,7 @@ def load() -> ctypes.CDLL:
     lib.ddif_plan_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     lib.ddif_plan_graph_build.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     lib.ddif_plan_graph_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.ddif_plan_set_side_branch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.ddif_plan_profile.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     for name in ("ddif_haar_dwt2_f32", "ddif_haar_idwt2_f32", "ddif_cond_assemble_f32", "ddif_ddpm_step_f32",
                  "ddif_ddim_step_f32", "ddif_dpmpp_step_f32", "ddif_q_sample_f32", "ddif_conv_igemm_bf16", "ddif_dpm_single_f32", "ddif_loss_f32", "ddif_dpm_err_f32", "ddif_multi_tensor_f32",

@@ -162,6 +162,9 @@ struct ddif_plan {
   std::vector<ddif::Op> ops;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
+  // side branch of the captured graph (ddif_plan_set_side_branch): ops [side_first, side_last) run concurrently with the ops that follow them,
+  // op join_before is the first one that needs their results
+  int side_first = -1, side_last = -1, join_before = -1;
 };
 
 extern "C" {
@@ -234,10 +237,41 @@ int ddif_plan_graph_build(ddif_plan_t* plan, ddif_stream_t stream) {
   if (!plan) return DDIF_ERR_ARG;
   if (plan->exec) return DDIF_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  const int n = (int)plan->ops.size();
+  const bool fork = plan->side_first >= 0 && plan->side_first < plan->side_last && plan->side_last <= plan->join_before && plan->join_before < n;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (fork) {  // created before the capture starts; destroyed after it ends (the graph keeps the dependency edges, not the objects)
+    DDIF_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    DDIF_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    DDIF_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
   DDIF_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-  int rc = ddif_plan_run(plan, 0, -1, stream);
+  int rc = DDIF_OK;
+  if (!fork) {
+    rc = ddif_plan_run(plan, 0, -1, stream);
+  } else {
+    cudaError_t ce = cudaSuccess;
+    for (int i = 0; i < n && rc == DDIF_OK && ce == cudaSuccess; ++i) {
+      if (i == plan->side_first) {
+        ce = cudaEventRecord(ev_fork, s);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(side, ev_fork, 0);
+      }
+      if (i == plan->join_before && ce == cudaSuccess) ce = cudaStreamWaitEvent(s, ev_join, 0);
+      if (ce != cudaSuccess) break;
+      const bool on_side = i >= plan->side_first && i < plan->side_last;
+      rc = ddif::dispatch(plan->ops[i], on_side ? side : s);
+      if (on_side && i == plan->side_last - 1 && rc == DDIF_OK) ce = cudaEventRecord(ev_join, side);
+    }
+    if (rc == DDIF_OK && ce != cudaSuccess) rc = (int)ce;
+  }
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(s, &g);
+  if (fork) {
+    cudaEventDestroy(ev_fork);
+    cudaEventDestroy(ev_join);
+    cudaStreamDestroy(side);
+  }
   if (rc != DDIF_OK) {
     if (g) cudaGraphDestroy(g);
     return rc;
@@ -245,6 +279,19 @@ int ddif_plan_graph_build(ddif_plan_t* plan, ddif_stream_t stream) {
   if (e != cudaSuccess) return (int)e;
   plan->graph = g;
   DDIF_CUDA_CHECK(cudaGraphInstantiate(&plan->exec, g, 0));
+  return DDIF_OK;
+}
+
+int ddif_plan_set_side_branch(ddif_plan_t* plan, int first, int last, int join_before) {
+  if (!plan) return DDIF_ERR_ARG;
+  if (plan->exec) return DDIF_ERR_STATE;
+  const int n = (int)plan->ops.size();
+  if (first < 0) {  // clear
+    plan->side_first = plan->side_last = plan->join_before = -1;
+    return DDIF_OK;
+  }
+  if (first >= last || last > join_before || join_before >= n) return DDIF_ERR_ARG;
+  plan->side_first = first; plan->side_last = last; plan->join_before = join_before;
   return DDIF_OK;
 }
 

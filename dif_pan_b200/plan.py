@@ -151,6 +151,10 @@ class PlanBuilder:
         with _lib.guard(stream):
             _lib.check(_lib.load().ddif_plan_run(self.handle, first, last, ctypes.c_void_p(stream)), "ddif_plan_run")
 
+    def set_side_branch(self, first: int, last: int, join_before: int) -> None:
+        """Ops [first, last) become a side branch of the captured graph, joined before op `join_before` (ddif_plan_set_side_branch)."""
+        _lib.check(_lib.load().ddif_plan_set_side_branch(self.handle, first, last, join_before), "ddif_plan_set_side_branch")
+
     def graph_build(self, stream: int) -> None:
         with _lib.guard(stream):
             _lib.check(_lib.load().ddif_plan_graph_build(self.handle, ctypes.c_void_p(stream)), "ddif_plan_graph_build")

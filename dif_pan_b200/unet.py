@@ -706,7 +706,7 @@ def _resolve_cache(pb: PlanBuilder, cache_base: int) -> None:
 class _Runtime:
     """Device buffers + recorded plans of one UNetSR3 at a fixed (B, H, W)."""
 
-    def __init__(self, net: UNetSR3, B: int, H: int, W: int, **schedule_options):
+    def __init__(self, net: UNetSR3, B: int, H: int, W: int, use_side_branch: bool = True, **schedule_options):
         _lib.load()
         P = net._packed
         dev = next(net.parameters()).device
@@ -733,6 +733,13 @@ class _Runtime:
         for pb in (sch.cnd, sch.fwd):
             _resolve_cache(pb, self.cache.data_ptr())
             pb.finalize(self.ws.data_ptr(), device=dev)
+        # The time embedding + FiLM vectors (one latency-bound launch, ~30 us) run as a side branch of the step graph, concurrently with the
+        # input conversion and the first convs; the first op that adds a FiLM vector joins it.  Its output buffer is live from op 1 to the last
+        # FiLM consumer, so the liveness packer never aliases it with anything those ops touch.
+        te = next(i for i, op in enumerate(sch.fwd.ops) if op.struct == "ddif_time_embed_t")
+        users = [i for i, op in enumerate(sch.fwd.ops) if i > te and op.fields.get("film") is not None]
+        if use_side_branch and users and users[0] > te + 1:
+            sch.fwd.set_side_branch(te, te + 1, users[0])
         self.cond_key = None
         self.graph_ready = False
         self.use_graph = True

@@ -263,13 +263,18 @@ void ddif_plan_destroy(ddif_plan_t* plan);
 /* Record an op (parameters are copied; GEMM tensor maps are encoded once here). Returns op index or <0. */
 int ddif_plan_add(ddif_plan_t* plan, int kind, const void* params);
 int ddif_plan_size(const ddif_plan_t* plan);
-/* Which kernel a recorded DDIF_OP_GEMM resolved to: 0 conv_igemm_tc_kernel, 2 conv3x3_halo_tc_kernel; -1 for every other op kind
+/* Which kernel a recorded DDIF_OP_GEMM resolved to: 0 conv_igemm_tc_kernel, 2 conv3x3_halo_tc_kernel, 3 cs_gemm_tc_kernel; -1 for every other op kind
  * (used by bench.py to attribute time per kernel). */
 int ddif_plan_op_variant(const ddif_plan_t* plan, int index);
 /* Enqueue ops [first, last) on `stream` (last<0 = all). */
 int ddif_plan_run(ddif_plan_t* plan, int first, int last, ddif_stream_t stream);
 /* Capture the whole plan into a CUDA graph once, then replay it. */
 int ddif_plan_graph_build(ddif_plan_t* plan, ddif_stream_t stream);
+/* Before ddif_plan_graph_build: ops [first, last) form a SIDE BRANCH of the captured graph -- they depend on everything before `first`, run
+ * concurrently with the ops after them, and op `join_before` (> last - 1) is the first that waits for them.  The caller guarantees that no op in
+ * [last, join_before) reads or writes what the branch writes.  Used for the time embedding + FiLM vectors (sr3_dwt.py:57-64,223-257), a
+ * latency-bound launch whose first consumer is the FiLM add of the first ResBlock.  first < 0 clears.  ddif_plan_run ignores it (one stream). */
+int ddif_plan_set_side_branch(ddif_plan_t* plan, int first, int last, int join_before);
 int ddif_plan_graph_launch(ddif_plan_t* plan, ddif_stream_t stream);
 /* Profiling: run the plan with a CUDA event pair around every op; ms[i] = duration of op i, kinds[i] = its kind. */
 int ddif_plan_profile(ddif_plan_t* plan, ddif_stream_t stream, float* ms, int* kinds, int capacity);

@@ -74,7 +74,15 @@ def test_schedule_structure(dataset, B, H, W):
     assert kinds.count("ddif_gemm_t") == 12 * 3 + 16 * 6 + 4 + (0 if fused_attn else 8 * 2) + 1 + 3 + 3 + 1
     assert kinds.count("ddif_attn_t") == (0 if fused_attn else 8)
     assert kinds.count("ddif_attn_block_t") == (8 if fused_attn else 0)
-    assert kinds.count("ddif_softmax_h_t") == 16
+    # FWM softmax over H is fused into the attn_out GEMM's loader (cs_gemm_tc_kernel) for the merged-q decoder blocks whose level has 16, 32 or
+    # 64 lines and a width that is a multiple of 128 / lines; the others keep the stand-alone softmax kernel (8x8 level, 128-line level, dim + o > 192)
+    cs = [op for op in s.fwd.ops if op.struct == "ddif_gemm_t" and op.fields.get("a_softmax_h")]
+    assert len(cs) == (7 if (H, W) == (128, 64) else 11)
+    assert kinds.count("ddif_softmax_h_t") == 16 - len(cs)
+    for op in cs:
+        f = op.fields
+        assert f["out_h"] in (16, 32, 64) and f["out_w"] % (128 // f["out_h"]) == 0 and f["taps"][0] == 1 and f["w_per_sample"][0] == 1
+        assert f["a_c"][0] % 64 == 0 and f["a_c"][0] == f["w_k"][0] and f["a_c"][0] <= f["a_ld"][0] and f["residual"] is not None
     # GroupNorm+Swish of every 3x3 conv is fused into the conv's loader (all 30 resblocks x 2 + final conv);
     # stand-alone normalisation launches left: 8 attention norms + 5 FWM prenorm(+dw) -- the other 11 decoder blocks get
     # r = attn_res(x_hat) as extra output channels of the q conv (dim + o <= 192), so x_hat is never materialised

@@ -209,6 +209,9 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
       if (++stage == nst) { stage = 0; phase ^= 1u; }
       continue;
     }
+#ifdef DDIF_VAR_TS2  // probe build: stamp 0 = top of the conv-slab iteration (after a residual relay), 1 = tables ready, 2 = landed, 3 = arrived
+    if (tid == 0) h_ts(dts, 3, tcount, 0);
+#endif
     if (it.b != cur_b || it.slab != cur_slab) {
       cur_b = it.b; cur_slab = it.slab;
       float mean, rstd;
@@ -230,9 +233,15 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
     }
     const int y0 = it.ty * 16 - 1, x0 = it.tx * 8 - 1;
     const uint32_t sbase = a_base + stage * p.stage_bytes;
+#ifdef DDIF_VAR_TS2
+    if (tid == 0) h_ts(dts, 3, tcount, 1);
+    mbar_wait(&a_tma[stage], phase);
+    if (tid == 0) h_ts(dts, 3, tcount, 2);
+#else
     if (tid == 0) h_ts(dts, 3, tcount, 0);
     mbar_wait(&a_tma[stage], phase);
     if (tid == 0) h_ts(dts, 3, tcount, 1);
+#endif
 #ifndef DDIF_VAR_NO_XFORM
     // Branch-free: every chunk is loaded and normalised unconditionally (rows past the halo / padding pixels compute on
     // whatever is there) and only the STORE is predicated, so the BATCH chunks of a thread form independent dependency
@@ -268,7 +277,9 @@ __device__ __forceinline__ void halo_transform_loop(const HaloKParams& p, uint32
         if (ok[k]) h_sts128(sbase + (tab[k0 + k] & 0xffffu), v[k]);
     }
 #endif
+#ifndef DDIF_VAR_TS2
     if (tid == 0) h_ts(dts, 3, tcount, 2);
+#endif
     h_fence_proxy_async();
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&a_ready[stage]);  // one arrive per warp (count kHxfGroup / 32)

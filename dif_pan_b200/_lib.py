@@ -62,6 +62,7 @@ KIND_OF_STRUCT = {
     "ddif_randn_t": "DDIF_OP_RANDN", "ddif_axpby_clip_t": "DDIF_OP_AXPBY_CLIP", "ddif_dpm_single_t": "DDIF_OP_DPM_SINGLE",
     "ddif_loss_t": "DDIF_OP_LOSS", "ddif_dpm_err_t": "DDIF_OP_DPM_ERR", "ddif_attn_block_t": "DDIF_OP_ATTN_BLOCK", "ddif_multi_tensor_t": "DDIF_OP_MULTI_TENSOR", "ddif_axpby_t": "DDIF_OP_AXPBY", "ddif_metrics_t": "DDIF_OP_METRICS", "ddif_tile_t": "DDIF_OP_TILE",
     "ddif_wavelet_cond_t": "DDIF_OP_WAVELET_COND", "ddif_wgrad_t": "DDIF_OP_WGRAD", "ddif_colsum_t": "DDIF_OP_COLSUM",
+    "ddif_fwm_front_t": "DDIF_OP_FWM_FRONT",
 }
 
 _lib = None

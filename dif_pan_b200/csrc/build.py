@@ -6,7 +6,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["gemm_tc.cu", "conv3x3_halo.cu", "elementwise.cu", "sampler.cu", "prep_post.cu", "attn_block.cu", "attn_tc.cu", "backward.cu", "capi.cu"]
+SOURCES = ["gemm_tc.cu", "conv3x3_halo.cu", "elementwise.cu", "sampler.cu", "prep_post.cu", "attn_block.cu", "attn_tc.cu", "backward.cu", "fwm_front.cu", "capi.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "libddif_b200.so")
 
 

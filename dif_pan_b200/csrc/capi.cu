@@ -48,6 +48,7 @@ union OpParams {
   ddif_wavelet_cond_t wavelet_cond;
   ddif_wgrad_t wgrad;
   ddif_colsum_t colsum;
+  ddif_fwm_front_t fwm_front;
 };
 
 static size_t params_size(int kind) {
@@ -57,6 +58,7 @@ static size_t params_size(int kind) {
     case DDIF_OP_TIME_EMBED: return sizeof(ddif_time_embed_t);
     case DDIF_OP_GN_APPLY: return sizeof(ddif_gn_apply_t);
     case DDIF_OP_SOFTMAX_H: return sizeof(ddif_softmax_h_t);
+    case DDIF_OP_FWM_FRONT: return sizeof(ddif_fwm_front_t);
     case DDIF_OP_ATTN: return sizeof(ddif_attn_t);
     case DDIF_OP_UPSAMPLE2X: return sizeof(ddif_upsample2x_t);
     case DDIF_OP_CONV_DIRECT: return sizeof(ddif_conv_direct_t);
@@ -102,6 +104,7 @@ static int dispatch(const Op& op, cudaStream_t s) {
     case DDIF_OP_TIME_EMBED: return launch_time_embed(op.p.time_embed, s);
     case DDIF_OP_GN_APPLY: return launch_gn_apply(op.p.gn_apply, s);
     case DDIF_OP_SOFTMAX_H: return launch_softmax_h(op.p.softmax_h, s);
+    case DDIF_OP_FWM_FRONT: return launch_fwm_front(op.p.fwm_front, s);
     case DDIF_OP_ATTN: return launch_attn(op.p.attn, s);
     case DDIF_OP_UPSAMPLE2X: return launch_upsample2x(op.p.upsample2x, s);
     case DDIF_OP_CONV_DIRECT: return launch_conv_direct(op.p.conv_direct, s);

@@ -54,6 +54,7 @@ int launch_dpm_single(const ddif_dpm_single_t& p, cudaStream_t s);
 int launch_loss(const ddif_loss_t& p, cudaStream_t s);
 int launch_dpm_err(const ddif_dpm_err_t& p, cudaStream_t s);
 int launch_attn_block(const ddif_attn_block_t& p, cudaStream_t s);
+int launch_fwm_front(const ddif_fwm_front_t& p, cudaStream_t s);  // fwm_front.cu
 bool attn_tc_applicable(const ddif_attn_t& p);            // attn_tc.cu: head_dim 16, ntok % 128 == 0
 int launch_attn_tc(const ddif_attn_t& p, cudaStream_t s);
 int launch_multi_tensor(const ddif_multi_tensor_t& p, cudaStream_t s);

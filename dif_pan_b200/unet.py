@@ -359,10 +359,10 @@ class Schedule:
     """Builds the cond-cache plan and the per-step forward plan of a UNetSR3 for a fixed (B, H, W)."""
 
     def __init__(self, net: UNetSR3, addr: Dict[str, int], B: int, H: int, W: int, io: Dict[str, int], *, use_qconv: bool = True,
-                 use_dwq: bool = True, use_attn_block: bool = True, use_cs_gemm: bool = True):
+                 use_dwq: bool = True, use_attn_block: bool = True, use_cs_gemm: bool = True, use_fwm_front: bool = True):
         """addr: packed-weight name -> device address; io: x, sc, t, out, cond addresses (fixed buffers).
-        use_qconv / use_dwq / use_attn_block / use_cs_gemm: A/B switches for tools/ (composed q conv, in-kernel depthwise q path, fused attention
-        block, softmax-over-H fused into the attn_out GEMM); the product always builds the schedule with all of them on."""
+        use_qconv / use_dwq / use_attn_block / use_cs_gemm / use_fwm_front: A/B switches for tools/ (composed q conv, in-kernel depthwise q path, fused
+        attention block, softmax-over-H fused into the attn_out GEMM, fused FWM front at 8x8); the product always builds the schedule with all of them on."""
         if H % 8 or W % 8 or min(H, W) < 8 * 2 ** (self._levels(net) - 1):
             raise ValueError(f"UNetSR3 needs H, W multiples of 8 and >= {8 * 2 ** (self._levels(net) - 1)}, got {H}x{W}")
         self.net, self.addr, self.B, self.H, self.W, self.io = net, addr, B, H, W, io
@@ -379,6 +379,7 @@ class Schedule:
         self.film_offsets = None
         self.first_body_op = 0
         self.use_qconv, self.use_dwq, self.use_attn_block, self.use_cs_gemm = use_qconv, use_dwq, use_attn_block, use_cs_gemm
+        self.use_fwm_front = use_fwm_front
 
     @staticmethod
     def _levels(net) -> int:
@@ -653,6 +654,16 @@ class Schedule:
                            h=x.H, w=x.W, c=dim, scale=1.0, in_ld=dim + o)
                     self._gemm(pb, q + ".attn_out", [qs], [("cache", self.weff[p])], o, y, taps=[1], bias=A[q + ".attn.b"], per_sample=(1,),
                                w_s=[B], w_k=[self.weff_k[p]], residual=qr, residual_off=dim, ref_flops=2.0 * B * x.H * x.W * o * dim)
+            elif (self.use_fwm_front and not qconv and has_res and (x.H, x.W) == (8, 8) and dim in (192, 256) and o == 128
+                  and x.stats is not None and skip.stats is not None):
+                # the whole front (prenorm_x, DW3x3, q 1x1, softmax over H, attn_out with the per-sample W_eff, attn_res, bias) in ONE launch, one
+                # CTA per sample (csrc/fwm_front.cu) instead of gn_apply+dw / 1x1 GEMM / softmax_h / two-segment 1x1 GEMM
+                y = self._act(pb, q + ".y", B, x.H, x.W, o)
+                pb.add("ddif_fwm_front_t", label=q + ".front", flops=2.0 * B * 64 * dim * (9 + dim + 2 * o), traffic=B * 64 * (dim + o) * 2,
+                       ref_flops=2.0 * B * 64 * dim * (9 + dim + 2 * o), x=x.buf, skip=skip.buf, c1=x.C, c2=skip.C, stats1=x.stats,
+                       stats2=skip.stats, gamma=A[q + ".gamma"], beta=A[q + ".beta"], eps=1e-5, dw_w=A[q + ".q0"], w1=A[q + ".q1.w"], w1_ld=dim,
+                       b1=A[q + ".q1.b"], weff=("cache", self.weff[p]), weff_ld=self.weff_k[p], weff_rows=_ceil(o, 16),
+                       wres=A[q + ".attn_res.w"], wres_ld=dim, bias=A[q + ".attn.b"], out=y.buf, out_ld=o, batch=B, h=x.H, w=x.W, o=o)
             else:
                 qt = self._act(pb, q + ".q", B, x.H, x.W, dim)
                 if qconv:

@@ -63,6 +63,7 @@ enum ddif_op_kind {
   DDIF_OP_WGRAD = 32,        /* convolution weight gradient: dW[tap][o][i] += sum_p dY[p][o] X[p + tap][i]  (autograd of F.conv2d in p_losses().backward(),
                                 diffusion_ddpm_pan.py:692-766, diffusion_engine.py:233) */
   DDIF_OP_COLSUM = 33,       /* per-channel sum of a gradient tensor over all pixels (bias gradient) or per sample (FiLM gradient, sr3_dwt.py:241-258) */
+  DDIF_OP_FWM_FRONT = 34,    /* FWM front at 8 x 8 in one kernel: prenorm_x + DW3x3 + q 1x1 + softmax over H + attn_out (W_eff) + attn_res + bias   sr3_dwt.py:507-573 */
   DDIF_OP_DPM_ERR = 29,      /* adaptive DPM-Solver error estimate per sample                      dpm_solver.py:1003-1006 */
   DDIF_OP_WAVELET_COND = 28  /* raw lms, pan -> cond in one pass: Haar DWT, /division, channel order, bilinear up, concat
                                 dataset/pan_dataset.py:73-142, dataset/hisr.py:48-59, diffusion_engine.py:221-228 */
@@ -139,6 +140,18 @@ typedef struct {
   const void* x; const double* stats_in; const float* gamma; const float* beta; const void* wqkv; const void* wout; const float* bout;
   void* out; double* stats_out; int64_t batch, ntok, c, heads; double scale, eps;
 } ddif_attn_block_t;
+/* Fused front of FastAttnCondInjection for 8 x 8 images (csrc/fwm_front.cu; one CTA per sample): x [B, 8, 8, c1] and skip [B, 8, 8, c2] bf16 NHWC
+ * (their channel concatenation is the block input, c1 + c2 = dim in {192, 256}), stats1 / stats2 = their per-sample (sum, sumsq) in fp64, gamma / beta
+ * [dim] of prenorm_x; dw_w [9][dim] fp32 (q.0, tap = ky*3+kx); w1 [dim][w1_ld] bf16 + b1 [dim] (q.1); weff [B][weff_rows][weff_ld] bf16 = the
+ * per-sample W_eff of the cond cache (DDIF_OP_FWM_WEFF); wres [o][wres_ld] bf16 (attn_res); bias [o] = attn_out.bias + attn_res.bias;
+ * out [B, 8, 8, out_ld] bf16 (first o = 128 channels):  out = W_eff[b] . softmax_H(w1 . dw3x3(x_hat) + b1) + wres . x_hat + bias. */
+typedef struct {
+  const void* x; const void* skip; int64_t c1, c2;
+  const double* stats1; const double* stats2; const float* gamma; const float* beta; double eps;
+  const float* dw_w; const void* w1; int64_t w1_ld; const float* b1;
+  const void* weff; int64_t weff_ld, weff_rows; const void* wres; int64_t wres_ld; const float* bias;
+  void* out; int64_t out_ld, batch, h, w, o;
+} ddif_fwm_front_t;
 typedef struct { const void* in; void* out; int64_t batch, h, w, c; } ddif_upsample2x_t;
 typedef struct {
   const void* in; int64_t in_ld, cin, in_h, in_w; const void* w; int64_t w_k, taps, stride;

@@ -405,3 +405,38 @@ def test_fused_attention_block_matches_torch():
         _lib.launch("ddif_attn_block_t", stream(), x=xa.data_ptr(), stats_in=stats_in.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
                     wqkv=wq_p.data_ptr(), wout=wo_p.data_ptr(), bout=bout.data_ptr(), out=out.data_ptr(), stats_out=None, batch=B, ntok=128,
                     c=C, heads=heads, scale=1.0, eps=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c1,c2,B", [(128, 128, 5), (128, 64, 3)])
+def test_fused_fwm_front_matches_torch(c1, c2, B):
+    """DDIF_OP_FWM_FRONT (csrc/fwm_front.cu): prenorm_x + DW3x3 + q 1x1 + softmax over H + W_eff[b] . qs + attn_res + bias at 8 x 8 in one launch,
+    against the fp32 torch expression of FastAttnCondInjection's front (sr3_dwt.py:507-573) on the same bf16 inputs."""
+    torch.manual_seed(c1 + c2 + B)
+    dim, o, H = c1 + c2, 128, 8
+    x = (torch.randn(B, H, H, c1) * 1.5 + 0.3).to(torch.bfloat16).to(DEV)
+    sk = (torch.randn(B, H, H, c2) * 0.7 - 0.2).to(torch.bfloat16).to(DEV)
+    st = lambda v: torch.stack([v.double().sum(dim=(1, 2, 3)), (v.double() ** 2).sum(dim=(1, 2, 3))], dim=1).contiguous()
+    s1, s2 = st(x), st(sk)
+    gamma, beta = (torch.rand(dim) + 0.5).to(DEV), (torch.randn(dim) * 0.1).to(DEV)
+    dw = (torch.randn(dim, 1, 3, 3) * 0.3).to(DEV)
+    w1 = (torch.randn(dim, dim) / dim ** 0.5).to(torch.bfloat16).to(DEV)
+    b1 = (torch.randn(dim) * 0.1).to(DEV)
+    weff = (torch.randn(B, o, dim) * 0.2).to(torch.bfloat16).to(DEV)
+    wres = (torch.randn(o, dim) / dim ** 0.5).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(o).to(DEV)
+    out = torch.zeros(B, H, H, o, dtype=torch.bfloat16, device=DEV)
+    dw9 = dw.reshape(dim, 9).t().contiguous()
+    _lib.launch("ddif_fwm_front_t", stream(), x=x.data_ptr(), skip=sk.data_ptr(), c1=c1, c2=c2, stats1=s1.data_ptr(), stats2=s2.data_ptr(),
+                gamma=gamma.data_ptr(), beta=beta.data_ptr(), eps=1e-5, dw_w=dw9.data_ptr(), w1=w1.data_ptr(), w1_ld=dim, b1=b1.data_ptr(),
+                weff=weff.data_ptr(), weff_ld=dim, weff_rows=o, wres=wres.data_ptr(), wres_ld=dim, bias=bias.data_ptr(), out=out.data_ptr(),
+                out_ld=o, batch=B, h=H, w=H, o=o)
+    torch.cuda.synchronize()
+    xc = torch.cat([x, sk], dim=3).float().permute(0, 3, 1, 2)                       # NCHW
+    xh = F.group_norm(xc, 1, gamma, beta, 1e-5)
+    q = F.conv2d(F.conv2d(xh, dw, padding=1, groups=dim), w1.float()[:, :, None, None], b1)
+    qs = torch.softmax(q, dim=-2)
+    ref = torch.einsum("boc,bchw->bohw", weff.float(), qs) + F.conv2d(xh, wres.float()[:, :, None, None]) + bias[None, :, None, None]
+    err = rel_err(out.float().permute(0, 3, 1, 2), ref)
+    print(f"[fwm front] dim {dim}: rel err {err:.3e}")
+    assert err < 1e-2, err

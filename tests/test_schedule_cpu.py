@@ -71,14 +71,17 @@ def test_schedule_structure(dataset, B, H, W):
     # 12 enc x (x_conv, 2 conv) + 16 dec x (q1 | qconv, attn, ffn0, ffn23, 2 conv) + mid 2x2 + 8 attn x 2 + conv0 + 3 down + 3 up + final
     # at 64 tokens (64x64 inputs) each SelfAttention block (norm, qkv, core, out) is ONE fused launch (csrc/attn_block.cu)
     fused_attn = (H // 8) * (W // 8) == 64
-    assert kinds.count("ddif_gemm_t") == 12 * 3 + 16 * 6 + 4 + (0 if fused_attn else 8 * 2) + 1 + 3 + 3 + 1
+    # at an 8x8 lowest level the front of the four FWM blocks there (prenorm+dw, q 1x1, softmax_h, attn_out+res) is ONE launch (csrc/fwm_front.cu)
+    front = kinds.count("ddif_fwm_front_t")
+    assert front == (4 if (H // 8, W // 8) == (8, 8) else 0)
+    assert kinds.count("ddif_gemm_t") == 12 * 3 + 16 * 6 + 4 + (0 if fused_attn else 8 * 2) + 1 + 3 + 3 + 1 - 2 * front
     assert kinds.count("ddif_attn_t") == (0 if fused_attn else 8)
     assert kinds.count("ddif_attn_block_t") == (8 if fused_attn else 0)
     # FWM softmax over H is fused into the attn_out GEMM's loader (cs_gemm_tc_kernel) for the merged-q decoder blocks whose level has 16, 32 or
     # 64 lines and a width that is a multiple of 128 / lines; the others keep the stand-alone softmax kernel (8x8 level, 128-line level, dim + o > 192)
     cs = [op for op in s.fwd.ops if op.struct == "ddif_gemm_t" and op.fields.get("a_softmax_h")]
     assert len(cs) == (7 if (H, W) == (128, 64) else 11)
-    assert kinds.count("ddif_softmax_h_t") == 16 - len(cs)
+    assert kinds.count("ddif_softmax_h_t") == 16 - len(cs) - front
     for op in cs:
         f = op.fields
         assert f["out_h"] in (16, 32, 64) and f["out_w"] % (128 // f["out_h"]) == 0 and f["taps"][0] == 1 and f["w_per_sample"][0] == 1
@@ -86,7 +89,7 @@ def test_schedule_structure(dataset, B, H, W):
     # GroupNorm+Swish of every 3x3 conv is fused into the conv's loader (all 30 resblocks x 2 + final conv);
     # stand-alone normalisation launches left: 8 attention norms + 5 FWM prenorm(+dw) -- the other 11 decoder blocks get
     # r = attn_res(x_hat) as extra output channels of the q conv (dim + o <= 192), so x_hat is never materialised
-    assert kinds.count("ddif_gn_apply_t") == (0 if fused_attn else 8) + 5
+    assert kinds.count("ddif_gn_apply_t") == (0 if fused_attn else 8) + 5 - front
     merged = [op for op in s.fwd.ops if op.label.endswith(".qconv") and op.fields["n_valid"] > op.fields["w_k"][0]]
     assert len(merged) == 11
     assert kinds.count("ddif_upsample2x_t") == 3  # nearest x2 as its own kernel + halo conv (faster than the fused LDG loader)
@@ -211,4 +214,4 @@ def test_every_op_kind_has_a_struct_and_named_wrappers_exist():
     lib = _lib.load()
     for name in _lib.EXPORTS:
         assert getattr(lib, name) is not None
-    assert len(_lib.EXPORTS) >= 31 and len(kinds) == 33   # round 2 added DDIF_OP_WGRAD, DDIF_OP_COLSUM
+    assert len(_lib.EXPORTS) >= 32 and len(kinds) == 34   # round 2 added DDIF_OP_WGRAD, DDIF_OP_COLSUM, DDIF_OP_FWM_FRONT

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--top", type=int, default=12)
     ap.add_argument("--out", default="gpurun_out")
     ap.add_argument("--no-cs-gemm", action="store_true", help="A/B: stand-alone softmax_h kernel + plain attn_out GEMM instead of the fused cs_gemm_tc_kernel")
+    ap.add_argument("--no-fwm-front", action="store_true", help="A/B: four launches for the FWM front at 8x8 instead of the fused fwm_front64_kernel")
     ap.add_argument("--no-side-branch", action="store_true", help="A/B: time embedding in line instead of as a side branch of the step graph")
     ap.add_argument("--ncu", action="store_true", help="run cond build + ONE eager step between cudaProfilerStart/Stop and exit")
     a = ap.parse_args()
@@ -43,10 +44,11 @@ def main():
     net.load_state_dict(synth.make_state_dict(0, **kw))
     net = net.to(dev).eval()
     B = a.batch
-    if a.no_cs_gemm or a.no_side_branch:
+    if a.no_cs_gemm or a.no_side_branch or a.no_fwm_front:
         from dif_pan_b200.unet import _Runtime
         net.pack_weights()
-        net._rt = _Runtime(net, B, a.size, a.size, use_cs_gemm=not a.no_cs_gemm, use_side_branch=not a.no_side_branch)
+        net._rt = _Runtime(net, B, a.size, a.size, use_cs_gemm=not a.no_cs_gemm, use_side_branch=not a.no_side_branch,
+                           use_fwm_front=not a.no_fwm_front)
     rt = net.runtime(B, a.size, a.size)
     cond = synth.make_batch(a.dataset, min(B, 16), size=a.size, seed=1)["cond"]
     cond = cond.repeat((B + cond.shape[0] - 1) // cond.shape[0], 1, 1, 1)[:B].contiguous().to(dev)

@@ -9,11 +9,13 @@
 //
 // Like the 64-token attention block (attn_block.cu) this uses warp-level mma.sync.m16n8k16 (bf16 -> fp32): a sample is 64 x 256, every GEMM has
 // M = 64 and the chain needs two block-wide exchanges (depthwise neighbours, softmax over the lines) that tcgen05 would pay with
-// TMEM -> register -> shared-memory -> descriptor round trips.  Warp w owns the token rows 16 w .. 16 w + 15 (image lines 2 w, 2 w + 1).
+// TMEM -> register -> shared-memory -> descriptor round trips.  Eight warps: warp w owns the token rows 16 (w & 3) .. + 15 (image lines 2 (w & 3),
+// + 1) and half w >> 2 of the 32 output channels of every weight slice (four warps with all 32: 42 instead of 39 us per launch).  Measured and
+// rejected: a ring of four 16-row slices with three in flight and ldmatrix A loads (47 us: twice the barriers, one HMMA chain per warp).
 //   P0  x, skip -> GroupNorm affine -> bufA (bf16, x_hat)                      one 16-byte chunk per thread and step
 //   P1  depthwise 3x3 of x_hat -> bufB                                         thread = one bf16x2 channel pair for all 64 pixels, weights in
 //                                                                              registers, a sliding 3 x 3 window along x (3 new LDS per pixel)
-//   P2  q = dw . W1^T + b1 -> bufB (in place: a warp holds its A fragments in registers before it overwrites its own rows)
+//   P2  q = dw . W1^T + b1 -> bufB (in place: the warps hold their A fragments in registers before they overwrite their own rows)
 //   P3  softmax over the 8 lines of every (column, channel pair) of bufB
 //   P4  y = qs . W_eff[b]^T + x_hat . W_res^T + bias -> global
 // The weights (W1 128 KB, W_eff[b] and W_res 64 KB each at dim 256) stream through a double-buffered 32-row slice in shared memory with cp.async
@@ -23,7 +25,7 @@
 
 namespace ddif {
 
-static constexpr int kFfTok = 64, kFfO = 128, kFfSlice = 32, kFfThreads = 128;
+static constexpr int kFfTok = 64, kFfO = 128, kFfSlice = 32, kFfThreads = 256;
 
 template <int DIM>
 struct FfCfg {
@@ -66,7 +68,8 @@ __global__ void __launch_bounds__(kFfThreads, 2) fwm_front64_kernel(ddif_fwm_fro
   float* s_d = s_a + DIM;
   const int b = blockIdx.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  const int nh = warp >> 2;                        // which 16 of the 32 output channels of a weight slice
+  const int r0 = (warp & 3) * 16 + g, r1 = r0 + 8;
   const bf16* w1 = reinterpret_cast<const bf16*>(p.w1);
   const bf16* weff = reinterpret_cast<const bf16*>(p.weff) + (size_t)b * p.weff_rows * p.weff_ld;
   const bf16* wres = reinterpret_cast<const bf16*>(p.wres);
@@ -128,13 +131,13 @@ __global__ void __launch_bounds__(kFfThreads, 2) fwm_front64_kernel(ddif_fwm_fro
   }
   __syncthreads();
   // ---- P1: depthwise 3x3 (zero padding of x_hat) -> bufB; thread = channel pair wc, all 64 pixels ----
-  if (tid < DIM / 2) {
-    const int wc = tid;
+  if (tid < DIM) {
+    const int wc = tid % (DIM / 2), yh = tid / (DIM / 2);  // channel pair, upper / lower four lines
     float2 w[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) w[k] = make_float2(__ldg(p.dw_w + (size_t)k * DIM + 2 * wc), __ldg(p.dw_w + (size_t)k * DIM + 2 * wc + 1));
     const uint32_t colA = sA + (uint32_t)(wc * 4), colB = sB + (uint32_t)(wc * 4);
-    for (int y = 0; y < 8; ++y) {
+    for (int y = 4 * yh; y < 4 * yh + 4; ++y) {
       const bool up = y > 0, dn = y < 7;
       // column triple (rows y-1, y, y+1) of image column xx; zero outside the image
       auto col = [&](int xx, float2 (&c)[3]) {
@@ -175,15 +178,15 @@ __global__ void __launch_bounds__(kFfThreads, 2) fwm_front64_kernel(ddif_fwm_fro
       af[ks][3] = ff_lds32(a1 + 16);
     }
   };
-  float acc[4][4];
+  float acc[2][4];
   bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)b * kFfTok * p.out_ld;
   for (int i = 0; i < C::nSlices; ++i) {
     ff_wait_all();
     __syncthreads();  // slice i has landed for everybody; everybody is done with the buffer slice i + 1 goes to (and, at i = 0, with P1)
     if (i + 1 < C::nSlices) issue(i + 1);
     if (i == 0) {
-      load_a(sB);      // A = depthwise output, rows of this warp
-      __syncwarp();    // every lane holds its fragments before any lane overwrites these rows with q
+      load_a(sB);       // A = depthwise output, rows of this warp
+      __syncthreads();  // both warps of a row block hold their fragments before either overwrites those rows with q
     }
     if (i == C::nP2) {
       // ---- P3: softmax over the 8 lines for every (image column, channel pair) of q (all warps passed the barrier above: q is complete) ----
@@ -218,22 +221,22 @@ __global__ void __launch_bounds__(kFfThreads, 2) fwm_front64_kernel(ddif_fwm_fro
     if (!p2) load_a((j & 1) ? sA : sB);
     if (p2 || (j & 1) == 0) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[u][e] = 0.f;
     }
 #pragma unroll
     for (int ks = 0; ks < C::KS; ++ks) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t ba = wb + (uint32_t)((8 * u + g) * C::LD * 2 + (16 * ks + 2 * t) * 2);
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t ba = wb + (uint32_t)((16 * nh + 8 * u + g) * C::LD * 2 + (16 * ks + 2 * t) * 2);
         ff_mma(acc[u], af[ks], ff_lds32(ba), ff_lds32(ba + 16));
       }
     }
     if (p2) {  // q = acc + b1 -> bufB (bf16, like the q tensor of the unfused path), channels 32 i + 8 u + 2 t
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = kFfSlice * i + 8 * u + 2 * t;
+      for (int u = 0; u < 2; ++u) {
+        const int c = kFfSlice * i + 16 * nh + 8 * u + 2 * t;
         const float b0 = p.b1 ? __ldg(p.b1 + c) : 0.f, b1v = p.b1 ? __ldg(p.b1 + c + 1) : 0.f;
         ff_sts32(sB + (uint32_t)(r0 * C::LD * 2 + c * 2), ff_pack(acc[u][0] + b0, acc[u][1] + b1v));
         ff_sts32(sB + (uint32_t)(r1 * C::LD * 2 + c * 2), ff_pack(acc[u][2] + b0, acc[u][3] + b1v));
@@ -241,8 +244,8 @@ __global__ void __launch_bounds__(kFfThreads, 2) fwm_front64_kernel(ddif_fwm_fro
     } else if (j & 1) {  // y = acc + bias -> global
       const int ns = j >> 1;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = kFfSlice * ns + 8 * u + 2 * t;
+      for (int u = 0; u < 2; ++u) {
+        const int c = kFfSlice * ns + 16 * nh + 8 * u + 2 * t;
         if (c < (int)p.o) {
           const float b0 = p.bias ? __ldg(p.bias + c) : 0.f, b1v = p.bias ? __ldg(p.bias + c + 1) : 0.f;
           *reinterpret_cast<uint32_t*>(out + (size_t)r0 * p.out_ld + c) = ff_pack(acc[u][0] + b0, acc[u][1] + b1v);

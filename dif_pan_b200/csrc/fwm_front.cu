@@ -92,10 +92,33 @@ __global__ void __launch_bounds__(kFfThreads, 2) fwm_front64_kernel(ddif_fwm_fro
     ff_commit();
   };
   issue(0);     // static weights: requested before the dependency wait (they overlap the previous kernel's tail)
+  // ... as are the GroupNorm scale / shift vectors and this thread's depthwise weights (one CTA wave covers the whole batch, so the kernel's
+  // duration IS one CTA's chain of dependent global round trips: everything static is fetched here, everything else in batches)
+  const int c1 = (int)p.c1;
+  float gam = 0.f, bet = 0.f;
+  if (tid < DIM) { gam = __ldg(p.gamma + tid); bet = __ldg(p.beta + tid); }
+  const int wc = tid % (DIM / 2), yh = tid / (DIM / 2);  // P1: channel pair, upper / lower four lines
+  float2 w[9];
+  if (tid < DIM) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = make_float2(__ldg(p.dw_w + (size_t)k * DIM + 2 * wc), __ldg(p.dw_w + (size_t)k * DIM + 2 * wc + 1));
+  }
   pdl_wait();
 
-  // ---- GroupNorm(1 group) over the concatenated sample: per-channel affine table ----
-  const int c1 = (int)p.c1;
+  // ---- P0: x, skip rows of this sample (all loads in flight at once), GroupNorm(1 group) affine -> bufA (x_hat, bf16) ----
+  constexpr int kChunks = kFfTok * C::NCH / kFfThreads;  // 16-byte chunks per thread: 8 (dim 256) or 6 (dim 192)
+  static_assert(kFfTok * C::NCH % kFfThreads == 0, "chunks per thread");
+  uint4 xin[kChunks];
+  {
+    const bf16* x = reinterpret_cast<const bf16*>(p.x) + (size_t)b * kFfTok * c1;
+    const bf16* sk = reinterpret_cast<const bf16*>(p.skip) + (size_t)b * kFfTok * (DIM - c1);
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+      const int idx = tid + k * kFfThreads, px = idx / C::NCH, ch = (idx - px * C::NCH) * 8;
+      xin[k] = ch < c1 ? *reinterpret_cast<const uint4*>(x + (size_t)px * c1 + ch)
+                       : *reinterpret_cast<const uint4*>(sk + (size_t)px * (DIM - c1) + (ch - c1));
+    }
+  }
   {
     double s = p.stats1[2 * b], ss = p.stats1[2 * b + 1];
     if (p.stats2) { s += p.stats2[2 * b]; ss += p.stats2[2 * b + 1]; }
@@ -104,38 +127,28 @@ __global__ void __launch_bounds__(kFfThreads, 2) fwm_front64_kernel(ddif_fwm_fro
     double var_d = ss / cnt - mean_d * mean_d;
     if (var_d < 0) var_d = 0;
     const float mean = (float)mean_d, rstd = rsqrtf((float)var_d + (float)p.eps);
-    for (int ch = tid; ch < DIM; ch += kFfThreads) {
-      const float a = rstd * __ldg(p.gamma + ch);
-      s_a[ch] = a;
-      s_d[ch] = __ldg(p.beta + ch) - mean * a;
+    if (tid < DIM) {
+      const float a = rstd * gam;
+      s_a[tid] = a;
+      s_d[tid] = bet - mean * a;
     }
   }
   __syncthreads();
-  // ---- P0: x_hat -> bufA ----
-  {
-    const bf16* x = reinterpret_cast<const bf16*>(p.x) + (size_t)b * kFfTok * c1;
-    const bf16* sk = reinterpret_cast<const bf16*>(p.skip) + (size_t)b * kFfTok * (DIM - c1);
-    for (int idx = tid; idx < kFfTok * C::NCH; idx += kFfThreads) {
-      const int px = idx / C::NCH, ch = (idx - px * C::NCH) * 8;
-      const uint4 v = ch < c1 ? *reinterpret_cast<const uint4*>(x + (size_t)px * c1 + ch)
-                              : *reinterpret_cast<const uint4*>(sk + (size_t)px * (DIM - c1) + (ch - c1));
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      uint32_t o[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 u = ff_unpack(w[j]);
-        o[j] = ff_pack(fmaf(u.x, s_a[ch + 2 * j], s_d[ch + 2 * j]), fmaf(u.y, s_a[ch + 2 * j + 1], s_d[ch + 2 * j + 1]));
-      }
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + (uint32_t)(px * C::LD * 2 + ch * 2)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+  for (int k = 0; k < kChunks; ++k) {
+    const int idx = tid + k * kFfThreads, px = idx / C::NCH, ch = (idx - px * C::NCH) * 8;
+    const uint32_t wv[4] = {xin[k].x, xin[k].y, xin[k].z, xin[k].w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 u = ff_unpack(wv[j]);
+      o[j] = ff_pack(fmaf(u.x, s_a[ch + 2 * j], s_d[ch + 2 * j]), fmaf(u.y, s_a[ch + 2 * j + 1], s_d[ch + 2 * j + 1]));
     }
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sA + (uint32_t)(px * C::LD * 2 + ch * 2)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
   }
   __syncthreads();
   // ---- P1: depthwise 3x3 (zero padding of x_hat) -> bufB; thread = channel pair wc, all 64 pixels ----
   if (tid < DIM) {
-    const int wc = tid % (DIM / 2), yh = tid / (DIM / 2);  // channel pair, upper / lower four lines
-    float2 w[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) w[k] = make_float2(__ldg(p.dw_w + (size_t)k * DIM + 2 * wc), __ldg(p.dw_w + (size_t)k * DIM + 2 * wc + 1));
     const uint32_t colA = sA + (uint32_t)(wc * 4), colB = sB + (uint32_t)(wc * 4);
     for (int y = 4 * yh; y < 4 * yh + 4; ++y) {
       const bool up = y > 0, dn = y < 7;

@@ -72,9 +72,10 @@ enum ddif_op_kind {
 /* ---- DDIF_OP_GEMM ------------------------------------------------------------------------------------------
  * out[b,y,x,n] = epilogue( sum_seg sum_tap sum_c  a_seg[b, y*stride+dy-pad, x*stride+dx-pad, c] * w_seg[z, n, c] )
  * z = tap (shared weights) or b (per-sample weights, 1x1 only).  Zero padding comes from TMA out-of-bounds fill.
- * Two kernels implement it: conv3x3_halo_tc_kernel (3x3, stride 1: ONE TMA halo tile feeds all nine taps, optional
- * fused GroupNorm(+Swish) prologue, 1-2 concatenated sources, N split over CTAs) and conv_igemm_tc_kernel (everything
- * else: 1x1, stride 2, per-sample weights).
+ * Three kernels implement it: conv3x3_halo_tc_kernel (3x3, stride 1: ONE TMA halo tile feeds all nine taps, optional
+ * fused GroupNorm(+Swish) prologue, 1-2 concatenated sources, N split over CTAs), cs_gemm_tc_kernel (1x1 with a_softmax_h: the
+ * softmax over the image height is computed on the loaded tile) and conv_igemm_tc_kernel (everything else: 1x1, stride 2,
+ * per-sample weights).
  * epilogue: v = acc + bias[n] + film[b*film_ld + n];  v = v*(1+mod[..,n]) + mod[..,n_valid+n];  v += residual;
  *           v = silu(v) if act;  stats[b] += (sum v, sum v^2);  store bf16 NHWC and/or fp32 NCHW.              */
 typedef struct {

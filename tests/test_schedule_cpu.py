@@ -215,3 +215,21 @@ def test_every_op_kind_has_a_struct_and_named_wrappers_exist():
     for name in _lib.EXPORTS:
         assert getattr(lib, name) is not None
     assert len(_lib.EXPORTS) >= 32 and len(kinds) == 34   # round 2 added DDIF_OP_WGRAD, DDIF_OP_COLSUM, DDIF_OP_FWM_FRONT
+
+
+def test_plan_side_branch_argument_checks():
+    """ddif_plan_set_side_branch (include/ddif_b200.h) validates its op ranges on the host: no CUDA call is made until the graph is built."""
+    import ctypes
+    lib = _lib.load()
+    plan = ctypes.c_void_p(lib.ddif_plan_create())
+    try:
+        ms = _lib.make("ddif_memset_t", ptr=None, bytes=0)
+        for _ in range(5):
+            assert lib.ddif_plan_add(plan, _lib.KINDS["DDIF_OP_MEMSET"], ctypes.byref(ms)) >= 0
+        assert lib.ddif_plan_set_side_branch(plan, 1, 2, 4) == 0          # ops [1, 2) beside ops 2, 3; joined before op 4
+        assert lib.ddif_plan_set_side_branch(plan, -1, 0, 0) == 0         # clear
+        for bad in ((2, 2, 4), (1, 3, 2), (1, 2, 5), (3, 2, 4)):         # empty range, join inside the branch, join past the end, reversed
+            assert lib.ddif_plan_set_side_branch(plan, *bad) < 0, bad
+        assert lib.ddif_plan_set_side_branch(None, 1, 2, 4) < 0
+    finally:
+        lib.ddif_plan_destroy(plan)

@@ -57,6 +57,9 @@ __device__ __forceinline__ void ff_cp16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void ff_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ff_ldsm4(uint32_t a, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a) : "memory");
+}
 __device__ __forceinline__ void ff_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int DIM>
@@ -181,15 +184,15 @@ __global__ void __launch_bounds__(kFfThreads, 2) fwm_front64_kernel(ddif_fwm_fro
 
   // ---- P2 / P4: two GEMM passes over a stream of 32-row weight slices ----
   uint32_t af[C::KS][4];
+  // Fragments come from shared memory with ldmatrix.x4 (ncu of the LDS.32 version: 44 % issue utilisation, mio_throttle the first stall reason --
+  // 3 100 of a warp's 8 600 instructions were 4-byte fragment loads).  A: one instruction per k-step (matrices rows 0-7 / 8-15 x k 0-7, rows 0-7 /
+  // 8-15 x k 8-15 = a0..a3 of mma.m16n8k16); B: one per k-step for both n-tiles of the warp (n-tile 0 x k lo / hi = b0, b1; n-tile 1 x k lo / hi).
+  // Lane l addresses row (l & 7) of matrix l >> 3.
+  const uint32_t a_lane = (uint32_t)((((warp & 3) * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * C::LD + (lane >> 4) * 8) * 2);
+  const uint32_t b_lane = (uint32_t)(((16 * nh + (lane >> 4) * 8 + (lane & 7)) * C::LD + ((lane >> 3) & 1) * 8) * 2);
   auto load_a = [&](uint32_t base) {
 #pragma unroll
-    for (int ks = 0; ks < C::KS; ++ks) {
-      const uint32_t a0 = base + (uint32_t)(r0 * C::LD * 2 + (16 * ks + 2 * t) * 2), a1 = base + (uint32_t)(r1 * C::LD * 2 + (16 * ks + 2 * t) * 2);
-      af[ks][0] = ff_lds32(a0);
-      af[ks][1] = ff_lds32(a1);
-      af[ks][2] = ff_lds32(a0 + 16);
-      af[ks][3] = ff_lds32(a1 + 16);
-    }
+    for (int ks = 0; ks < C::KS; ++ks) ff_ldsm4(base + a_lane + (uint32_t)(32 * ks), af[ks]);
   };
   float acc[2][4];
   bf16* out = reinterpret_cast<bf16*>(p.out) + (size_t)b * kFfTok * p.out_ld;
@@ -240,11 +243,10 @@ __global__ void __launch_bounds__(kFfThreads, 2) fwm_front64_kernel(ddif_fwm_fro
     }
 #pragma unroll
     for (int ks = 0; ks < C::KS; ++ks) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const uint32_t ba = wb + (uint32_t)((16 * nh + 8 * u + g) * C::LD * 2 + (16 * ks + 2 * t) * 2);
-        ff_mma(acc[u], af[ks], ff_lds32(ba), ff_lds32(ba + 16));
-      }
+      uint32_t bf[4];
+      ff_ldsm4(wb + b_lane + (uint32_t)(32 * ks), bf);
+      ff_mma(acc[0], af[ks], bf[0], bf[1]);
+      ff_mma(acc[1], af[ks], bf[2], bf[3]);
     }
     if (p2) {  // q = acc + b1 -> bufB (bf16, like the q tensor of the unfused path), channels 32 i + 8 u + 2 t
 #pragma unroll
